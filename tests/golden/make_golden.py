@@ -1,0 +1,216 @@
+"""Generate the committed golden fixtures (tests/golden/*.npz) from the REAL reference.
+
+Run in the authoring container only (needs /root/reference and torchvision):
+    python tests/golden/make_golden.py
+
+Sources of truth used (never our own code):
+  * torchvision CPU ops  -- the reference's backend for roi_align / nms / deform_conv2d
+    (detectron2/layers/roi_align.py:3,58; nms.py:5-22; deform_conv.py:9,55)
+  * oracle/_ref/d2_ref_cpu.so -- the reference CPU csrc compiled in place (oracle/build.py):
+    torch.ops.detectron2.{roi_align_rotated_forward,roi_align_rotated_backward,box_iou_rotated,nms_rotated}
+  * /root/reference/detectron2/layers/mask_ops.py loaded as a stand-alone module
+    (paste_masks_in_image, pure torch)
+Inputs are seeded; both inputs and outputs are stored so the GPU box needs nothing but the .npz.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+import torchvision
+from torchvision.ops import boxes as tv_boxes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle as orc  # noqa: E402  (only for load_reference())
+
+assert orc.load_reference(), "reference CPU csrc must be built (python oracle/build.py)"
+D2 = torch.ops.detectron2
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+def rand_rois(g, k, n, wimg, himg, lo=2.0, hi=None):
+    hi = hi or min(wimg, himg) * 0.8
+    cx = torch.rand(k, generator=g) * wimg
+    cy = torch.rand(k, generator=g) * himg
+    w = lo + torch.rand(k, generator=g) * (hi - lo)
+    h = lo + torch.rand(k, generator=g) * (hi - lo)
+    b = torch.randint(0, n, (k,), generator=g).float()
+    rois = torch.stack([b, cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    return rois
+
+
+def gen_roi_align():
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 8, 24, 32, generator=g)
+    rois = rand_rois(g, 40, 2, 64, 48)  # image coords, spatial_scale 0.5
+    # edge cases: empty box (tests/layers/test_roi_align.py:111-121), box outside the map, huge box, tiny box
+    rois[0] = torch.tensor([0, 3.0, 4.0, 5.0, 4.0])
+    rois[1] = torch.tensor([1, -40.0, -30.0, -10.0, -5.0])
+    rois[2] = torch.tensor([0, -20.0, -20.0, 200.0, 150.0])
+    rois[3] = torch.tensor([1, 10.2, 10.3, 10.9, 11.0])
+    rois[4] = torch.tensor([1, 60.0, 40.0, 70.0, 55.0])
+    cfgs = [(7, 7, 0, True), (7, 7, 2, True), (5, 3, 0, False), (14, 14, 0, True), (2, 2, 3, False)]
+    out = {"x": x, "rois": rois, "cfgs": np.asarray([[a, b, c, int(d)] for a, b, c, d in cfgs])}
+    for i, (ph, pw, sr, al) in enumerate(cfgs):
+        xi = x.clone().requires_grad_(True)
+        y = torchvision.ops.roi_align(xi, rois, (ph, pw), 0.5, sr, al)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        out[f"y{i}"] = y
+        out[f"go{i}"] = go
+        out[f"gx{i}"] = xi.grad
+    save("roi_align", **out)
+
+
+def gen_roi_align_rotated():
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(2, 6, 20, 28, generator=g)
+    k = 36
+    cx = torch.rand(k, generator=g) * 56
+    cy = torch.rand(k, generator=g) * 40
+    w = 2 + torch.rand(k, generator=g) * 30
+    h = 2 + torch.rand(k, generator=g) * 30
+    a = (torch.rand(k, generator=g) - 0.5) * 360
+    b = torch.randint(0, 2, (k,), generator=g).float()
+    rois = torch.stack([b, cx, cy, w, h, a], 1)
+    rois[0] = torch.tensor([0, 2.0, 3.0, 0.0, 0.0, 0.0])  # empty (test_roi_align_rotated.py:102-105)
+    rois[1] = torch.tensor([1, 28.0, 20.0, 12.0, 8.0, 90.0])
+    rois[2] = torch.tensor([1, -30.0, -30.0, 10.0, 10.0, 33.0])  # outside
+    cfgs = [(7, 7, 0), (5, 5, 2), (3, 4, 1)]
+    out = {"x": x, "rois": rois, "cfgs": np.asarray(cfgs)}
+    for i, (ph, pw, sr) in enumerate(cfgs):
+        y = D2.roi_align_rotated_forward(x, rois, 0.5, ph, pw, sr)
+        go = torch.randn(y.shape, generator=g)
+        gx = D2.roi_align_rotated_backward(go, rois, 0.5, ph, pw, 2, 6, 20, 28, sr)
+        out[f"y{i}"] = y
+        out[f"go{i}"] = go
+        out[f"gx{i}"] = gx
+    save("roi_align_rotated", **out)
+
+
+def random_boxes(g, n, size):  # after detectron2/utils/testing.py:42-53
+    b = torch.rand(n, 4, generator=g) * (size * 0.5)
+    b[:, 2:] += size * 0.5
+    return b
+
+
+def gen_nms():
+    g = torch.Generator().manual_seed(99)
+    m = 700
+    boxes = random_boxes(g, m, 300)
+    # clusters of near-duplicates so that many IoUs sit near the thresholds
+    boxes[100:200] = boxes[:100] + torch.randn(100, 4, generator=g) * 3
+    boxes[200:230] = boxes[:30]  # exact duplicates
+    scores = torch.rand(m, generator=g)
+    scores[300:340] = scores[260:300]  # score ties
+    idxs = torch.randint(0, 6, (m,), generator=g)
+    out = {"boxes": boxes, "scores": scores, "idxs": idxs, "thr": np.asarray([0.2, 0.3, 0.5, 0.7, 0.8])}
+    for i, t in enumerate([0.2, 0.3, 0.5, 0.7, 0.8]):
+        out[f"keep{i}"] = torchvision.ops.nms(boxes, scores, t)
+        out[f"bkeep_trick{i}"] = tv_boxes._batched_nms_coordinate_trick(boxes, scores, idxs, t)
+        out[f"bkeep_vanilla{i}"] = tv_boxes._batched_nms_vanilla(boxes, scores, idxs, t)
+    save("nms", **out)
+
+
+def rand_rotated(g, n, size, wmax):
+    cx = torch.rand(n, generator=g) * size
+    cy = torch.rand(n, generator=g) * size
+    w = 1 + torch.rand(n, generator=g) * wmax
+    h = 1 + torch.rand(n, generator=g) * wmax
+    a = (torch.rand(n, generator=g) - 0.5) * 360
+    return torch.stack([cx, cy, w, h, a], 1)
+
+
+def gen_rotated_iou_nms():
+    g = torch.Generator().manual_seed(7)
+    b1 = rand_rotated(g, 90, 100, 60)
+    b2 = rand_rotated(g, 110, 100, 60)
+    # structured cases: identical, same-centre different angle, axis-aligned neighbours, zero-area
+    b2[:10] = b1[:10]
+    b2[10:20, :4] = b1[10:20, :4]
+    b1[20:30, 4] = 0
+    b2[20:30, 4] = 90
+    b1[30, 2] = 0.0
+    b2[31] = torch.tensor([50.0, 50.0, 1e-8, 1e-8, 10.0])
+    ious = D2.box_iou_rotated(b1, b2)
+    dets = rand_rotated(g, 400, 120, 50)
+    dets[100:180] = dets[:80] + torch.randn(80, 5, generator=g) * torch.tensor([2.0, 2.0, 2.0, 2.0, 5.0])
+    dets[:, 2:4].clamp_(min=0.5)
+    # no exact score ties here: the reference sorts with a non-stable `scores.sort(0, descending=True)`
+    # (nms_rotated_cpu.cpp:26), so the order of tied scores is implementation-defined (probed: AVX sort
+    # returns ties in reverse index order).  Tie behaviour is pinned separately as "stable, lower index first".
+    scores = torch.rand(400, generator=g)
+    idxs = torch.randint(0, 4, (400,), generator=g)
+    out = {"b1": b1, "b2": b2, "ious": ious, "dets": dets, "scores": scores, "idxs": idxs,
+           "thr": np.asarray([0.1, 0.3, 0.5, 0.7])}
+    for i, t in enumerate([0.1, 0.3, 0.5, 0.7]):
+        out[f"keep{i}"] = D2.nms_rotated(dets, scores, t)
+    save("rotated", **out)
+
+
+def gen_deform_conv():
+    g = torch.Generator().manual_seed(2024)
+    cases = [
+        # n, cin, h, w, cout, k, stride, pad, dil, groups, dg, modulated, bias
+        (2, 8, 10, 12, 8, 3, 1, 1, 1, 1, 1, False, False),
+        (2, 8, 10, 12, 12, 3, 2, 1, 1, 2, 2, True, True),
+        (1, 4, 9, 7, 6, 3, 1, 2, 2, 1, 1, True, False),
+        (1, 6, 2, 2, 6, 3, 1, 1, 1, 3, 1, False, False),  # input smaller than kernel (test_deformable.py:112-133)
+    ]
+    out = {"cases": np.asarray([[int(v) for v in c] for c in cases])}
+    for i, (n, cin, h, w, cout, k, s, p, d, grp, dg, mod, hb) in enumerate(cases):
+        ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+        wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+        x = torch.randn(n, cin, h, w, generator=g, requires_grad=True)
+        off = (torch.randn(n, 2 * dg * k * k, ho, wo, generator=g) * 1.5).requires_grad_(True)
+        mask = torch.sigmoid(torch.randn(n, dg * k * k, ho, wo, generator=g)).requires_grad_(True) if mod else None
+        wt = (torch.randn(cout, cin // grp, k, k, generator=g) * 0.2).requires_grad_(True)
+        bias = torch.randn(cout, generator=g).requires_grad_(True) if hb else None
+        y = torchvision.ops.deform_conv2d(x, off, wt, bias, stride=s, padding=p, dilation=d, mask=mask)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        out.update({f"x{i}": x, f"off{i}": off, f"w{i}": wt, f"y{i}": y, f"go{i}": go,
+                    f"gx{i}": x.grad, f"goff{i}": off.grad, f"gw{i}": wt.grad})
+        if mod:
+            out.update({f"mask{i}": mask, f"gmask{i}": mask.grad})
+        if hb:
+            out.update({f"bias{i}": bias, f"gbias{i}": bias.grad})
+    save("deform_conv", **out)
+
+
+def gen_paste_masks():
+    spec = importlib.util.spec_from_file_location("ref_mask_ops", "/root/reference/detectron2/layers/mask_ops.py")
+    mo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mo)
+    g = torch.Generator().manual_seed(42)
+    n, m, h, w = 9, 28, 61, 83
+    masks = torch.rand(n, m, m, generator=g)
+    boxes = random_boxes(g, n, 60)
+    boxes[0] = torch.tensor([-5.0, -7.5, 30.2, 20.1])  # partly outside
+    boxes[1] = torch.tensor([10.0, 10.0, 10.0, 30.0])  # degenerate width (x1 == x0)
+    boxes[2] = torch.tensor([70.0, 50.0, 120.0, 90.0])  # crosses the border
+    boxes[3] = torch.tensor([20.3, 20.7, 21.1, 21.9])  # sub-pixel box
+    out_bool = mo.paste_masks_in_image(masks, boxes, (h, w), threshold=0.5)
+    out_u8 = mo.paste_masks_in_image(masks, boxes, (h, w), threshold=-1)
+    soft, _ = mo._do_paste_mask(masks[:, None], boxes, h, w, skip_empty=False)
+    save("paste_masks", masks=masks, boxes=boxes, hw=np.asarray([h, w]), out_bool=out_bool, out_u8=out_u8, soft=soft)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    gen_roi_align()
+    gen_roi_align_rotated()
+    gen_nms()
+    gen_rotated_iou_nms()
+    gen_deform_conv()
+    gen_paste_masks()
