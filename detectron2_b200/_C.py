@@ -1,0 +1,104 @@
+"""ctypes binding of libd2b200.so -- the C-ABI drop-in boundary declared in include/d2b200.h.
+
+This module plays the role of ``detectron2._C`` (csrc/vision.cpp:81-113) for the hot path: it is the only place
+where the Python host touches native code.  There is NO CPU fallback: if the library is missing or a tensor is not
+on a CUDA device the call raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd2b200.so")
+
+_lib = None
+
+D2B_ERRORS = {-1: "invalid argument", -2: "workspace too small", -3: "unsupported configuration"}
+
+
+class DcnParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("N", "Cin", "H", "W", "Cout", "kh", "kw", "stride_h", "stride_w", "pad_h",
+                                        "pad_w", "dil_h", "dil_w", "groups", "deformable_groups")]
+
+
+def _declare(lib):
+    vp, f32p, i64p, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    i, f, d, sz, i64 = C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_int64
+    sig = {
+        "d2b_abi_version": (i, []),
+        "d2b_cuda_version": (i, []),
+        "d2b_arch": (C.c_char_p, []),
+        "d2b_roi_align_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, i, f32p, vp]),
+        "d2b_roi_align_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, i, f32p, vp]),
+        "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
+        "d2b_roi_align_rotated_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
+        "d2b_nms_workspace_bytes": (sz, [i64, i]),
+        "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64p, i64p, vp, sz, vp]),
+        "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
+        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, f32p, vp]),
+        "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams)]),
+        "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), f32p, f32p, f32p, f32p,
+                                         f32p, vp, sz, vp]),
+        "d2b_paste_masks": (i, [f32p, f32p, i, i, i, i, f, u8p, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == symbol missing from the .so
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTED = None
+
+
+def lib():
+    """Load (once) and return the native library.  Raises if it cannot be loaded -- never falls back."""
+    global _lib, EXPORTED
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "detectron2_b200: native library %s is missing. Build it with `python -m detectron2_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for these ops." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        EXPORTED = _declare(l)
+        if l.d2b_abi_version() != 1:
+            raise RuntimeError("libd2b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError("%s: %s (d2b error %d)" % (what, D2B_ERRORS.get(rc, "error"), rc))
+    raise RuntimeError("%s: CUDA error %d" % (what, rc))
+
+
+def stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError("detectron2_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# --- detectron2._C-shaped helpers (csrc/vision.cpp:86-88) -----------------------------------------
+def get_cuda_version():
+    v = lib().d2b_cuda_version()
+    return "CUDA %d.%d" % (v // 1000, (v % 1000) // 10)
+
+
+def has_cuda():
+    return True
+
+
+def get_compiler_version():
+    return "nvcc (sm_100a)"

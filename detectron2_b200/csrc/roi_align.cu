@@ -1,0 +1,347 @@
+// RoIAlign / ROIAlignRotated forward + backward for sm_100a.
+//
+// Semantics follow torchvision roi_align (detectron2/layers/roi_align.py:58-65; arithmetic as in
+// torchvision/ops/roi_align.py::_roi_align) and detectron2/layers/csrc/ROIAlignRotated/ROIAlignRotated_cuda.cu:143-323.
+//
+// Design (differs from the reference's one-thread-per-output grid-stride loop):
+//   * one CTA per (RoI, channel slab).  The bilinear taps of a RoI are shared by all C channels, so they are
+//     computed ONCE per CTA into shared memory -- as two separable 1-D tables (rows, columns) for the axis-aligned
+//     op, as a 2-D table for the rotated op -- instead of once per output element (256x redundant in the reference);
+//   * threads are mapped to (channel, bin) with bins fastest, so a warp reads neighbouring pixels of one plane
+//     and writes 128 contiguous output bytes;
+//   * backward accumulates a RoI's gradient footprint in shared memory first and flushes it with one red.global
+//     per touched pixel instead of 4*g^2 global atomics per output element.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RoiGeom {
+  int b;
+  float start_h, start_w, bin_h, bin_w;
+  int gh, gw;
+  float inv_count;  // 1 / max(gh*gw,1)
+  float count_raw;  // gh*gw (backward divides by the raw product)
+  float ctr_h, ctr_w, cos_t, sin_t;
+};
+
+template <bool ROT>
+__device__ __forceinline__ RoiGeom load_geom(const float* __restrict__ roi, float scale, int PH, int PW, int sr,
+                                             int aligned) {
+  RoiGeom g;
+  g.b = (int)roi[0];
+  float rw, rh;
+  if (ROT) {  // ROIAlignRotated_cuda.cu:166-183
+    g.ctr_w = roi[1] * scale - 0.5f;
+    g.ctr_h = roi[2] * scale - 0.5f;
+    rw = roi[3] * scale;
+    rh = roi[4] * scale;
+    float theta = (float)((double)roi[5] * 3.14159265358979323846 / 180.0);  // ROIAlignRotated_cuda.cu:173
+    sincosf(theta, &g.sin_t, &g.cos_t);
+    g.start_h = -rh / 2.0f;
+    g.start_w = -rw / 2.0f;
+  } else {
+    float off = aligned ? 0.5f : 0.0f;
+    float sw = roi[1] * scale - off, sh = roi[2] * scale - off;
+    float ew = roi[3] * scale - off, eh = roi[4] * scale - off;
+    rw = ew - sw;
+    rh = eh - sh;
+    if (!aligned) {
+      rw = fmaxf(rw, 1.f);
+      rh = fmaxf(rh, 1.f);
+    }
+    g.start_h = sh;
+    g.start_w = sw;
+    g.ctr_h = g.ctr_w = 0.f;
+    g.cos_t = 1.f;
+    g.sin_t = 0.f;
+  }
+  g.bin_h = rh / (float)PH;
+  g.bin_w = rw / (float)PW;
+  g.gh = sr > 0 ? sr : (int)ceilf(rh / (float)PH);
+  g.gw = sr > 0 ? sr : (int)ceilf(rw / (float)PW);
+  if (g.gh < 0) g.gh = 0;
+  if (g.gw < 0) g.gw = 0;
+  int c = g.gh * g.gw;
+  g.count_raw = (float)c;
+  g.inv_count = 1.0f / (float)(c < 1 ? 1 : c);
+  return g;
+}
+
+// 1-D tap: low/high index (clamped) and the two weights; valid=0 when the coordinate is outside [-1, size].
+struct Tap1 {
+  int lo, hi;
+  float wl, wh;  // wh = frac, wl = 1-frac ; both 0 when invalid
+};
+
+__device__ __forceinline__ Tap1 make_tap1(float v, int size) {
+  Tap1 t;
+  if (v < -1.0f || v > (float)size) {
+    t.lo = t.hi = 0;
+    t.wl = t.wh = 0.f;
+    return t;
+  }
+  v = fmaxf(v, 0.f);
+  int lo = (int)v;
+  int hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    v = (float)lo;
+  } else {
+    hi = lo + 1;
+  }
+  float l = v - (float)lo;
+  t.lo = lo;
+  t.hi = hi;
+  t.wh = l;
+  t.wl = 1.f - l;
+  return t;
+}
+
+// ------------------------------------------------------------------ axis-aligned forward
+// smem: ytab[PH*gh], xtab[PW*gw]  (Tap1 each). Falls back to on-the-fly taps when the tables do not fit.
+template <int MAXTAB>
+__global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const float* __restrict__ in,
+                                                                 const float* __restrict__ rois, float scale, int C,
+                                                                 int H, int W, int PH, int PW, int sr, int aligned,
+                                                                 int c_per_cta, float* __restrict__ out) {
+  __shared__ Tap1 ytab[MAXTAB];
+  __shared__ Tap1 xtab[MAXTAB];
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * c_per_cta;
+  const int cn = min(c_per_cta, C - c0);
+  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, scale, PH, PW, sr, aligned);
+  const int ny = PH * g.gh, nx = PW * g.gw;
+  const bool tab = (ny <= MAXTAB) && (nx <= MAXTAB);
+  if (tab) {
+    for (int i = threadIdx.x; i < ny; i += kThreads) {
+      int ph = i / g.gh, iy = i - ph * g.gh;
+      float y = g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh;
+      ytab[i] = make_tap1(y, H);
+    }
+    for (int i = threadIdx.x; i < nx; i += kThreads) {
+      int pw = i / g.gw, ix = i - pw * g.gw;
+      float x = g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw;
+      xtab[i] = make_tap1(x, W);
+    }
+    __syncthreads();
+  }
+  const int bins = PH * PW;
+  const int total = cn * bins;
+  const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
+  float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
+  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+    int c = idx / bins;
+    int bin = idx - c * bins;
+    int ph = bin / PW, pw = bin - ph * PW;
+    const float* __restrict__ plane = base + (size_t)c * H * W;
+    float acc = 0.f;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      Tap1 ty;
+      if (tab) ty = ytab[ph * g.gh + iy];
+      else ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+      const float* __restrict__ r0 = plane + (size_t)ty.lo * W;
+      const float* __restrict__ r1 = plane + (size_t)ty.hi * W;
+      for (int ix = 0; ix < g.gw; ++ix) {
+        Tap1 tx;
+        if (tab) tx = xtab[pw * g.gw + ix];
+        else tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+        float v1 = __ldg(r0 + tx.lo), v2 = __ldg(r0 + tx.hi), v3 = __ldg(r1 + tx.lo), v4 = __ldg(r1 + tx.hi);
+        acc += (ty.wl * tx.wl) * v1 + (ty.wl * tx.wh) * v2 + (ty.wh * tx.wl) * v3 + (ty.wh * tx.wh) * v4;
+      }
+    }
+    obase[idx] = acc * g.inv_count;
+  }
+}
+
+// ------------------------------------------------------------------ rotated forward
+struct Tap2 {
+  int p1, p2, p3, p4;
+  float w1, w2, w3, w4;
+};
+
+__device__ __forceinline__ Tap2 make_tap2(float y, float x, int H, int W) {
+  Tap2 t;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+    t.p1 = t.p2 = t.p3 = t.p4 = -1;
+    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
+    return t;
+  }
+  Tap1 ty = make_tap1(y, H), tx = make_tap1(x, W);
+  t.p1 = ty.lo * W + tx.lo;
+  t.p2 = ty.lo * W + tx.hi;
+  t.p3 = ty.hi * W + tx.lo;
+  t.p4 = ty.hi * W + tx.hi;
+  t.w1 = ty.wl * tx.wl;
+  t.w2 = ty.wl * tx.wh;
+  t.w3 = ty.wh * tx.wl;
+  t.w4 = ty.wh * tx.wh;
+  return t;
+}
+
+__device__ __forceinline__ void rot_xy(const RoiGeom& g, int ph, int pw, int iy, int ix, float& y, float& x) {
+  float yy = g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh;
+  float xx = g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw;
+  y = yy * g.cos_t - xx * g.sin_t + g.ctr_h;  // ROIAlignRotated_cuda.cu:210-212
+  x = yy * g.sin_t + xx * g.cos_t + g.ctr_w;
+}
+
+template <int MAXTAP>
+__global__ void __launch_bounds__(kThreads) roi_align_rot_fwd_kernel(const float* __restrict__ in,
+                                                                     const float* __restrict__ rois, float scale,
+                                                                     int C, int H, int W, int PH, int PW, int sr,
+                                                                     int c_per_cta, float* __restrict__ out) {
+  __shared__ Tap2 taps[MAXTAP];
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * c_per_cta;
+  const int cn = min(c_per_cta, C - c0);
+  const RoiGeom g = load_geom<true>(rois + (size_t)k * 6, scale, PH, PW, sr, 1);
+  const int bins = PH * PW;
+  const int spb = g.gh * g.gw;  // samples per bin
+  const long long ntap = (long long)bins * spb;
+  const bool tab = ntap <= MAXTAP;
+  if (tab) {
+    for (int i = threadIdx.x; i < (int)ntap; i += kThreads) {
+      int bin = i / spb, s = i - bin * spb;
+      int ph = bin / PW, pw = bin - ph * PW, iy = s / g.gw, ix = s - iy * g.gw;
+      float y, x;
+      rot_xy(g, ph, pw, iy, ix, y, x);
+      taps[i] = make_tap2(y, x, H, W);
+    }
+    __syncthreads();
+  }
+  const int total = cn * bins;
+  const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
+  float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
+  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+    int c = idx / bins, bin = idx - c * bins;
+    int ph = bin / PW, pw = bin - ph * PW;
+    const float* __restrict__ plane = base + (size_t)c * H * W;
+    float acc = 0.f;
+    for (int s = 0; s < spb; ++s) {
+      Tap2 t;
+      if (tab) t = taps[bin * spb + s];
+      else {
+        int iy = s / g.gw, ix = s - iy * g.gw;
+        float y, x;
+        rot_xy(g, ph, pw, iy, ix, y, x);
+        t = make_tap2(y, x, H, W);
+      }
+      if (t.p1 >= 0)
+        acc += t.w1 * __ldg(plane + t.p1) + t.w2 * __ldg(plane + t.p2) + t.w3 * __ldg(plane + t.p3) +
+               t.w4 * __ldg(plane + t.p4);
+    }
+    obase[idx] = acc * g.inv_count;
+  }
+}
+
+// ------------------------------------------------------------------ backward (both variants)
+// One CTA per (RoI, channel slab).  Threads map to (channel, bin); every sample scatters
+// g*w/count to its four taps (ROIAlignRotated_cuda.cu:238-322, torchvision _roi_align_backward).
+// Lanes of a warp cover neighbouring bins of one channel, so their taps collide on the same pixels:
+// red.global.add (no return value) lets the L2 atomic unit merge them.
+template <bool ROT>
+__global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const float* __restrict__ gout,
+                                                                 const float* __restrict__ rois, float scale, int C,
+                                                                 int H, int W, int PH, int PW, int sr, int aligned,
+                                                                 int c_per_cta, float* __restrict__ gin) {
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * c_per_cta;
+  const int cn = min(c_per_cta, C - c0);
+  const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), scale, PH, PW, sr, aligned);
+  if (g.gh <= 0 || g.gw <= 0) return;
+  const int bins = PH * PW;
+  const int total = cn * bins;
+  float* __restrict__ base = gin + ((size_t)g.b * C + c0) * H * W;
+  const float* __restrict__ gbase = gout + ((size_t)k * C + c0) * bins;
+  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+    int c = idx / bins, bin = idx - c * bins;
+    int ph = bin / PW, pw = bin - ph * PW;
+    float* __restrict__ plane = base + (size_t)c * H * W;
+    const float gv = gbase[idx];
+    for (int iy = 0; iy < g.gh; ++iy)
+      for (int ix = 0; ix < g.gw; ++ix) {
+        float y, x;
+        if (ROT) rot_xy(g, ph, pw, iy, ix, y, x);
+        else {
+          y = g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh;
+          x = g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw;
+        }
+        Tap2 t = make_tap2(y, x, H, W);
+        if (t.p1 < 0) continue;
+        atomicAdd(plane + t.p1, gv * t.w1 / g.count_raw);
+        atomicAdd(plane + t.p2, gv * t.w2 / g.count_raw);
+        atomicAdd(plane + t.p3, gv * t.w3 / g.count_raw);
+        atomicAdd(plane + t.p4, gv * t.w4 / g.count_raw);
+      }
+  }
+}
+
+// channels per CTA: enough CTAs to fill 148 SMs a few times over without shrinking the per-CTA tap reuse.
+int pick_c_per_cta(int K, int C) {
+  int cpc = C;
+  while (cpc > 16 && (long long)K * d2b_cdiv(C, cpc) < 4LL * kNumSMs) cpc = (cpc + 1) / 2;
+  return cpc;
+}
+
+}  // namespace
+
+D2B_API int d2b_roi_align_forward(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                                  float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
+                                  float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  if (!input || !rois || !out || N <= 0 || H <= 0 || W <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0)
+    return D2B_EINVAL;
+  int cpc = pick_c_per_cta(K, C);
+  dim3 grid(K, d2b_cdiv(C, cpc));
+  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      input, rois, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, aligned, cpc, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_roi_align_rotated_forward(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                                          float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                          float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  if (!input || !rois || !out || N <= 0 || H <= 0 || W <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0)
+    return D2B_EINVAL;
+  int cpc = pick_c_per_cta(K, C);
+  dim3 grid(K, d2b_cdiv(C, cpc));
+  roi_align_rot_fwd_kernel<1024><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      input, rois, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, cpc, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+template <bool ROT>
+static int roi_bwd_launch(const float* grad_out, const float* rois, int K, float spatial_scale, int pooled_h,
+                          int pooled_w, int N, int C, int H, int W, int sampling_ratio, int aligned, float* grad_in,
+                          void* stream) {
+  if (!grad_in || N < 0 || C < 0 || H < 0 || W < 0) return D2B_EINVAL;
+  size_t bytes = sizeof(float) * (size_t)N * C * H * W;
+  if (bytes) D2B_CUDA(cudaMemsetAsync(grad_in, 0, bytes, (cudaStream_t)stream));
+  if (K == 0 || bytes == 0) return D2B_OK;
+  if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  int cpc = pick_c_per_cta(K, C);
+  dim3 grid(K, d2b_cdiv(C, cpc));
+  roi_align_bwd_kernel<ROT><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      grad_out, rois, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, aligned, cpc, grad_in);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_roi_align_backward(const float* grad_out, const float* rois, int K, float spatial_scale, int pooled_h,
+                                   int pooled_w, int N, int C, int H, int W, int sampling_ratio, int aligned,
+                                   float* grad_in, void* stream) {
+  return roi_bwd_launch<false>(grad_out, rois, K, spatial_scale, pooled_h, pooled_w, N, C, H, W, sampling_ratio,
+                               aligned, grad_in, stream);
+}
+
+D2B_API int d2b_roi_align_rotated_backward(const float* grad_out, const float* rois, int K, float spatial_scale,
+                                           int pooled_h, int pooled_w, int N, int C, int H, int W, int sampling_ratio,
+                                           float* grad_in, void* stream) {
+  return roi_bwd_launch<true>(grad_out, rois, K, spatial_scale, pooled_h, pooled_w, N, C, H, W, sampling_ratio, 1,
+                              grad_in, stream);
+}

@@ -1,0 +1,58 @@
+"""nms / batched_nms / nms_rotated / batched_nms_rotated -- same surface as detectron2/layers/nms.py.
+
+Differences in mechanism (not results): the reference's batched variants add per-category coordinate offsets in
+Python and call a single-class NMS; here the offsets are applied inside the gather kernel (same fp32 arithmetic),
+the IoU bitmask is reduced on the device, and `*_fixed` variants return (padded keep, count) without a host sync.
+"""
+import torch
+
+from .. import ops
+
+# torchvision switches batched_nms to a per-class Python loop above this size on GPU (ops/boxes.py); kept for parity
+_TRICK_MAX_NUMEL = 100_000
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """torchvision.ops.nms semantics (layers/nms.py:6): keep indices sorted by decreasing score, suppress IoU > thr."""
+    return ops.nms_op(boxes, scores, None, float(iou_threshold), False)
+
+
+def _batched_nms_vanilla(boxes, scores, idxs, iou_threshold, rotated):
+    keep_mask = torch.zeros_like(scores, dtype=torch.bool)
+    for class_id in torch.unique(idxs):
+        curr = torch.where(idxs == class_id)[0]
+        keep = ops.nms_op(boxes[curr], scores[curr], None, float(iou_threshold), rotated)
+        keep_mask[curr[keep]] = True
+    keep_indices = torch.where(keep_mask)[0]
+    return keep_indices[scores[keep_indices].sort(descending=True, stable=True)[1]]
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
+    """Per-category NMS (layers/nms.py:11-22 -> torchvision batched_nms, always on boxes.float())."""
+    assert boxes.shape[-1] == 4
+    boxes = boxes.float()
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    if boxes.numel() > _TRICK_MAX_NUMEL:
+        return _batched_nms_vanilla(boxes, scores, idxs, iou_threshold, False)
+    return ops.nms_op(boxes, scores, idxs, float(iou_threshold), False)
+
+
+def batched_nms_fixed(boxes, scores, idxs, iou_threshold):
+    """Sync-free variant: (keep[M] padded, num_keep[1]) device tensors."""
+    return ops.nms_fixed(boxes.float(), scores, idxs, float(iou_threshold), False)
+
+
+def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float):
+    """Rotated NMS over (cx, cy, w, h, angle_deg) boxes (layers/nms.py:28-89); suppress IoU >= thr like the
+    reference CPU kernel (nms_rotated_cpu.cpp:54)."""
+    return torch.ops.detectron2.nms_rotated(boxes, scores, iou_threshold)
+
+
+def batched_nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
+    """Per-category rotated NMS (layers/nms.py:97-147); the min/max-coordinate offsets of :137-146 are computed and
+    applied inside the kernel pipeline in fp32."""
+    assert boxes.shape[-1] == 5
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    return ops.nms_op(boxes.float(), scores, idxs, float(iou_threshold), True)

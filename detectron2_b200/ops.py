@@ -1,0 +1,382 @@
+"""torch custom-op registration over the C ABI (libd2b200.so).
+
+Two op namespaces are served:
+  * ``d2b200::*``      -- our own ops (autograd + fake/meta kernels, so they trace and compile);
+  * ``detectron2::*``  -- the four dispatcher ops the reference registers in csrc/vision.cpp:115-120
+    (nms_rotated, box_iou_rotated, roi_align_rotated_forward, roi_align_rotated_backward) with the same
+    schemas, so reference call sites ``torch.ops.detectron2.*`` (layers/roi_align_rotated.py:20,33,89,
+    layers/nms.py:89, layers/rotated_boxes.py:21) run unchanged on CUDA tensors.  If the reference's own
+    library already defined them (e.g. the CPU oracle build is loaded) only a CUDA kernel is added.
+
+PyTorch is plumbing here: allocation, streams, autograd graph.  All arithmetic happens in the hand-written kernels.
+"""
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _C
+from ._C import check, ptr, stream_ptr
+
+Tensor = torch.Tensor
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    return t.to(dtype=torch.float32).contiguous()
+
+
+# =================================================================================== RoIAlign
+def _roi_common(input: Tensor, rois: Tensor, cols: int):
+    _C.require_cuda(input, rois)
+    if input.dim() != 4:
+        raise RuntimeError("roi_align: input must be NCHW")
+    if rois.dim() != 2 or rois.size(1) != cols:
+        raise RuntimeError("roi_align: rois must be K x %d" % cols)
+
+
+@torch.library.custom_op("d2b200::roi_align", mutates_args=(), device_types="cuda")
+def roi_align_op(input: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
+                 sampling_ratio: int, aligned: bool) -> Tensor:
+    _roi_common(input, rois, 5)
+    x, r = _f32c(input), _f32c(rois)
+    n, c, h, w = x.shape
+    k = r.shape[0]
+    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(_C.lib().d2b_roi_align_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h, pooled_w,
+                                                 sampling_ratio, int(aligned), ptr(out), stream_ptr(x.device)),
+                  "roi_align_forward")
+    return out.to(input.dtype)
+
+
+@roi_align_op.register_fake
+def _(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned):
+    return input.new_empty((rois.shape[0], input.shape[1], pooled_h, pooled_w))
+
+
+@torch.library.custom_op("d2b200::roi_align_backward", mutates_args=(), device_types="cuda")
+def roi_align_backward_op(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int, n: int,
+                          c: int, h: int, w: int, sampling_ratio: int, aligned: bool) -> Tensor:
+    _C.require_cuda(grad, rois)
+    g, r = _f32c(grad), _f32c(rois)
+    gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(_C.lib().d2b_roi_align_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w, n, c, h,
+                                              w, sampling_ratio, int(aligned), ptr(gin), stream_ptr(g.device)),
+              "roi_align_backward")
+    return gin.to(grad.dtype)
+
+
+@roi_align_backward_op.register_fake
+def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio, aligned):
+    return grad.new_empty((n, c, h, w))
+
+
+def _roi_align_setup(ctx, inputs, output):
+    input, rois, spatial_scale, ph, pw, sr, aligned = inputs
+    ctx.save_for_backward(rois)
+    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr, aligned)
+
+
+def _roi_align_bwd(ctx, grad):
+    (rois,) = ctx.saved_tensors
+    scale, ph, pw, (n, c, h, w), sr, aligned = ctx.args
+    gin = roi_align_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    return gin, None, None, None, None, None, None
+
+
+roi_align_op.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
+
+
+@torch.library.custom_op("d2b200::roi_align_rotated", mutates_args=(), device_types="cuda")
+def roi_align_rotated_op(input: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
+                         sampling_ratio: int) -> Tensor:
+    _roi_common(input, rois, 6)
+    x, r = _f32c(input), _f32c(rois)
+    n, c, h, w = x.shape
+    k = r.shape[0]
+    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(_C.lib().d2b_roi_align_rotated_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h,
+                                                         pooled_w, sampling_ratio, ptr(out), stream_ptr(x.device)),
+                  "roi_align_rotated_forward")
+    return out.to(input.dtype)
+
+
+@roi_align_rotated_op.register_fake
+def _(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+    return input.new_empty((rois.shape[0], input.shape[1], pooled_h, pooled_w))
+
+
+@torch.library.custom_op("d2b200::roi_align_rotated_backward", mutates_args=(), device_types="cuda")
+def roi_align_rotated_backward_op(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
+                                  n: int, c: int, h: int, w: int, sampling_ratio: int) -> Tensor:
+    _C.require_cuda(grad, rois)
+    g, r = _f32c(grad), _f32c(rois)
+    gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(_C.lib().d2b_roi_align_rotated_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w,
+                                                      n, c, h, w, sampling_ratio, ptr(gin), stream_ptr(g.device)),
+              "roi_align_rotated_backward")
+    return gin.to(grad.dtype)
+
+
+@roi_align_rotated_backward_op.register_fake
+def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio):
+    return grad.new_empty((n, c, h, w))
+
+
+def _roi_rot_setup(ctx, inputs, output):
+    input, rois, spatial_scale, ph, pw, sr = inputs
+    ctx.save_for_backward(rois)
+    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr)
+
+
+def _roi_rot_bwd(ctx, grad):
+    (rois,) = ctx.saved_tensors
+    scale, ph, pw, (n, c, h, w), sr = ctx.args
+    return roi_align_rotated_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr), None, None, None, None, None
+
+
+roi_align_rotated_op.register_autograd(_roi_rot_bwd, setup_context=_roi_rot_setup)
+
+
+# =================================================================================== NMS / rotated IoU
+def nms_fixed(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,
+              rotated: bool) -> Tuple[Tensor, Tensor]:
+    """Sync-free NMS: returns (keep[M] int64 padded buffer, num_keep[1] int64 device tensor).
+    keep[:num_keep] are the kept original indices in descending-score order.  CUDA-graph friendly."""
+    _C.require_cuda(boxes, scores, idxs)
+    b, s = _f32c(boxes), _f32c(scores)
+    ix = None if idxs is None else idxs.to(dtype=torch.int64).contiguous()
+    m = b.shape[0]
+    keep = torch.empty((m,), dtype=torch.int64, device=b.device)
+    num = torch.zeros((1,), dtype=torch.int64, device=b.device)
+    if m:
+        ws_bytes = _C.lib().d2b_nms_workspace_bytes(m, int(rotated))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=b.device)
+        with torch.cuda.device(b.device):
+            check(_C.lib().d2b_nms(ptr(b), ptr(s), ptr(ix), m, float(iou_threshold), int(rotated), ptr(keep),
+                                   ptr(num), ptr(ws), ws_bytes, stream_ptr(b.device)), "nms")
+    return keep, num
+
+
+@torch.library.custom_op("d2b200::nms", mutates_args=(), device_types="cuda")
+def nms_op(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float, rotated: bool) -> Tensor:
+    keep, num = nms_fixed(boxes, scores, idxs, iou_threshold, rotated)
+    n = int(num.item())  # the one host sync: the reference contract returns an exactly-sized tensor
+    return keep[:n].clone()
+
+
+@nms_op.register_fake
+def _(boxes, scores, idxs, iou_threshold, rotated):
+    ctx = torch.library.get_ctx()
+    n = ctx.new_dynamic_size()
+    return boxes.new_empty((n,), dtype=torch.int64)
+
+
+@torch.library.custom_op("d2b200::box_iou_rotated", mutates_args=(), device_types="cuda")
+def box_iou_rotated_op(boxes1: Tensor, boxes2: Tensor) -> Tensor:
+    _C.require_cuda(boxes1, boxes2)
+    b1, b2 = _f32c(boxes1), _f32c(boxes2)
+    n, m = b1.shape[0], b2.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=b1.device)
+    if n and m:
+        with torch.cuda.device(b1.device):
+            check(_C.lib().d2b_box_iou_rotated(ptr(b1), n, ptr(b2), m, ptr(out), stream_ptr(b1.device)),
+                  "box_iou_rotated")
+    return out
+
+
+@box_iou_rotated_op.register_fake
+def _(boxes1, boxes2):
+    return boxes1.new_empty((boxes1.shape[0], boxes2.shape[0]), dtype=torch.float32)
+
+
+# =================================================================================== deformable conv
+def _dcn_params(x, weight, stride, padding, dilation, groups, deformable_groups):
+    n, cin, h, w = x.shape
+    cout, _, kh, kw = weight.shape
+    return _C.DcnParams(n, cin, h, w, cout, kh, kw, stride[0], stride[1], padding[0], padding[1], dilation[0],
+                        dilation[1], groups, deformable_groups)
+
+
+def dcn_output_shape(x, weight, stride, padding, dilation):
+    n, _, h, w = x.shape
+    cout, _, kh, kw = weight.shape
+    ho = (h + 2 * padding[0] - (dilation[0] * (kh - 1) + 1)) // stride[0] + 1
+    wo = (w + 2 * padding[1] - (dilation[1] * (kw - 1) + 1)) // stride[1] + 1
+    return n, cout, ho, wo
+
+
+def _dcn_check(x, offset, mask, weight, stride, padding, dilation, groups, dg):
+    """Shape checks of deform_conv_cuda.cu:140-270 / :894-905 -> RuntimeError like TORCH_CHECK."""
+    if x.dim() != 4:
+        raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(x.dim()))
+    if weight.dim() != 4:
+        raise RuntimeError("deform_conv: weight must be 4D")
+    n, cout, ho, wo = dcn_output_shape(x, weight, stride, padding, dilation)
+    kh, kw = weight.shape[2:]
+    if ho < 1 or wo < 1:
+        raise RuntimeError("deform_conv: output size is too small")
+    if x.shape[1] != weight.shape[1] * groups:
+        raise RuntimeError("deform_conv: input channels and weight/groups do not match")
+    if tuple(offset.shape) != (n, 2 * dg * kh * kw, ho, wo):
+        raise RuntimeError("invalid spatial size or number of channels of offset: got %s, expected %s" %
+                           (tuple(offset.shape), (n, 2 * dg * kh * kw, ho, wo)))
+    if mask is not None and tuple(mask.shape) != (n, dg * kh * kw, ho, wo):
+        raise RuntimeError("invalid spatial size or number of channels of mask: got %s, expected %s" %
+                           (tuple(mask.shape), (n, dg * kh * kw, ho, wo)))
+
+
+@torch.library.custom_op("d2b200::deform_conv", mutates_args=(), device_types="cuda")
+def deform_conv_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
+                   stride: List[int], padding: List[int], dilation: List[int], groups: int, deformable_groups: int,
+                   precision: int) -> Tensor:
+    _C.require_cuda(x, offset, mask, weight, bias)
+    _dcn_check(x, offset, mask, weight, stride, padding, dilation, groups, deformable_groups)
+    xf, of, mf, wf, bf = _f32c(x), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(bias)
+    p = _dcn_params(xf, wf, stride, padding, dilation, groups, deformable_groups)
+    out = torch.empty(dcn_output_shape(xf, wf, stride, padding, dilation), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_C.lib().d2b_deform_conv_forward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision,
+                                               ptr(out), stream_ptr(x.device)), "deform_conv_forward")
+    return out.to(x.dtype)
+
+
+@deform_conv_op.register_fake
+def _(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups, precision):
+    return x.new_empty(dcn_output_shape(x, weight, stride, padding, dilation))
+
+
+@torch.library.custom_op("d2b200::deform_conv_backward", mutates_args=(), device_types="cuda")
+def deform_conv_backward_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, grad_out: Tensor,
+                            stride: List[int], padding: List[int], dilation: List[int], groups: int,
+                            deformable_groups: int, with_bias: bool, need_data: bool,
+                            need_weight: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _C.require_cuda(x, offset, mask, weight, grad_out)
+    xf, of, mf, wf, gf = _f32c(x), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(grad_out)
+    p = _dcn_params(xf, wf, stride, padding, dilation, groups, deformable_groups)
+    dev = x.device
+    e = lambda: torch.empty((0,), dtype=torch.float32, device=dev)  # noqa: E731
+    gx = torch.empty_like(xf) if need_data else e()
+    go = torch.empty_like(of) if need_data else e()
+    gm = torch.empty_like(mf) if (need_data and mf is not None) else e()
+    gw = torch.empty_like(wf) if need_weight else e()
+    gb = torch.empty((wf.shape[0],), dtype=torch.float32, device=dev) if (with_bias and need_weight) else e()
+    P = lambda t: ptr(t) if t.numel() else None  # noqa: E731
+    with torch.cuda.device(dev):
+        check(_C.lib().d2b_deform_conv_backward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(gf), C.byref(p), P(gx), P(go),
+                                                P(gm), P(gw), P(gb), None, 0, stream_ptr(dev)),
+              "deform_conv_backward")
+    return gx, go, gm, gw, gb
+
+
+@deform_conv_backward_op.register_fake
+def _(x, offset, mask, weight, grad_out, stride, padding, dilation, groups, deformable_groups, with_bias, need_data,
+      need_weight):
+    e = lambda: x.new_empty((0,))  # noqa: E731
+    return (torch.empty_like(x) if need_data else e(), torch.empty_like(offset) if need_data else e(),
+            torch.empty_like(mask) if (need_data and mask is not None) else e(),
+            torch.empty_like(weight) if need_weight else e(),
+            x.new_empty((weight.shape[0],)) if (with_bias and need_weight) else e())
+
+
+def _dcn_setup(ctx, inputs, output):
+    x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, precision = inputs
+    ctx.save_for_backward(x, offset, mask, weight)
+    ctx.args = (stride, padding, dilation, groups, dg, bias is not None)
+    ctx.has_mask = mask is not None
+
+
+def _dcn_bwd(ctx, grad):
+    x, offset, mask, weight = ctx.saved_tensors
+    stride, padding, dilation, groups, dg, with_bias = ctx.args
+    need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ctx.has_mask and ctx.needs_input_grad[2])
+    need_weight = ctx.needs_input_grad[3] or (with_bias and ctx.needs_input_grad[4])
+    gx, go, gm, gw, gb = deform_conv_backward_op(x, offset, mask, weight, grad, stride, padding, dilation, groups, dg,
+                                                 with_bias, need_data, need_weight)
+    return (gx.to(x.dtype) if need_data else None, go.to(offset.dtype) if need_data else None,
+            gm.to(mask.dtype) if (need_data and ctx.has_mask) else None,
+            gw.to(weight.dtype) if need_weight else None, gb if (with_bias and need_weight) else None,
+            None, None, None, None, None, None)
+
+
+deform_conv_op.register_autograd(_dcn_bwd, setup_context=_dcn_setup)
+
+
+# =================================================================================== paste masks
+@torch.library.custom_op("d2b200::paste_masks", mutates_args=(), device_types="cuda")
+def paste_masks_op(masks: Tensor, boxes: Tensor, img_h: int, img_w: int, threshold: float) -> Tensor:
+    _C.require_cuda(masks, boxes)
+    mk, bx = _f32c(masks), _f32c(boxes)
+    n, m = mk.shape[0], mk.shape[-1]
+    out = torch.empty((n, img_h, img_w), dtype=torch.uint8, device=mk.device)
+    if out.numel():
+        with torch.cuda.device(mk.device):
+            check(_C.lib().d2b_paste_masks(ptr(mk), ptr(bx), n, m, img_h, img_w, threshold, ptr(out),
+                                           stream_ptr(mk.device)), "paste_masks")
+    return out
+
+
+@paste_masks_op.register_fake
+def _(masks, boxes, img_h, img_w, threshold):
+    return masks.new_empty((masks.shape[0], img_h, img_w), dtype=torch.uint8)
+
+
+# =================================================================================== detectron2::* dispatcher ops
+def _d2_nms_rotated(dets: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
+    return nms_op(dets, scores, None, iou_threshold, True)
+
+
+def _d2_box_iou_rotated(boxes1: Tensor, boxes2: Tensor) -> Tensor:
+    return box_iou_rotated_op(boxes1, boxes2)
+
+
+def _d2_roi_align_rotated_forward(input: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int,
+                                  pooled_width: int, sampling_ratio: int) -> Tensor:
+    return roi_align_rotated_op(input, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio)
+
+
+def _d2_roi_align_rotated_backward(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int,
+                                   pooled_width: int, batch_size: int, channels: int, height: int, width: int,
+                                   sampling_ratio: int) -> Tensor:
+    return roi_align_rotated_backward_op(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels,
+                                         height, width, sampling_ratio)
+
+
+_D2_SCHEMAS = {  # schemas as registered by the reference (dumped from the compiled csrc)
+    "nms_rotated": ("(Tensor dets, Tensor scores, float iou_threshold) -> Tensor", _d2_nms_rotated),
+    "box_iou_rotated": ("(Tensor boxes1, Tensor boxes2) -> Tensor", _d2_box_iou_rotated),
+    "roi_align_rotated_forward": ("(Tensor input, Tensor rois, float spatial_scale, int pooled_height, "
+                                  "int pooled_width, int sampling_ratio) -> Tensor", _d2_roi_align_rotated_forward),
+    "roi_align_rotated_backward": ("(Tensor grad, Tensor rois, float spatial_scale, int pooled_height, "
+                                   "int pooled_width, int batch_size, int channels, int height, int width, "
+                                   "int sampling_ratio) -> Tensor", _d2_roi_align_rotated_backward),
+}
+
+_d2_lib = None
+
+
+def register_detectron2_namespace():
+    """Expose our CUDA kernels under torch.ops.detectron2.* (idempotent)."""
+    global _d2_lib
+    if _d2_lib is not None:
+        return
+    _d2_lib = torch.library.Library("detectron2", "FRAGMENT")
+    for name, (schema, fn) in _D2_SCHEMAS.items():
+        exists = True
+        try:
+            torch._C._dispatch_find_schema_or_throw("detectron2::" + name, "")
+        except RuntimeError:
+            exists = False
+        if not exists:
+            _d2_lib.define(name + schema)
+        _d2_lib.impl(name, fn, "CUDA")
+
+
+register_detectron2_namespace()

@@ -1,0 +1,122 @@
+/*
+ * d2b200.h -- C ABI of the B200-native detection hot path (libd2b200.so).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a CUDA stream, no torch types.
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * detectron2 source tree).  The Python host (detectron2_b200/) binds these with ctypes and
+ * re-exports the reference's `detectron2.layers` operator surface on top; INTEGRATION.md shows
+ * the binding a detectron2 maintainer would add.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers on the current device, dense row-major
+ *     ("contiguous" NCHW unless stated); the caller owns every buffer (no hidden allocation:
+ *     scratch comes in through explicit workspace pointers whose size is queried first);
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, there are no
+ *     internal device synchronisations;
+ *   - return value: 0 = ok, <0 = invalid argument (D2B_E*), >0 = cudaError_t from a launch;
+ *   - stateless and re-entrant.
+ */
+#ifndef D2B200_H_
+#define D2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2B_OK 0
+#define D2B_EINVAL (-1)      /* bad shape / null pointer / unsupported parameter */
+#define D2B_EWORKSPACE (-2)  /* workspace too small */
+#define D2B_EUNSUPPORTED (-3)
+
+#define D2B_ABI_VERSION 1
+int d2b_abi_version(void);
+/* compile-time facts, replaces detectron2._C.get_cuda_version / has_cuda (csrc/vision.cpp:23-49,86-88) */
+int d2b_cuda_version(void);
+const char* d2b_arch(void); /* "sm_100a" */
+
+/* ---- RoIAlign, axis-aligned -------------------------------------------------------------
+ * Replaces torchvision::roi_align / torchvision::_roi_align_backward as reached from
+ * detectron2/layers/roi_align.py:58-65 (forward) and its autograd (backward).
+ * input [N,C,H,W] fp32, rois [K,5] = (batch_idx,x1,y1,x2,y2) fp32, out [K,C,PH,PW] fp32.
+ * sampling_ratio <= 0 -> adaptive ceil(roi/pooled) grid.  aligned: 0/1. */
+int d2b_roi_align_forward(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                          float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                          int aligned, float* out, void* stream);
+/* grad_in [N,C,H,W] is fully written (zero-filled inside, then accumulated with atomics). */
+int d2b_roi_align_backward(const float* grad_out, const float* rois, int K, float spatial_scale,
+                           int pooled_h, int pooled_w, int N, int C, int H, int W,
+                           int sampling_ratio, int aligned, float* grad_in, void* stream);
+
+/* ---- RoIAlign, rotated ------------------------------------------------------------------
+ * Replaces torch.ops.detectron2.roi_align_rotated_forward / _backward
+ * (csrc/vision.cpp:118-119, csrc/ROIAlignRotated/ROIAlignRotated.h:50-113).
+ * rois [K,6] = (batch_idx,cx,cy,w,h,angle_degrees). */
+int d2b_roi_align_rotated_forward(const float* input, int N, int C, int H, int W, const float* rois,
+                                  int K, float spatial_scale, int pooled_h, int pooled_w,
+                                  int sampling_ratio, float* out, void* stream);
+int d2b_roi_align_rotated_backward(const float* grad_out, const float* rois, int K,
+                                   float spatial_scale, int pooled_h, int pooled_w, int N, int C,
+                                   int H, int W, int sampling_ratio, float* grad_in, void* stream);
+
+/* ---- NMS --------------------------------------------------------------------------------
+ * Replaces torchvision::nms reached from detectron2/layers/nms.py:5-22 (nms, batched_nms) and
+ * torch.ops.detectron2.nms_rotated (csrc/vision.cpp:116, csrc/nms_rotated/nms_rotated.h:22-37).
+ * Greedy NMS in stable descending-score order (equal scores: lower index first).
+ *   boxes  [M,4] xyxy fp32 (rotated: [M,5] cx,cy,w,h,angle_deg), scores [M] fp32
+ *   idxs   [M] int64 category ids or NULL (plain nms).  When non-NULL the reference's coordinate
+ *          trick is applied on the fly:  axis-aligned  box + idx*(max_coord+1)   (torchvision
+ *          ops/boxes.py _batched_nms_coordinate_trick);  rotated  centre + idx*(max-min+1)
+ *          (detectron2/layers/nms.py:137-146), all in fp32 like the reference.
+ *   keep   [M] int64 out: kept ORIGINAL indices, score-descending; num_keep [1] int64 out (device).
+ * Suppression rule: axis-aligned  iou >  thr (torchvision);  rotated  iou >= thr (nms_rotated_cpu.cpp:54).
+ * workspace: d2b_nms_workspace_bytes(M, rotated) bytes of device scratch. */
+size_t d2b_nms_workspace_bytes(int64_t M, int rotated);
+int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
+            double iou_threshold, int rotated, int64_t* keep, int64_t* num_keep, void* workspace,
+            size_t workspace_bytes, void* stream);
+
+/* ---- Rotated-box IoU --------------------------------------------------------------------
+ * Replaces torch.ops.detectron2.box_iou_rotated (csrc/vision.cpp:117,
+ * csrc/box_iou_rotated/box_iou_rotated.h:20-33).  boxes1 [N,5], boxes2 [M,5] fp32 -> ious [N,M] fp32. */
+int d2b_box_iou_rotated(const float* boxes1, int64_t N, const float* boxes2, int64_t M, float* ious,
+                        void* stream);
+
+/* ---- Deformable convolution v1 / v2 -----------------------------------------------------
+ * Replaces detectron2._C.deform_conv_forward / deform_conv_backward_input /
+ * deform_conv_backward_filter / modulated_deform_conv_forward / modulated_deform_conv_backward
+ * (csrc/vision.cpp:90-102, csrc/deformable/deform_conv.h:116-375).  One description for both:
+ * mask == NULL -> DCNv1, bias == NULL -> no bias.
+ *   x [N,Cin,H,W], offset [N,2*DG*kh*kw,Ho,Wo] (channel 2k = dy, 2k+1 = dx of kernel point k),
+ *   mask [N,DG*kh*kw,Ho,Wo], weight [Cout,Cin/G,kh,kw], bias [Cout], out [N,Cout,Ho,Wo]; all fp32.
+ * precision: 0 = fp32 FFMA (parity path, <=1e-4 rel), 1 = bf16x3 split on tcgen05 (fp32-class
+ * accuracy), 2 = plain bf16 tcgen05 (autocast path). */
+typedef struct {
+  int N, Cin, H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups,
+      deformable_groups;
+} d2b_dcn_params;
+
+int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask,
+                            const float* weight, const float* bias, const d2b_dcn_params* p,
+                            int precision, float* out, void* stream);
+/* Backward.  grad_columns scratch: workspace of d2b_deform_conv_backward_workspace_bytes(p) bytes.
+ * Any of the grad outputs may be NULL to skip it.  Outputs are fully written (zero-filled inside). */
+size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p);
+int d2b_deform_conv_backward(const float* x, const float* offset, const float* mask,
+                             const float* weight, const float* grad_out, const d2b_dcn_params* p,
+                             float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
+                             float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- paste_masks_in_image ---------------------------------------------------------------
+ * Replaces detectron2/layers/mask_ops.py:74-147 (GPU branch: every pixel of the image for every mask).
+ * masks [N,M,M] fp32, boxes [N,4] xyxy fp32 -> out [N,H,W] uint8: (v >= threshold) as 0/1 when
+ * threshold >= 0, else (uint8)(v*255). */
+int d2b_paste_masks(const float* masks, const float* boxes, int N, int M, int H, int W,
+                    float threshold, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2B200_H_ */

@@ -1,0 +1,93 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/d2b200.h declares, and the host
+wrappers keep the reference's surface (names, repr strings, exception types).  No compute calls: there is no GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from detectron2_b200 import _C
+
+    lib = _C.lib()
+    header = open(os.path.join(ROOT, "include", "d2b200.h")).read()
+    declared = set(re.findall(r"\b(d2b_[a-z0-9_]+)\s*\(", header)) - {"d2b_dcn_params"}
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_C.EXPORTED) == declared
+    assert lib.d2b_abi_version() == 1
+    assert lib.d2b_arch() == b"sm_100a"
+    assert _C.get_cuda_version().startswith("CUDA 12")
+
+
+def test_workspace_queries_run_on_host():
+    from detectron2_b200 import _C
+
+    small, big = _C.lib().d2b_nms_workspace_bytes(1000, 0), _C.lib().d2b_nms_workspace_bytes(10000, 0)
+    assert 0 < small < big
+    assert _C.lib().d2b_nms_workspace_bytes(10000, 1) > big  # 5 floats per rotated box
+
+
+def test_surface_matches_reference_names():
+    import detectron2_b200.layers as L
+
+    for name in ["ROIAlign", "roi_align", "ROIAlignRotated", "roi_align_rotated", "DeformConv", "ModulatedDeformConv",
+                 "batched_nms", "nms", "batched_nms_rotated", "nms_rotated", "paste_masks_in_image",
+                 "pairwise_iou_rotated"]:
+        assert hasattr(L, name), name
+    for op in ["nms_rotated", "box_iou_rotated", "roi_align_rotated_forward", "roi_align_rotated_backward"]:
+        assert hasattr(torch.ops.detectron2, op)
+
+
+def test_repr_strings():  # /root/reference/tests/layers/test_deformable.py:157-171
+    import detectron2_b200.layers as L
+
+    assert repr(L.DeformConv(3, 10, kernel_size=3, padding=1, deformable_groups=2)) == (
+        "DeformConv(in_channels=3, out_channels=10, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), "
+        "dilation=(1, 1), groups=1, deformable_groups=2, bias=False)")
+    assert repr(L.ModulatedDeformConv(3, 10, kernel_size=3, padding=1, deformable_groups=2)) == (
+        "ModulatedDeformConv(in_channels=3, out_channels=10, kernel_size=(3, 3), stride=1, padding=1, dilation=1, "
+        "groups=1, deformable_groups=2, bias=True)")
+    assert "aligned=True" in repr(L.ROIAlign((7, 7), 0.25, 0))
+    m = L.ModulatedDeformConv(4, 8, 3)
+    assert m.weight.shape == (8, 4, 3, 3) and m.bias.shape == (8,) and (m.bias == 0).all()
+
+
+def test_no_cpu_fallback():
+    import detectron2_b200.layers as L
+
+    with pytest.raises(NotImplementedError):
+        L.nms(torch.rand(4, 4), torch.rand(4), 0.5)
+    with pytest.raises(NotImplementedError):
+        L.ROIAlign((7, 7), 1.0, 0)(torch.rand(1, 1, 8, 8), torch.tensor([[0.0, 1, 1, 4, 4]]))
+    with pytest.raises(NotImplementedError):
+        L.DeformConv(1, 1, 3, padding=1)(torch.rand(1, 1, 5, 5), torch.zeros(1, 18, 5, 5))
+    with pytest.raises(ValueError):
+        L.deform_conv(torch.rand(1, 5, 5), torch.zeros(1, 18, 5, 5), torch.rand(1, 1, 3, 3))
+    with pytest.raises(AssertionError):
+        L.ROIAlign((7, 7), 1.0, 0)(torch.rand(1, 1, 8, 8), torch.rand(3, 4))
+
+
+def test_empty_inputs_host_side():
+    import detectron2_b200.layers as L
+
+    assert L.batched_nms_rotated(torch.zeros(0, 5), torch.zeros(0), torch.zeros(0, dtype=torch.int64), 0.5).shape == (0,)
+    assert L.batched_nms(torch.zeros(0, 4), torch.zeros(0), torch.zeros(0, dtype=torch.int64), 0.5).shape == (0,)
+    out = L.paste_masks_in_image(torch.zeros(0, 28, 28), torch.zeros(0, 4), (10, 12))
+    assert out.shape == (0, 10, 12) and out.dtype == torch.uint8
+    y = L.DeformConv(2, 4, 3, padding=1)(torch.zeros(0, 2, 8, 8), torch.zeros(0, 18, 8, 8))
+    assert y.shape == (0, 4, 8, 8)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "detectron2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "import torchvision" not in src and "from torchvision" not in src, f

@@ -1,0 +1,383 @@
+"""GPU parity tests proper: the CUDA path (through the detectron2.layers-shaped surface -> ctypes -> C ABI)
+against the CPU oracle and the committed reference fixtures.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): bit-exact NMS keep indices and box_iou_rotated; <= 1e-4 relative for
+RoIAlign and deform-conv (fp32).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def L():
+    import detectron2_b200.layers as layers
+
+    return layers
+
+
+def rel_close(a, b, rtol=1e-4, atol=1e-5):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return torch.allclose(a, b, rtol=rtol, atol=atol), (a - b).abs().max().item()
+
+
+def bits(t):
+    return t.detach().cpu().contiguous().numpy().view(np.uint32)
+
+
+# ------------------------------------------------------------------------------- RoIAlign
+def test_roi_align_golden(L, golden):
+    d = golden("roi_align")
+    x, rois = T(d["x"]).to(DEV), T(d["rois"]).to(DEV)
+    for i, (ph, pw, sr, al) in enumerate(d["cfgs"]):
+        xi = x.clone().requires_grad_(True)
+        y = L.ROIAlign((int(ph), int(pw)), 0.5, int(sr), bool(al))(xi, rois)
+        ok, err = rel_close(y, T(d[f"y{i}"]))
+        assert ok, (i, err)
+        y.backward(T(d[f"go{i}"]).to(DEV))
+        ok, err = rel_close(xi.grad, T(d[f"gx{i}"]), atol=1e-4)
+        assert ok, (i, err)
+
+
+def test_roi_align_reference_kats(L):
+    # /root/reference/tests/layers/test_roi_align.py:14-47,111-128
+    img = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5).to(DEV)
+    rois = torch.tensor([[0.0, 1, 1, 3, 3]], device=DEV)
+    old = [[7.5, 8, 8.5, 9], [10, 10.5, 11, 11.5], [12.5, 13, 13.5, 14], [15, 15.5, 16, 16.5]]
+    new = [[4.5, 5.0, 5.5, 6.0], [7.0, 7.5, 8.0, 8.5], [9.5, 10.0, 10.5, 11.0], [12.0, 12.5, 13.0, 13.5]]
+    assert np.allclose(L.ROIAlign((4, 4), 1.0, 0, aligned=False)(img, rois)[0, 0].cpu().numpy(), old)
+    assert np.allclose(L.ROIAlign((4, 4), 1.0, 0, aligned=True)(img, rois)[0, 0].cpu().numpy(), new)
+    x = torch.rand(1, 1, 5, 5, device=DEV, requires_grad=True)
+    o = L.ROIAlign((7, 7), 1.0, 0, aligned=True)(x, torch.tensor([[0.0, 3, 4, 5, 4]], device=DEV))
+    assert o.shape == (1, 1, 7, 7) and (o == 0).all()
+    o.sum().backward()
+    assert (x.grad == 0).all()
+    out = L.ROIAlign((7, 7), 1.0, 0)(torch.zeros(0, 3, 10, 10, device=DEV), torch.zeros(0, 5, device=DEV))
+    assert out.shape == (0, 3, 7, 7)
+
+
+@pytest.mark.parametrize("sr", [0, 2])
+def test_roi_align_cfg1_vs_oracle(L, sr):
+    # BASELINE config 1: 512 boxes over 1x256x200x304, scale 0.25, 7x7 (SURVEY 8d generator)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 256, 200, 304, generator=g)
+    k = 512
+    cx, cy = torch.rand(k, generator=g) * 1216, torch.rand(k, generator=g) * 800
+    w, h = 16 + torch.rand(k, generator=g) * 300, 16 + torch.rand(k, generator=g) * 300
+    rois = torch.stack([torch.zeros(k), (cx - w / 2).clamp(0, 1216), (cy - h / 2).clamp(0, 800),
+                        (cx + w / 2).clamp(0, 1216), (cy + h / 2).clamp(0, 800)], 1)
+    ref = orc.roi_align_forward(x, rois, 0.25, 7, 7, sr, True)
+    xg = x.to(DEV).requires_grad_(True)
+    y = L.ROIAlign((7, 7), 0.25, sr, True)(xg, rois.to(DEV))
+    ok, err = rel_close(y, ref)
+    assert ok, err
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go.to(DEV))
+    gref = orc.roi_align_backward(go, rois, 0.25, 7, 7, 1, 256, 200, 304, sr, True)
+    ok, err = rel_close(xg.grad, gref, rtol=1e-4, atol=2e-4)
+    assert ok, err
+
+
+def test_roi_align_linearity_full_size(L):
+    # size-independent property at config-2 size: RoIAlign is linear in the feature map
+    g = torch.Generator(device=DEV).manual_seed(1)
+    a = torch.randn(2, 256, 100, 168, device=DEV, generator=g)
+    b = torch.randn(2, 256, 100, 168, device=DEV, generator=g)
+    k = 1000
+    ctr = torch.rand(k, 2, device=DEV, generator=g) * torch.tensor([1344.0, 800.0], device=DEV)
+    wh = 8 + torch.rand(k, 2, device=DEV, generator=g) * 400
+    rois = torch.cat([torch.randint(0, 2, (k, 1), device=DEV, generator=g).float(), ctr - wh / 2, ctr + wh / 2], 1)
+    op = L.ROIAlign((7, 7), 0.125, 0, True)
+    lhs = op(2.0 * a + b, rois)
+    rhs = 2.0 * op(a, rois) + op(b, rois)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-4)
+
+
+def test_roi_align_rotated_golden(L, golden):
+    d = golden("roi_align_rotated")
+    x, rois = T(d["x"]).to(DEV), T(d["rois"]).to(DEV)
+    for i, (ph, pw, sr) in enumerate(d["cfgs"]):
+        xi = x.clone().requires_grad_(True)
+        y = L.ROIAlignRotated((int(ph), int(pw)), 0.5, int(sr))(xi, rois)
+        ok, err = rel_close(y, T(d[f"y{i}"]))
+        assert ok, (i, err)
+        y.backward(T(d[f"go{i}"]).to(DEV))
+        ok, err = rel_close(xi.grad, T(d[f"gx{i}"]), atol=1e-4)
+        assert ok, (i, err)
+        # the dispatcher op the reference wrappers call (roi_align_rotated.py:20)
+        y2 = torch.ops.detectron2.roi_align_rotated_forward(x, rois, 0.5, int(ph), int(pw), int(sr))
+        assert torch.equal(y2, y.detach())
+
+
+def test_roi_align_rotated_kats(L):
+    # /root/reference/tests/layers/test_roi_align_rotated.py:30-71,102-105,127-172
+    img = torch.arange(25, dtype=torch.float32).reshape(5, 5)
+    exp = torch.tensor([[4.5, 5.0, 5.5, 6.0], [7.0, 7.5, 8.0, 8.5], [9.5, 10.0, 10.5, 11.0], [12.0, 12.5, 13.0, 13.5]])
+
+    def rot90(t, num):
+        for _ in range(num % 4):
+            t = t.transpose(0, 1).flip(0)
+        return t
+
+    for i in range(4):
+        rois = torch.tensor([[0, 2.0, 2.0, 2.0, 2.0, 90.0 * i]], device=DEV)
+        out = L.ROIAlignRotated((4, 4), 1.0, 0)(img[None, None].to(DEV), rois)[0, 0].cpu()
+        assert torch.allclose(out, rot90(exp, -i), atol=1e-5)
+    out = L.ROIAlignRotated((7, 7), 1.0, 0)(torch.rand(1, 1, 5, 5, device=DEV),
+                                             torch.tensor([[0, 2.0, 3, 0, 0, 0]], device=DEV))
+    assert (out == 0).all()
+    # gradients of the rotated op at 0 degrees equal the axis-aligned op's
+    x = torch.rand(1, 1, 10, 10, device=DEV)
+    xa, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    rr = torch.tensor([[0, 4.5, 4.5, 9, 9, 0], [0, 2, 7, 4, 4, 0], [0, 7, 7, 4, 4, 0]], dtype=torch.float32, device=DEV)
+    ra = torch.tensor([[0, 0, 0, 9, 9], [0, 0, 5, 4, 9], [0, 5, 5, 9, 9]], dtype=torch.float32, device=DEV)
+    L.ROIAlignRotated((5, 5), 1, 2)(xr, rr).sum().backward()
+    L.ROIAlign((5, 5), 1, 2)(xa, ra).sum().backward()
+    assert torch.allclose(xa.grad, xr.grad, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------- NMS
+def test_nms_golden_bit_exact(L, golden):
+    d = golden("nms")
+    boxes, scores, idxs = T(d["boxes"]).to(DEV), T(d["scores"]).to(DEV), T(d["idxs"]).to(DEV)
+    for i, t in enumerate(d["thr"]):
+        assert torch.equal(L.nms(boxes, scores, float(t)).cpu(), T(d[f"keep{i}"])), i
+        assert torch.equal(L.batched_nms(boxes, scores, idxs, float(t)).cpu(), T(d[f"bkeep_trick{i}"])), i
+
+
+def _random_boxes(g, n, size):
+    b = torch.rand(n, 4, generator=g) * (size * 0.5)
+    b[:, 2:] += size * 0.5
+    return b
+
+
+@pytest.mark.parametrize("m,ncls,thr", [(1, 1, 0.5), (63, 2, 0.5), (64, 3, 0.3), (65, 1, 0.7), (2000, 50, 0.5),
+                                        (4819, 5, 0.7), (8819, 5, 0.7), (5000, 80, 0.5)])
+def test_nms_vs_oracle_bit_exact(L, m, ncls, thr):
+    g = torch.Generator().manual_seed(m)
+    boxes = _random_boxes(g, m, 400)
+    if m > 200:  # near-duplicates and score ties
+        boxes[100:200] = boxes[:100] + torch.randn(100, 4, generator=g)
+    scores = torch.rand(m, generator=g)
+    if m > 400:
+        scores[300:350] = scores[250:300]
+    idxs = torch.randint(0, ncls, (m,), generator=g)
+    assert torch.equal(L.nms(boxes.to(DEV), scores.to(DEV), thr).cpu(), orc.nms(boxes, scores, thr))
+    got = L.batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), thr).cpu()
+    assert torch.equal(got, orc.batched_nms(boxes, scores, idxs, thr))
+
+
+def test_nms_fixed_capacity_and_idempotence(L):
+    g = torch.Generator().manual_seed(3)
+    m = 25000
+    boxes, scores = _random_boxes(g, m, 1333).to(DEV), torch.rand(m, generator=g).to(DEV)
+    idxs = torch.randint(0, 80, (m,), generator=g).to(DEV)
+    keep_buf, num = L.batched_nms_fixed(boxes, scores, idxs, 0.5)
+    keep = L.batched_nms(boxes, scores, idxs, 0.5)
+    assert int(num.item()) == keep.numel() and torch.equal(keep_buf[: keep.numel()], keep)
+    s = scores[keep]
+    assert (s[:-1] >= s[1:]).all()  # sorted by score
+    # idempotence: NMS of the survivors keeps every one of them, in the same order
+    again = L.batched_nms(boxes[keep], scores[keep], idxs[keep], 0.5)
+    assert torch.equal(again, torch.arange(keep.numel(), device=DEV))
+
+
+def test_batched_nms_vanilla_path_large(L):
+    # > 100k coordinates: torchvision's per-class strategy (exact IoU on un-shifted boxes)
+    g = torch.Generator().manual_seed(5)
+    m = 26000
+    boxes, scores = _random_boxes(g, m, 1333), torch.rand(m, generator=g)
+    idxs = torch.randint(0, 80, (m,), generator=g)
+    got = L.batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), 0.5).cpu()
+    keep_mask = torch.zeros(m, dtype=torch.bool)
+    for c in idxs.unique():
+        cur = torch.where(idxs == c)[0]
+        keep_mask[cur[orc.nms(boxes[cur], scores[cur], 0.5)]] = True
+    ki = torch.where(keep_mask)[0]
+    assert torch.equal(got, ki[scores[ki].sort(descending=True, stable=True)[1]])
+
+
+# ------------------------------------------------------------------------------- rotated IoU / NMS
+def test_rotated_golden_bit_exact(L, golden):
+    d = golden("rotated")
+    ious = L.pairwise_iou_rotated(T(d["b1"]).to(DEV), T(d["b2"]).to(DEV))
+    assert np.array_equal(bits(ious), d["ious"].view(np.uint32))
+    dets, scores = T(d["dets"]).to(DEV), T(d["scores"]).to(DEV)
+    for i, t in enumerate(d["thr"]):
+        assert torch.equal(L.nms_rotated(dets, scores, float(t)).cpu(), T(d[f"keep{i}"])), i
+
+
+def test_rotated_iou_kats(L):
+    from test_oracle_pins import IOU_KATS
+
+    for b1, b2, exp in IOU_KATS:
+        out = L.pairwise_iou_rotated(torch.tensor(b1, dtype=torch.float32, device=DEV),
+                                     torch.tensor(b2, dtype=torch.float32, device=DEV))
+        assert torch.allclose(out.cpu(), torch.tensor(exp, dtype=torch.float32)), (b1, b2)
+    assert L.pairwise_iou_rotated(torch.rand(0, 5, device=DEV), torch.rand(10, 5, device=DEV)).shape == (0, 10)
+    assert L.pairwise_iou_rotated(torch.rand(10, 5, device=DEV), torch.rand(0, 5, device=DEV)).shape == (10, 0)
+    s = L.pairwise_iou_rotated(torch.zeros(5, 5, device=DEV), torch.zeros(1289035, 5, device=DEV))  # :71-78
+    assert tuple(s.shape) == (5, 1289035)
+
+
+def _rand_rot(g, n, size, wmax):
+    return torch.stack([torch.rand(n, generator=g) * size, torch.rand(n, generator=g) * size,
+                        1 + torch.rand(n, generator=g) * wmax, 1 + torch.rand(n, generator=g) * wmax,
+                        (torch.rand(n, generator=g) - 0.5) * 720], 1)
+
+
+def test_rotated_iou_random_bit_exact_and_symmetric(L):
+    g = torch.Generator().manual_seed(21)
+    b1, b2 = _rand_rot(g, 400, 200, 90), _rand_rot(g, 500, 200, 90)
+    got = L.pairwise_iou_rotated(b1.to(DEV), b2.to(DEV))
+    ref = orc.box_iou_rotated(b1, b2)
+    neq = bits(got) != ref.numpy().view(np.uint32)
+    assert neq.sum() == 0, (int(neq.sum()), (got.cpu() - ref).abs().max().item())
+    # 1000x1000 (BASELINE cfg) property: symmetry IoU(a,b) == IoU(b,a) up to the ordering of the clip
+    a = _rand_rot(g, 1000, 300, 120).to(DEV)
+    m1, m2 = L.pairwise_iou_rotated(a, a), L.pairwise_iou_rotated(a, a).t()
+    assert torch.allclose(m1, m2, atol=1e-4)
+    assert (m1 >= 0).all() and (m1 <= 1 + 1e-4).all()
+
+
+@pytest.mark.parametrize("m,thr", [(300, 0.3), (1500, 0.5)])
+def test_nms_rotated_vs_oracle(L, m, thr):
+    g = torch.Generator().manual_seed(m)
+    dets = _rand_rot(g, m, 150, 60)
+    dets[100:200] = dets[:100] + torch.randn(100, 5, generator=g) * torch.tensor([2.0, 2, 2, 2, 5])
+    dets[:, 2:4].clamp_(min=0.5)
+    scores = torch.rand(m, generator=g)
+    idxs = torch.randint(0, 4, (m,), generator=g)
+    assert torch.equal(L.nms_rotated(dets.to(DEV), scores.to(DEV), thr).cpu(), orc.nms_rotated(dets, scores, thr))
+    got = L.batched_nms_rotated(dets.to(DEV), scores.to(DEV), idxs.to(DEV), thr).cpu()
+    assert torch.equal(got, orc.batched_nms_rotated(dets, scores, idxs, thr))
+
+
+# ------------------------------------------------------------------------------- deformable conv
+def _dcn_run(L, x, off, mask, wt, bias, s, p, dil, grp, dg):
+    if mask is None:
+        return L.deform_conv(x, off, wt, s, p, dil, grp, dg)
+    return L.modulated_deform_conv(x, off, mask, wt, bias, s, p, dil, grp, dg)
+
+
+def test_deform_conv_golden(L, golden):
+    d = golden("deform_conv")
+    for i, (n, cin, h, w, cout, k, s, p, dil, grp, dg, mod, hb) in enumerate(d["cases"]):
+        x = T(d[f"x{i}"]).to(DEV).requires_grad_(True)
+        off = T(d[f"off{i}"]).to(DEV).requires_grad_(True)
+        wt = T(d[f"w{i}"]).to(DEV).requires_grad_(True)
+        mask = T(d[f"mask{i}"]).to(DEV).requires_grad_(True) if mod else None
+        bias = T(d[f"bias{i}"]).to(DEV).requires_grad_(True) if hb else None
+        y = _dcn_run(L, x, off, mask, wt, bias, int(s), int(p), int(dil), int(grp), int(dg))
+        ok, err = rel_close(y, T(d[f"y{i}"]), atol=1e-4)
+        assert ok, (i, err)
+        y.backward(T(d[f"go{i}"]).to(DEV))
+        for name, t in (("gx", x), ("goff", off), ("gw", wt)):
+            ok, err = rel_close(t.grad, T(d[f"{name}{i}"]), atol=2e-4)
+            assert ok, (i, name, err)
+        if mod:
+            ok, err = rel_close(mask.grad, T(d[f"gmask{i}"]), atol=2e-4)
+            assert ok, (i, "gmask", err)
+        if hb:
+            ok, err = rel_close(bias.grad, T(d[f"gbias{i}"]), atol=2e-4)
+            assert ok, (i, "gbias", err)
+
+
+def test_deform_conv_reference_kats(L):
+    # /root/reference/tests/layers/test_deformable.py:16-58,112-171
+    x = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5).to(DEV)
+    off = torch.full((1, 18, 5, 5), 0.5, device=DEV)
+    exp = np.array([[30, 41.25, 48.75, 45, 28.75], [62.25, 81, 90, 80.25, 50.25], [99.75, 126, 135, 117.75, 72.75],
+                    [105, 131.25, 138.75, 120, 73.75], [71.75, 89.25, 93.75, 80.75, 49.5]])
+    dc = L.DeformConv(1, 1, kernel_size=3, padding=1).to(DEV)
+    dc.weight = torch.nn.Parameter(torch.ones_like(dc.weight))
+    assert np.allclose(dc(x, off).detach().cpu().numpy().reshape(5, 5), exp)
+    mdc = L.ModulatedDeformConv(1, 1, 3, padding=1, bias=False).to(DEV)
+    mdc.weight = dc.weight
+    out = mdc(x, off, torch.full((1, 9, 5, 5), 0.5, device=DEV))
+    assert np.allclose(out.detach().cpu().numpy().reshape(5, 5), exp * 0.5)
+    for ks in (3, 5):  # input smaller than the kernel
+        xin = torch.rand(1, 1, ks - 1, ks - 1, device=DEV)
+        o = torch.randn(1, 2 * ks * ks, ks - 1, ks - 1, device=DEV)
+        assert L.DeformConv(1, 1, ks, padding=ks // 2).to(DEV)(xin, o).shape == xin.shape
+    with pytest.raises(RuntimeError):  # wrong offset channels
+        L.DeformConv(1, 1, 3, padding=1).to(DEV)(torch.rand(1, 1, 3, 3, device=DEV), torch.randn(1, 9, 3, 3, device=DEV))
+    with pytest.raises(RuntimeError):  # wrong mask channels
+        L.ModulatedDeformConv(1, 1, 3, padding=1, bias=False).to(DEV)(
+            torch.rand(1, 1, 3, 3, device=DEV), torch.randn(1, 18, 3, 3, device=DEV), torch.ones(1, 18, 3, 3, device=DEV))
+
+
+@pytest.mark.parametrize("cin,cout,h,w,grp,dg,mod,stride", [(32, 48, 20, 28, 1, 1, False, 1), (64, 64, 13, 17, 4, 2, True, 1),
+                                                            (48, 32, 21, 19, 2, 1, True, 2), (128, 128, 25, 42, 32, 1, False, 1)])
+def test_deform_conv_vs_oracle(L, cin, cout, h, w, grp, dg, mod, stride):
+    g = torch.Generator().manual_seed(cin + cout)
+    n, k, p = 2, 3, 1
+    ho, wo = (h + 2 * p - k) // stride + 1, (w + 2 * p - k) // stride + 1
+    x = torch.randn(n, cin, h, w, generator=g)
+    off = torch.randn(n, 2 * dg * k * k, ho, wo, generator=g) * 2
+    mask = torch.sigmoid(torch.randn(n, dg * k * k, ho, wo, generator=g)) if mod else None
+    wt = torch.randn(cout, cin // grp, k, k, generator=g) * (1.0 / math.sqrt(cin // grp * 9))
+    bias = torch.randn(cout, generator=g) if mod else None
+    go = torch.randn(n, cout, ho, wo, generator=g)
+    yref = orc.deform_conv_forward(x, off, mask, wt, bias, stride, p, 1, grp, dg)
+    gref = orc.deform_conv_backward(x, off, mask, wt, go, stride, p, 1, grp, dg, bias is not None)
+    tens = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (x, off, mask, wt, bias)]
+    y = _dcn_run(L, tens[0], tens[1], tens[2], tens[3], tens[4], stride, p, 1, grp, dg)
+    ok, err = rel_close(y, yref, rtol=1e-4, atol=1e-4)
+    assert ok, err
+    y.backward(go.to(DEV))
+    for t, r, name in zip(tens, [gref[0], gref[1], gref[2], gref[3], gref[4]], ["gx", "goff", "gmask", "gw", "gb"]):
+        if t is None:
+            continue
+        scale = r.abs().max().item() + 1e-6
+        err = (t.grad.cpu() - r).abs().max().item()
+        assert err <= 1e-4 * scale + 1e-5, (name, err, scale)
+
+
+# ------------------------------------------------------------------------------- paste masks
+def test_paste_masks_golden(L, golden):
+    d = golden("paste_masks")
+    h, w = [int(v) for v in d["hw"]]
+    masks, boxes = T(d["masks"]).to(DEV), T(d["boxes"]).to(DEV)
+    out = L.paste_masks_in_image(masks, boxes, (h, w), 0.5)
+    assert out.dtype == torch.bool and out.shape == (9, h, w)
+    ref_soft = T(d["soft"])
+    mism = out.cpu() != T(d["out_bool"])
+    assert not (mism & ((ref_soft - 0.5).abs() > 1e-5)).any() and mism.sum() <= 2
+    ob = orc.paste_masks(T(d["masks"]), T(d["boxes"]), (h, w), 0.5)
+    assert torch.equal(out.cpu(), ob)  # kernel and oracle share the expression order -> identical bytes
+    u8 = L.paste_masks_in_image(masks, boxes, (h, w), -1)
+    assert u8.dtype == torch.uint8
+    assert (u8.cpu().int() - T(d["out_u8"]).int()).abs().max() <= 1
+    assert L.paste_masks_in_image(torch.zeros(0, 28, 28, device=DEV), torch.zeros(0, 4, device=DEV), (h, w)).shape == (0, h, w)
+
+
+def test_paste_masks_full_size_vs_oracle(L):
+    # config 2: 100 masks, 800x1333 image; oracle on a 12-mask subset (seconds), all 100 via a checksum property
+    g = torch.Generator().manual_seed(42)
+    n, h, w = 100, 800, 1333
+    masks = torch.rand(n, 28, 28, generator=g)
+    ctr = torch.rand(n, 2, generator=g) * torch.tensor([1333.0, 800.0])
+    wh = 20 + torch.rand(n, 2, generator=g) * 500
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    out = L.paste_masks_in_image(masks.to(DEV), boxes.to(DEV), (h, w), 0.5)
+    sub = torch.arange(0, n, 9)
+    ref = orc.paste_masks(masks[sub], boxes[sub], (h, w), 0.5)
+    assert torch.equal(out[sub.to(DEV)].cpu(), ref)
+    # constant masks: pasted area == clipped box area (within the 1-pixel bilinear border)
+    ones = torch.ones(n, 28, 28)
+    cnt = L.paste_masks_in_image(ones.to(DEV), boxes.to(DEV), (h, w), 0.5).flatten(1).sum(1).cpu().float()
+    cb = boxes.clone()
+    cb[:, 0::2].clamp_(0, w)
+    cb[:, 1::2].clamp_(0, h)
+    area = (cb[:, 2] - cb[:, 0]) * (cb[:, 3] - cb[:, 1])
+    per = 2 * ((cb[:, 2] - cb[:, 0]) + (cb[:, 3] - cb[:, 1]))
+    assert ((cnt - area).abs() <= per + 4).all()
