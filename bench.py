@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the detection hot path (BASELINE.json configs[1]).
+
+One "step" = one pass of the per-image custom-op hot path of Mask R-CNN R50-FPN inference over one synthetic image
+(3x800x1333 -> padded 800x1344, FPN p2..p5 256 ch fp32, 1000 proposals):
+
+    rpn_nms     batched_nms(4819 boxes, 5 levels, thr 0.7)                 (proposal_utils.py:121)
+    box_pool    ROIPooler 7x7, sampling_ratio 0, aligned, 1000 proposals    (roi_heads.py:798 -> poolers.py:206)
+    det_nms     batched_nms(~3000 (box,class) pairs, 80 classes, thr 0.5)  (fast_rcnn.py:162), top-100
+    mask_pool   ROIPooler 14x14 on the 100 detections                       (roi_heads.py:843)
+    paste       paste_masks_in_image(100 x 28x28 -> 800x1333)               (postprocessing.py -> mask_ops.py:74)
+
+(the backbone / heads between those ops are cuDNN/cuBLAS work outside the scope of this repository: see DESIGN.md).
+Prints ONE JSON line (see the contract in DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W = 800, 1333
+PAD_H, PAD_W = 800, 1344
+LEVELS = [(200, 336, 1 / 4), (100, 168, 1 / 8), (50, 84, 1 / 16), (25, 42, 1 / 32)]
+C = 256
+N_PROPOSALS = 1000
+N_RPN_BOXES = 4819  # 1000 per level p2..p5 + 819 on p6 (13*21*3 anchors)
+N_DET_CANDIDATES = 3000
+N_DET = 100
+MASK_SIDE = 28
+METRIC = "Mask R-CNN R50-FPN hot-path images/sec (custom-op path of inference, 1000 proposals/image)"
+WORKLOAD = ("configs[1]: Mask R-CNN R50-FPN inference hot path on 1xB200, synthetic 3x800x1333 image, "
+            "1000 proposals/image, fp32 FPN features")
+
+
+# ----------------------------------------------------------------------------------------- synthetic inputs
+def synth_boxes(g, n, smin=16.0, smax=600.0):
+    """sqrt(area) log-uniform in [16,600] px, aspect log-uniform in [1/2,2], centres uniform, clipped."""
+    s = torch.exp(torch.rand(n, generator=g) * (math.log(smax) - math.log(smin)) + math.log(smin))
+    a = torch.exp((torch.rand(n, generator=g) - 0.5) * 2 * math.log(2.0))
+    w, h = s * torch.sqrt(a), s / torch.sqrt(a)
+    cx, cy = torch.rand(n, generator=g) * IMG_W, torch.rand(n, generator=g) * IMG_H
+    b = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    b[:, 0::2].clamp_(0, IMG_W)
+    b[:, 1::2].clamp_(0, IMG_H)
+    return b
+
+
+def make_image_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    d = {}
+    d["feats"] = [torch.randn(1, C, h, w, generator=g) for (h, w, _) in LEVELS]
+    d["rpn_boxes"] = synth_boxes(g, N_RPN_BOXES, 16.0, 500.0)
+    d["rpn_scores"] = torch.rand(N_RPN_BOXES, generator=g)
+    lv = torch.cat([torch.full((1000,), i) for i in range(4)] + [torch.full((819,), 4)])
+    d["rpn_levels"] = lv.to(torch.int64)
+    d["proposals"] = synth_boxes(g, N_PROPOSALS)
+    # Fast R-CNN candidates: each is a jittered copy of one of ~300 objects so that NMS has real work to do
+    base = synth_boxes(g, 300, 24.0, 500.0)
+    pick = torch.randint(0, 300, (N_DET_CANDIDATES,), generator=g)
+    d["det_boxes"] = (base[pick] + torch.randn(N_DET_CANDIDATES, 4, generator=g) * 6).clamp_(0, IMG_W)
+    d["det_boxes"][:, 2:] = torch.maximum(d["det_boxes"][:, 2:], d["det_boxes"][:, :2] + 2)
+    d["det_scores"] = 0.05 + 0.95 * torch.rand(N_DET_CANDIDATES, generator=g)
+    d["det_classes"] = (pick % 80).to(torch.int64)
+    d["masks"] = torch.rand(N_DET, MASK_SIDE, MASK_SIDE, generator=g)
+    return d
+
+
+def h2d_bytes(d):
+    n = sum(t.numel() * t.element_size() for t in d["feats"])
+    for k in ("rpn_boxes", "rpn_scores", "rpn_levels", "proposals", "det_boxes", "det_scores", "det_classes", "masks"):
+        n += d[k].numel() * d[k].element_size()
+    return n
+
+
+def roi_align_algorithmic_bytes(rois_img, ph, pw):
+    """sum_l min(N*C*H_l*W_l, sum_k C*fp_k)*4 + K*C*PH*PW*4 + K*5*4, fp_k = pixel footprint on its level."""
+    b = rois_img
+    sizes = torch.sqrt((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))
+    lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).long() - 2
+    total = 0
+    for l, (h, w, s) in enumerate(LEVELS):
+        bl = b[lv == l] * s - 0.5
+        if len(bl) == 0:
+            continue
+        fp = (torch.floor(bl[:, 2]) - torch.floor(bl[:, 0]) + 2).clamp(1, w) * \
+             (torch.floor(bl[:, 3]) - torch.floor(bl[:, 1]) + 2).clamp(1, h)
+        total += min(C * h * w, int(fp.sum().item()) * C) * 4
+    k = len(b)
+    return total + k * C * ph * pw * 4 + k * 5 * 4
+
+
+# ----------------------------------------------------------------------------------------- our arm
+class OursRunner:
+    KERNELS_PER_STEP = 13  # nms: iota+range+gather+mask+scan (x2), pooler (x2), paste (x1); CUB's sort kernels not counted
+
+    def __init__(self, device):
+        import detectron2_b200.layers as L
+        from detectron2_b200.poolers import ROIPooler
+
+        self.L = L
+        self.dev = device
+        scales = [s for (_, _, s) in LEVELS]
+        self.box_pooler = ROIPooler(7, scales, 0, "ROIAlignV2")
+        self.mask_pooler = ROIPooler(14, scales, 0, "ROIAlignV2")
+
+    def to_device(self, d):
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, list):
+                out[k] = [t.to(self.dev, non_blocking=True) for t in v]
+            else:
+                out[k] = v.to(self.dev, non_blocking=True)
+        return out
+
+    def step(self, d, ev=None, sync_free=True):
+        """One image through the hot path. Returns (pooled box feats, mask feats, pasted masks)."""
+        L = self.L
+
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+
+        mark(0)
+        if sync_free:
+            keep, _ = L.batched_nms_fixed(d["rpn_boxes"], d["rpn_scores"], d["rpn_levels"], 0.7)
+            keep = keep[:N_PROPOSALS]
+        else:
+            keep = L.batched_nms(d["rpn_boxes"], d["rpn_scores"], d["rpn_levels"], 0.7)[:N_PROPOSALS]
+        mark(1)
+        box_feats = self.box_pooler(d["feats"], [d["proposals"]])
+        mark(2)
+        if sync_free:
+            dk, _ = L.batched_nms_fixed(d["det_boxes"], d["det_scores"], d["det_classes"], 0.5)
+        else:
+            dk = L.batched_nms(d["det_boxes"], d["det_scores"], d["det_classes"], 0.5)
+        dk = dk[:N_DET]
+        det = d["det_boxes"][dk]
+        mark(3)
+        mask_feats = self.mask_pooler(d["feats"], [det])
+        mark(4)
+        pasted = L.paste_masks_in_image(d["masks"][: det.shape[0]], det, (IMG_H, IMG_W), 0.5)
+        mark(5)
+        return keep, box_feats, det, mask_feats, pasted
+
+
+# ----------------------------------------------------------------------------------------- reference (CPU) arm
+class ReferenceRunner:
+    """The reference's own CPU implementation of the path: torchvision CPU ops (the backend detectron2.layers calls:
+    roi_align.py:3,58 / nms.py:5-22), the per-level ROIPooler loop (poolers.py:245-263) and the CPU branch of
+    paste_masks_in_image (mask_ops.py:116-119: one mask at a time, skip_empty) restated in oracle/paste_ref.py."""
+
+    def __init__(self):
+        import torchvision
+        from oracle import paste_ref
+
+        self.tv = torchvision
+        self.paste = paste_ref.paste_masks_in_image_cpu
+
+    def pooler(self, feats, boxes, out):
+        tv = self.tv
+        sizes = torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]))
+        lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).to(torch.int64) - 2
+        rois = torch.cat([torch.zeros(len(boxes), 1), boxes], 1)
+        res = torch.zeros(len(boxes), C, out, out)
+        for l, (_, _, s) in enumerate(LEVELS):
+            inds = torch.nonzero(lv == l, as_tuple=True)[0]
+            res.index_put_((inds,), tv.ops.roi_align(feats[l], rois[inds], (out, out), s, 0, True))
+        return res
+
+    def step(self, d, frac=1.0):
+        tv = self.tv
+        n_rpn, n_prop = max(8, int(N_RPN_BOXES * frac)), max(4, int(N_PROPOSALS * frac))
+        n_cand, n_det = max(8, int(N_DET_CANDIDATES * frac)), max(2, int(N_DET * frac))
+        keep = tv.ops.boxes.batched_nms(d["rpn_boxes"][:n_rpn].float(), d["rpn_scores"][:n_rpn], d["rpn_levels"][:n_rpn], 0.7)
+        box_feats = self.pooler(d["feats"], d["proposals"][:n_prop], 7)
+        dk = tv.ops.boxes.batched_nms(d["det_boxes"][:n_cand].float(), d["det_scores"][:n_cand], d["det_classes"][:n_cand], 0.5)[:n_det]
+        det = d["det_boxes"][:n_cand][dk]
+        mask_feats = self.pooler(d["feats"], det, 14)
+        pasted = self.paste(d["masks"][: det.shape[0]], det, (IMG_H, IMG_W), 0.5)
+        return keep, box_feats, det, mask_feats, pasted
+
+
+def time_reference(steps, warmup, budget_s=150.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = ReferenceRunner()
+    d = make_image_inputs(0)
+    t0 = time.perf_counter()
+    ref.step(d, 0.125)
+    t_eighth = time.perf_counter() - t0
+    frac = 1.0
+    while frac > 1 / 64 and (steps + warmup) * t_eighth * 8 * frac > budget_s:
+        frac /= 2
+    for _ in range(warmup):
+        ref.step(d, frac)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step(d, frac)
+    dt = time.perf_counter() - t0
+    return frac * steps / dt, dt / steps * 1e3, frac, torch.get_num_threads()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML unavailable: report that instead of inventing clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    base = {"metric": METRIC, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "proposals_per_image": N_PROPOSALS, "rpn_boxes": N_RPN_BOXES,
+                       "det_candidates": N_DET_CANDIDATES, "detections": N_DET, "parallelism": "replicas (image-parallel, no data-path collective)"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, ms, frac, cores = time_reference(args.steps, max(args.warmup, 1))
+        line = dict(base)
+        line.update({"impl": "reference", "value": v, "ms_per_step": ms, "n_gpus": args.gpus,
+                     "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "reference",
+                                      "sample": "%.4g of one image's hot path per step (torchvision CPU roi_align/nms, reference "
+                                                "per-level ROIPooler loop, CPU paste port), %d threads" % (frac, cores)},
+                     "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    runner = OursRunner(dev)
+    NBUF = 3  # rotate over 3 distinct images so that every step reads cold feature maps (3 x 91 MB > 126 MB L2)
+    host = [make_image_inputs(1000 * rank + i) for i in range(NBUF)]
+    devin = [runner.to_device(h) for h in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value")
+    for i in range(max(args.warmup, 3)):
+        runner.step(devin[i % NBUF])
+    nstage = 6
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(nstage)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        runner.step(devin[i % NBUF], evs[i])
+    t_end.record()
+    barrier()
+    sampler.stop_flag = True
+    elapsed_ms = t_start.elapsed_time(t_end)
+    stage_names = ["rpn_nms", "box_pool", "det_nms", "mask_pool", "paste"]
+    stage_ms = [sum(evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(args.steps)) / args.steps for s in range(5)]
+
+    # ---------------- end to end through the reference-shaped API with HOST buffers
+    pinned = []
+    for h in host:
+        p = {}
+        for k, v in h.items():
+            p[k] = [t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()
+        pinned.append(p)
+    out_host = torch.empty((N_DET, IMG_H, IMG_W), dtype=torch.bool).pin_memory()
+    det_host = torch.empty((N_DET, 4), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        d = runner.to_device(pinned[i % NBUF])
+        keep, box_feats, det, mask_feats, pasted = runner.step(d, None, sync_free=False)
+        out_host[: pasted.shape[0]].copy_(pasted, non_blocking=True)
+        det_host[: det.shape[0]].copy_(det, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    sampler.join(timeout=1.0)
+
+    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = times.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (elapsed_ms / 1e3)
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = roi_align_algorithmic_bytes(host[0]["proposals"], 7, 7)
+    box_ms = stage_ms[1]
+    achieved = alg_bytes / (box_ms / 1e3) / 1e9
+    line = dict(base)
+    line.update({
+        "value": value, "ms_per_step": elapsed_ms / args.steps, "n_gpus": world,
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d_bytes(host[0]),
+                "d2h_bytes_per_step": out_host.numel() + det_host.numel() * 4},
+        "gpu_launches": OursRunner.KERNELS_PER_STEP * args.steps,
+        "clocks": sampler.summary(),
+        "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
+        "roofline": {"kernel": "roi_align_fwd_kernel (box pooler, 1000 RoIs x 256 ch x 7x7 over p2..p5)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                     "algorithmic_bytes": alg_bytes, "avg_launch_ms": box_ms, "traffic": None},
+    })
+    line["config"]["l2"] = "inputs rotate over 3 images (3 x 91 MB features) and each step writes 107 MB: > 126 MB L2"
+    if world == 1:
+        v, ms, frac, cores = time_reference(3, 1, budget_s=30.0)
+        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "reference",
+                                "sample": "3 steps x %.4g of one image's hot path (torchvision CPU roi_align/nms + reference "
+                                          "ROIPooler loop + CPU paste port), %d threads" % (frac, cores)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,16 @@ class DcnParams(C.Structure):
                                         "pad_w", "dil_h", "dil_w", "groups", "deformable_groups")]
 
 
+MAX_LEVELS = 8
+
+
+class Pyramid(C.Structure):
+    _fields_ = [("num_levels", C.c_int), ("feat", C.c_void_p * MAX_LEVELS), ("grad", C.c_void_p * MAX_LEVELS),
+                ("H", C.c_int * MAX_LEVELS), ("W", C.c_int * MAX_LEVELS), ("scale", C.c_float * MAX_LEVELS),
+                ("min_level", C.c_int), ("max_level", C.c_int), ("canonical_level", C.c_int),
+                ("canonical_box_size", C.c_float)]
+
+
 def _declare(lib):
     vp, f32p, i64p, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     i, f, d, sz, i64 = C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_int64
@@ -31,6 +41,8 @@ def _declare(lib):
         "d2b_arch": (C.c_char_p, []),
         "d2b_roi_align_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, i, f32p, vp]),
         "d2b_roi_align_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, i, f32p, vp]),
+        "d2b_roi_pooler_forward": (i, [C.POINTER(Pyramid), i, i, f32p, i, i, i, i, i, f32p, vp]),
+        "d2b_roi_pooler_backward": (i, [C.POINTER(Pyramid), i, i, f32p, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
         "d2b_roi_align_rotated_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
         "d2b_nms_workspace_bytes": (sz, [i64, i]),

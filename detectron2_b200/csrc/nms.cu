@@ -312,13 +312,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
   for (int i = tid; i < nb; i += kScanThreads) removed[i] = 0ull;
   if (tid == 0) s_count = 0;
 
-  // prefetch state for the block being processed: column words w = b + 1 + warp + 32*c, rows 2*lane, 2*lane+1
+  // prefetch state for the block being processed: column words w = b + 1 + warp + kScanWarps*c, rows 2*lane, 2*lane+1
   ulonglong2 pre[kMaxColsPerWarp];
   auto prefetch = [&](int b) {
     const int r = b * 64 + 2 * lane;
 #pragma unroll
     for (int c = 0; c < kMaxColsPerWarp; ++c) {
-      const int w = b + 1 + warp + 32 * c;
+      const int w = b + 1 + warp + kScanWarps * c;
       pre[c] = make_ulonglong2(0ull, 0ull);
       if (w < nb) {
         const unsigned long long* p = maskT + (size_t)w * M + r;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
     const unsigned long long k1 = (kept >> (2 * lane + 1)) & 1ull ? ~0ull : 0ull;
 #pragma unroll
     for (int c = 0; c < kMaxColsPerWarp; ++c) {
-      const int w = b + 1 + warp + 32 * c;
+      const int w = b + 1 + warp + kScanWarps * c;
       if (w < nb) {  // warp-uniform
         unsigned long long v = (pre[c].x & k0) | (pre[c].y & k1);
         unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
       }
     }
     // columns beyond the register-prefetched window (very large M): plain loads
-    for (int w = b + 1 + warp + 32 * kMaxColsPerWarp; w < nb; w += 32) {
+    for (int w = b + 1 + warp + kScanWarps * kMaxColsPerWarp; w < nb; w += kScanWarps) {
       const int r = b * 64 + 2 * lane;
       unsigned long long v = 0ull;
       if (r < M) v |= maskT[(size_t)w * M + r] & k0;

@@ -26,6 +26,29 @@ struct RoiGeom {
   float ctr_h, ctr_w, cos_t, sin_t;
 };
 
+// Feature pyramid passed by value to the kernels (single-level ops use num_levels == 1).
+struct Pyr {
+  int num_levels;
+  const float* feat[D2B_MAX_LEVELS];
+  float* grad[D2B_MAX_LEVELS];
+  int H[D2B_MAX_LEVELS], W[D2B_MAX_LEVELS];
+  float scale[D2B_MAX_LEVELS];
+  int min_level, max_level, canonical_level;
+  float canonical_box_size;
+};
+
+// FPN level of a box: detectron2/modeling/poolers.py:54-62 (assign_boxes_to_levels), fp32 like torch:
+//   floor(canonical_level + log2(sqrt(area) / canonical_box_size + 1e-8)), clamped to [min_level, max_level]
+__device__ __forceinline__ int pick_level(const Pyr& P, const float* __restrict__ roi) {
+  if (P.num_levels == 1) return 0;
+  const float area = (roi[3] - roi[1]) * (roi[4] - roi[2]);
+  const float size = sqrtf(area);
+  float lvl = floorf((float)P.canonical_level + log2f(size / P.canonical_box_size + 1e-8f));
+  lvl = fminf(fmaxf(lvl, (float)P.min_level), (float)P.max_level);  // NaN (negative area) -> min_level like torch.clamp? see below
+  if (!(lvl == lvl)) lvl = (float)P.min_level;
+  return (int)lvl - P.min_level;
+}
+
 template <bool ROT>
 __device__ __forceinline__ RoiGeom load_geom(const float* __restrict__ roi, float scale, int PH, int PW, int sr,
                                              int aligned) {
@@ -102,16 +125,18 @@ __device__ __forceinline__ Tap1 make_tap1(float v, int size) {
 // ------------------------------------------------------------------ axis-aligned forward
 // smem: ytab[PH*gh], xtab[PW*gw]  (Tap1 each). Falls back to on-the-fly taps when the tables do not fit.
 template <int MAXTAB>
-__global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const float* __restrict__ in,
-                                                                 const float* __restrict__ rois, float scale, int C,
-                                                                 int H, int W, int PH, int PW, int sr, int aligned,
-                                                                 int c_per_cta, float* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const Pyr P, const float* __restrict__ rois, int C,
+                                                                 int PH, int PW, int sr, int aligned, int c_per_cta,
+                                                                 float* __restrict__ out) {
   __shared__ Tap1 ytab[MAXTAB];
   __shared__ Tap1 xtab[MAXTAB];
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * c_per_cta;
   const int cn = min(c_per_cta, C - c0);
-  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, scale, PH, PW, sr, aligned);
+  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const float* __restrict__ in = P.feat[lvl];
+  const int H = P.H[lvl], W = P.W[lvl];
+  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
   const int ny = PH * g.gh, nx = PW * g.gw;
   const bool tab = (ny <= MAXTAB) && (nx <= MAXTAB);
   if (tab) {
@@ -242,14 +267,16 @@ __global__ void __launch_bounds__(kThreads) roi_align_rot_fwd_kernel(const float
 // Lanes of a warp cover neighbouring bins of one channel, so their taps collide on the same pixels:
 // red.global.add (no return value) lets the L2 atomic unit merge them.
 template <bool ROT>
-__global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const float* __restrict__ gout,
-                                                                 const float* __restrict__ rois, float scale, int C,
-                                                                 int H, int W, int PH, int PW, int sr, int aligned,
-                                                                 int c_per_cta, float* __restrict__ gin) {
+__global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, const float* __restrict__ gout,
+                                                                 const float* __restrict__ rois, int C, int PH, int PW,
+                                                                 int sr, int aligned, int c_per_cta) {
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * c_per_cta;
   const int cn = min(c_per_cta, C - c0);
-  const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), scale, PH, PW, sr, aligned);
+  const int lvl = ROT ? 0 : pick_level(P, rois + (size_t)k * 5);
+  float* __restrict__ gin = P.grad[lvl];
+  const int H = P.H[lvl], W = P.W[lvl];
+  const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), P.scale[lvl], PH, PW, sr, aligned);
   if (g.gh <= 0 || g.gw <= 0) return;
   const int bins = PH * PW;
   const int total = cn * bins;
@@ -293,10 +320,70 @@ D2B_API int d2b_roi_align_forward(const float* input, int N, int C, int H, int W
   if (K == 0 || C == 0) return D2B_OK;
   if (!input || !rois || !out || N <= 0 || H <= 0 || W <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0)
     return D2B_EINVAL;
+  Pyr P = {};
+  P.num_levels = 1;
+  P.feat[0] = input;
+  P.H[0] = H;
+  P.W[0] = W;
+  P.scale[0] = spatial_scale;
   int cpc = pick_c_per_cta(K, C);
   dim3 grid(K, d2b_cdiv(C, cpc));
-  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-      input, rois, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, aligned, cpc, out);
+  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, rois, C, pooled_h, pooled_w,
+                                                                         sampling_ratio, aligned, cpc, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+static bool make_pyr(const d2b_pyramid* pyr, Pyr& P) {
+  if (!pyr || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS) return false;
+  P = Pyr{};
+  P.num_levels = pyr->num_levels;
+  for (int l = 0; l < pyr->num_levels; ++l) {
+    if (pyr->H[l] <= 0 || pyr->W[l] <= 0) return false;
+    P.feat[l] = pyr->feat[l];
+    P.grad[l] = pyr->grad[l];
+    P.H[l] = pyr->H[l];
+    P.W[l] = pyr->W[l];
+    P.scale[l] = pyr->scale[l];
+  }
+  P.min_level = pyr->min_level;
+  P.max_level = pyr->max_level;
+  P.canonical_level = pyr->canonical_level;
+  P.canonical_box_size = pyr->canonical_box_size;
+  if (P.num_levels > 1 && P.max_level - P.min_level + 1 != P.num_levels) return false;
+  return true;
+}
+
+D2B_API int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                   int pooled_w, int sampling_ratio, int aligned, float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  Pyr P;
+  if (!make_pyr(pyr, P) || !rois || !out || N <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0) return D2B_EINVAL;
+  for (int l = 0; l < P.num_levels; ++l)
+    if (!P.feat[l]) return D2B_EINVAL;
+  int cpc = pick_c_per_cta(K, C);
+  dim3 grid(K, d2b_cdiv(C, cpc));
+  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, rois, C, pooled_h, pooled_w,
+                                                                         sampling_ratio, aligned, cpc, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
+                                    int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
+  Pyr P;
+  if (!make_pyr(pyr, P) || N < 0 || C < 0) return D2B_EINVAL;
+  for (int l = 0; l < P.num_levels; ++l) {
+    if (!P.grad[l]) return D2B_EINVAL;
+    size_t bytes = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
+    if (bytes) D2B_CUDA(cudaMemsetAsync(P.grad[l], 0, bytes, (cudaStream_t)stream));
+  }
+  if (K == 0 || C == 0 || N == 0) return D2B_OK;
+  if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  int cpc = pick_c_per_cta(K, C);
+  dim3 grid(K, d2b_cdiv(C, cpc));
+  roi_align_bwd_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, grad_out, rois, C, pooled_h, pooled_w,
+                                                                           sampling_ratio, aligned, cpc);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
@@ -324,10 +411,16 @@ static int roi_bwd_launch(const float* grad_out, const float* rois, int K, float
   if (bytes) D2B_CUDA(cudaMemsetAsync(grad_in, 0, bytes, (cudaStream_t)stream));
   if (K == 0 || bytes == 0) return D2B_OK;
   if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  Pyr P = {};
+  P.num_levels = 1;
+  P.grad[0] = grad_in;
+  P.H[0] = H;
+  P.W[0] = W;
+  P.scale[0] = spatial_scale;
   int cpc = pick_c_per_cta(K, C);
   dim3 grid(K, d2b_cdiv(C, cpc));
-  roi_align_bwd_kernel<ROT><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-      grad_out, rois, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, aligned, cpc, grad_in);
+  roi_align_bwd_kernel<ROT><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, grad_out, rois, C, pooled_h, pooled_w,
+                                                                         sampling_ratio, aligned, cpc);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

@@ -91,6 +91,90 @@ def _roi_align_bwd(ctx, grad):
 roi_align_op.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
 
 
+# ----------------------------------------------------------------------------------- fused multi-level pooler
+def _pyramid(feats, grads, scales, min_level, max_level, canonical_level, canonical_box_size):
+    P = _C.Pyramid()
+    P.num_levels = len(feats)
+    for l, t in enumerate(feats):
+        P.feat[l] = t.data_ptr()
+        P.grad[l] = grads[l].data_ptr() if grads is not None else None
+        P.H[l], P.W[l] = t.shape[2], t.shape[3]
+        P.scale[l] = scales[l]
+    P.min_level, P.max_level, P.canonical_level = min_level, max_level, canonical_level
+    P.canonical_box_size = canonical_box_size
+    return P
+
+
+@torch.library.custom_op("d2b200::roi_pooler", mutates_args=(), device_types="cuda")
+def roi_pooler_op(feats: List[Tensor], rois: Tensor, scales: List[float], pooled_h: int, pooled_w: int,
+                  sampling_ratio: int, aligned: bool, min_level: int, max_level: int, canonical_level: int,
+                  canonical_box_size: float) -> Tensor:
+    _C.require_cuda(rois, *feats)
+    if len(feats) < 1 or len(feats) > _C.MAX_LEVELS or len(feats) != len(scales):
+        raise RuntimeError("roi_pooler: need 1..%d feature levels with one scale each" % _C.MAX_LEVELS)
+    fs = [_f32c(t) for t in feats]
+    r = _f32c(rois)
+    n, c = fs[0].shape[:2]
+    k = r.shape[0]
+    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=r.device)
+    if out.numel():
+        P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size)
+        with torch.cuda.device(r.device):
+            check(_C.lib().d2b_roi_pooler_forward(C.byref(P), n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio,
+                                                  int(aligned), ptr(out), stream_ptr(r.device)), "roi_pooler_forward")
+    return out.to(feats[0].dtype)
+
+
+@roi_pooler_op.register_fake
+def _(feats, rois, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_level, max_level, canonical_level,
+      canonical_box_size):
+    return feats[0].new_empty((rois.shape[0], feats[0].shape[1], pooled_h, pooled_w))
+
+
+@torch.library.custom_op("d2b200::roi_pooler_backward", mutates_args=(), device_types="cuda")
+def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales: List[float], pooled_h: int,
+                           pooled_w: int, sampling_ratio: int, aligned: bool, min_level: int, max_level: int,
+                           canonical_level: int, canonical_box_size: float) -> List[Tensor]:
+    _C.require_cuda(grad, rois)
+    g, r = _f32c(grad), _f32c(rois)
+    nl = len(scales)
+    n, c = shapes[0], shapes[1]
+    grads = [torch.empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=torch.float32, device=g.device)
+             for l in range(nl)]
+    P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size)
+    with torch.cuda.device(g.device):
+        check(_C.lib().d2b_roi_pooler_backward(C.byref(P), n, c, ptr(g), ptr(r), r.shape[0], pooled_h, pooled_w,
+                                               sampling_ratio, int(aligned), stream_ptr(g.device)),
+              "roi_pooler_backward")
+    return grads
+
+
+@roi_pooler_backward_op.register_fake
+def _(grad, rois, shapes, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_level, max_level, canonical_level,
+      canonical_box_size):
+    n, c = shapes[0], shapes[1]
+    return [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
+
+
+def _pooler_setup(ctx, inputs, output):
+    feats, rois, scales, ph, pw, sr, aligned, lo, hi, cl, cs = inputs
+    ctx.save_for_backward(rois)
+    shapes = [feats[0].shape[0], feats[0].shape[1]]
+    for t in feats:
+        shapes += [t.shape[2], t.shape[3]]
+    ctx.args = (shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, [t.dtype for t in feats])
+
+
+def _pooler_bwd(ctx, grad):
+    (rois,) = ctx.saved_tensors
+    shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, dts = ctx.args
+    grads = roi_pooler_backward_op(grad, rois, shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs)
+    return [g.to(dt) for g, dt in zip(grads, dts)], None, None, None, None, None, None, None, None, None, None
+
+
+roi_pooler_op.register_autograd(_pooler_bwd, setup_context=_pooler_setup)
+
+
 @torch.library.custom_op("d2b200::roi_align_rotated", mutates_args=(), device_types="cuda")
 def roi_align_rotated_op(input: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
                          sampling_ratio: int) -> Tensor:

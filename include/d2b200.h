@@ -50,6 +50,29 @@ int d2b_roi_align_backward(const float* grad_out, const float* rois, int K, floa
                            int pooled_h, int pooled_w, int N, int C, int H, int W,
                            int sampling_ratio, int aligned, float* grad_in, void* stream);
 
+/* ---- Multi-level RoI pooler (fused) --------------------------------------------------------
+ * Replaces the per-level loop of detectron2/modeling/poolers.py:206-263 (ROIPooler.forward with
+ * pooler_type "ROIAlign"/"ROIAlignV2"): level assignment (poolers.py:23-59,
+ * floor(canonical_level + log2(sqrt(area)/canonical_box_size + 1e-8)) clamped), the per-level
+ * nonzero / gather / roi_align / index_put_ -- one launch, no host synchronisation.
+ * feat[l] is [N,C,H[l],W[l]] fp32 (level min_level + l), scale[l] its spatial scale; grad[l] is
+ * only read by the backward (fully written: zero-filled inside, then accumulated).
+ * rois [K,5] in image coordinates, out / grad_out [K,C,PH,PW]. */
+#define D2B_MAX_LEVELS 8
+typedef struct {
+  int num_levels;
+  const float* feat[D2B_MAX_LEVELS];
+  float* grad[D2B_MAX_LEVELS];
+  int H[D2B_MAX_LEVELS], W[D2B_MAX_LEVELS];
+  float scale[D2B_MAX_LEVELS];
+  int min_level, max_level, canonical_level;
+  float canonical_box_size;
+} d2b_pyramid;
+int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                           int pooled_w, int sampling_ratio, int aligned, float* out, void* stream);
+int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
+                            int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream);
+
 /* ---- RoIAlign, rotated ------------------------------------------------------------------
  * Replaces torch.ops.detectron2.roi_align_rotated_forward / _backward
  * (csrc/vision.cpp:118-119, csrc/ROIAlignRotated/ROIAlignRotated.h:50-113).

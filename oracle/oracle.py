@@ -35,6 +35,12 @@ def load_reference():
     Returns True when available."""
     global _ref_loaded
     if _ref_loaded is None:
+        try:  # another library (the product's ops.py) already DEFined the schemas: loading would abort the process
+            torch._C._dispatch_find_schema_or_throw("detectron2::nms_rotated", "")
+            _ref_loaded = False
+            return False
+        except RuntimeError:
+            pass
         so = _build.build_ref()
         if so is None or not os.path.exists(so):
             _ref_loaded = False

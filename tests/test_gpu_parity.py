@@ -381,3 +381,50 @@ def test_paste_masks_full_size_vs_oracle(L):
     area = (cb[:, 2] - cb[:, 0]) * (cb[:, 3] - cb[:, 1])
     per = 2 * ((cb[:, 2] - cb[:, 0]) + (cb[:, 3] - cb[:, 1]))
     assert ((cnt - area).abs() <= per + 4).all()
+
+
+# ------------------------------------------------------------------------------- fused multi-level ROIPooler
+def _oracle_pooler(feats, boxes, scales, out, sr, aligned):
+    # the reference's per-level loop (detectron2/modeling/poolers.py:23-59,245-263) on top of the oracle RoIAlign
+    sizes = torch.sqrt((boxes[:, 3] - boxes[:, 1]) * (boxes[:, 4] - boxes[:, 2]))
+    lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).to(torch.int64) - 2
+    res = torch.zeros(len(boxes), feats[0].shape[1], out, out)
+    for l, s in enumerate(scales):
+        inds = torch.nonzero(lv == l, as_tuple=True)[0]
+        res[inds] = orc.roi_align_forward(feats[l], boxes[inds], s, out, out, sr, aligned)
+    return res, lv
+
+
+@pytest.mark.parametrize("out,ptype", [(7, "ROIAlignV2"), (14, "ROIAlignV2"), (7, "ROIAlign")])
+def test_roi_pooler_fused_vs_reference_loop(out, ptype):
+    from detectron2_b200.poolers import ROIPooler, assign_boxes_to_levels
+
+    g = torch.Generator().manual_seed(out)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    feats = [torch.randn(2, 32, 200 // 2 ** i, 336 // 2 ** i, generator=g) for i in range(4)]
+    per_img = []
+    for _ in range(2):
+        s = torch.exp(torch.rand(150, generator=g) * (math.log(700) - math.log(8)) + math.log(8))
+        ctr = torch.rand(150, 2, generator=g) * torch.tensor([1344.0, 800.0])
+        ar = torch.exp((torch.rand(150, generator=g) - 0.5) * 1.4)
+        wh = torch.stack([s * ar.sqrt(), s / ar.sqrt()], 1)
+        per_img.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+    # boxes sitting exactly on level boundaries (sqrt(area) = 112, 224, 448)
+    per_img[0][:3] = torch.tensor([[100.0, 100, 212, 212], [100, 100, 324, 324], [100, 100, 548, 548]])
+    rois = torch.cat([torch.cat([torch.full((150, 1), float(i)), b], 1) for i, b in enumerate(per_img)])
+    aligned = ptype == "ROIAlignV2"
+    ref, lv = _oracle_pooler(feats, rois, scales, out, 0, aligned)
+    pooler = ROIPooler(out, scales, 0, ptype)
+    fg = [f.to(DEV).requires_grad_(True) for f in feats]
+    boxes_dev = [b.to(DEV) for b in per_img]
+    y = pooler(fg, boxes_dev)
+    assert torch.equal(assign_boxes_to_levels(boxes_dev, 2, 5, 224, 4).cpu(), lv)
+    ok, err = rel_close(y, ref)
+    assert ok, err
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go.to(DEV))
+    for l, s in enumerate(scales):
+        inds = torch.nonzero(lv == l, as_tuple=True)[0]
+        gref = orc.roi_align_backward(go[inds], rois[inds], s, out, out, 2, 32, feats[l].shape[2], feats[l].shape[3], 0, aligned)
+        ok, err = rel_close(fg[l].grad, gref, atol=2e-4)
+        assert ok, (l, err)

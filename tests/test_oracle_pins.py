@@ -237,3 +237,30 @@ def test_live_vs_compiled_reference():
     s = torch.rand(n, generator=g)
     for thr in (0.2, 0.5):
         assert torch.equal(orc.nms_rotated(b, s, thr), torch.ops.detectron2.nms_rotated(b, s, thr))
+
+
+def test_paste_port_matches_fixture_and_reference(golden):
+    """oracle/paste_ref.py (the CPU-baseline port) against the golden fixture, and against the real reference
+    function when /root/reference is present (authoring container)."""
+    import importlib.util
+    import os
+
+    from oracle import paste_ref
+
+    d = golden("paste_masks")
+    h, w = [int(v) for v in d["hw"]]
+    got = paste_ref.paste_masks_in_image_cpu(T(d["masks"]), T(d["boxes"]), (h, w), 0.5)
+    keep = [i for i in range(9) if i != 1]  # box 1 is degenerate (x1 == x0): nan grid, not a baseline case
+    assert torch.equal(got[keep], T(d["out_bool"])[keep])
+    path = "/root/reference/detectron2/layers/mask_ops.py"
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("ref_mask_ops", path)
+        mo = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mo)
+        g = torch.Generator().manual_seed(8)
+        masks = torch.rand(6, 28, 28, generator=g)
+        ctr = torch.rand(6, 2, generator=g) * torch.tensor([200.0, 150.0])
+        wh = 10 + torch.rand(6, 2, generator=g) * 90
+        boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        assert torch.equal(paste_ref.paste_masks_in_image_cpu(masks, boxes, (150, 200), 0.5),
+                           mo.paste_masks_in_image(masks, boxes, (150, 200), 0.5))
