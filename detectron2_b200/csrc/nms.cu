@@ -300,63 +300,100 @@ constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kMaxColsPerWarp = 10;  // register-prefetched column words per warp (covers M <= 64*16*10 = 10240)
 
 // Greedy scan over the bitmask.  dynamic smem: removed[nb] (uint64).
+// Per 64-box block b:  (B) thread 0 resolves the intra-block chain from removed[b] and the diagonal word of each row;
+// (C) the warps OR the kept rows into the `removed` words of the later column blocks.  Everything the next block needs
+// from global memory (its diagonal words, its rows of the later columns) is requested one full iteration ahead and
+// parked in registers, so the serial chain never waits on L2.
 __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigned long long* __restrict__ maskT,
                                                                    const int* __restrict__ order, int M, int nb,
                                                                    long long* __restrict__ keep,
                                                                    long long* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];
-  __shared__ unsigned long long s_diag[64];
+  __shared__ __align__(16) unsigned long long s_diag[2][64];
   __shared__ unsigned long long s_kept;
-  __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < nb; i += kScanThreads) removed[i] = 0ull;
-  if (tid == 0) s_count = 0;
+  int count = 0;  // kept so far; every thread tracks it from the broadcast `kept` words
 
-  // prefetch state for the block being processed: column words w = b + 1 + warp + kScanWarps*c, rows 2*lane, 2*lane+1
-  ulonglong2 pre[kMaxColsPerWarp];
-  auto prefetch = [&](int b) {
+  // rows 2*lane, 2*lane+1 of block b, column words w = b + 1 + warp + kScanWarps*c
+  auto fetch = [&](int b, ulonglong2 (&dst)[kMaxColsPerWarp]) {
     const int r = b * 64 + 2 * lane;
 #pragma unroll
     for (int c = 0; c < kMaxColsPerWarp; ++c) {
       const int w = b + 1 + warp + kScanWarps * c;
-      pre[c] = make_ulonglong2(0ull, 0ull);
-      if (w < nb) {
+      dst[c] = make_ulonglong2(0ull, 0ull);
+      if (b < nb && w < nb) {
         const unsigned long long* p = maskT + (size_t)w * M + r;
         if (r + 1 < M) {
-          if ((M & 1) == 0) pre[c] = *reinterpret_cast<const ulonglong2*>(p);  // 16 B aligned when M is even
-          else pre[c] = make_ulonglong2(p[0], p[1]);
+          if ((M & 1) == 0) dst[c] = *reinterpret_cast<const ulonglong2*>(p);  // 16 B aligned when M is even
+          else dst[c] = make_ulonglong2(p[0], p[1]);
         } else if (r < M) {
-          pre[c].x = p[0];
+          dst[c].x = p[0];
         }
       }
     }
   };
-  if (nb > 0) {
-    prefetch(0);
-    if (tid < 64) s_diag[tid] = (tid < M) ? maskT[tid] : 0ull;
-  }
+  auto diag_word = [&](int b) -> unsigned long long {
+    const int r = b * 64 + tid;
+    return (b < nb && tid < 64 && r < M) ? maskT[(size_t)b * M + r] : 0ull;
+  };
+  ulonglong2 bufA[kMaxColsPerWarp], bufB[kMaxColsPerWarp];
+  fetch(0, bufA);
+  if (tid < 64) s_diag[0][tid] = diag_word(0);
+  unsigned long long dnext = diag_word(1);
   __syncthreads();
 
-  for (int b = 0; b < nb; ++b) {
+  // one block of 64 boxes; `cur` holds its rows (requested one iteration ago), `nxt` receives the next block's rows.
+  // The two register buffers ping-pong (no copies: a copy would be a use and would expose the load latency).
+  auto process = [&](int b, ulonglong2 (&cur)[kMaxColsPerWarp], ulonglong2 (&nxt)[kMaxColsPerWarp]) {
     const int nrow = min(64, M - b * 64);
-    // ---- step B: one thread resolves the intra-block chain
+    // ---- step B: intra-block chain.  One thread, branch-free: per row the dependent path is
+    //      bit test -> mask -> and/or (about four ALU latencies); the diagonal words are pre-read from shared memory
+    //      sixteen rows at a time so that no load sits on the chain.
     if (tid == 0) {
-      unsigned long long rem = removed[b];
-      unsigned long long d[64];
+      const unsigned long long rem = removed[b];
+      unsigned rlo = (unsigned)rem, rhi = (unsigned)(rem >> 32), klo = 0u, khi = 0u;
+      const ulonglong2* dg = reinterpret_cast<const ulonglong2*>(s_diag[b & 1]);
+      const unsigned vlo = nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u);               // valid rows 0..31
+      const unsigned vhi = nrow >= 64 ? 0xffffffffu : (nrow > 32 ? ((1u << (nrow - 32)) - 1u) : 0u);  // rows 32..63
 #pragma unroll
-      for (int i = 0; i < 64; ++i) d[i] = s_diag[i];
-      unsigned long long kept = 0ull;
+      for (int blk = 0; blk < 2; ++blk) {
+        ulonglong2 d[8];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const bool alive = (i < nrow) && !((rem >> i) & 1ull);
-        kept |= alive ? (1ull << i) : 0ull;
-        rem |= alive ? d[i] : 0ull;
+        for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int i = blk * 16 + q;
+          const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
+          const unsigned m = 0u - ((~rlo & vlo) >> i & 1u);  // all-ones when row i is alive
+          klo |= m & (1u << i);
+          rlo |= m & (unsigned)dw;
+          rhi |= m & (unsigned)(dw >> 32);
+        }
       }
-      s_kept = kept;
+#pragma unroll
+      for (int blk = 2; blk < 4; ++blk) {
+        ulonglong2 d[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int i = (blk - 2) * 16 + q;
+          const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
+          const unsigned m = 0u - ((~rhi & vhi) >> i & 1u);
+          khi |= m & (1u << i);
+          rhi |= m & (unsigned)(dw >> 32);
+        }
+      }
+      s_kept = ((unsigned long long)khi << 32) | klo;
     }
     __syncthreads();
     const unsigned long long kept = s_kept;
-    const int base = s_count;
+    const int base = count;
+    // requests for block b+1 / b+2 go out now and are consumed one iteration later
+    fetch(b + 1, nxt);
+    if (tid < 64) s_diag[(b + 1) & 1][tid] = dnext;
+    dnext = diag_word(b + 2);
     // ---- emit kept indices of this block in score order
     if (tid < 64 && ((kept >> tid) & 1ull)) {
       const int rank = __popcll(kept & ((1ull << tid) - 1ull));
@@ -369,7 +406,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
     for (int c = 0; c < kMaxColsPerWarp; ++c) {
       const int w = b + 1 + warp + kScanWarps * c;
       if (w < nb) {  // warp-uniform
-        unsigned long long v = (pre[c].x & k0) | (pre[c].y & k1);
+        unsigned long long v = (cur[c].x & k0) | (cur[c].y & k1);
         unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
         unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
         if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
@@ -385,18 +422,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
       unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
       if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
     }
-    __syncthreads();  // s_kept / s_count / s_diag consumed, removed[] updated
-    if (tid == 0) s_count = base + __popcll(kept);
-    if (b + 1 < nb) {
-      prefetch(b + 1);
-      if (tid < 64) {
-        const int r = (b + 1) * 64 + tid;
-        s_diag[tid] = (r < M) ? maskT[(size_t)(b + 1) * M + r] : 0ull;
-      }
-    }
-    __syncthreads();
+    count = base + __popcll(kept);
+    __syncthreads();  // removed[], s_diag[(b+1)&1] visible; s_kept consumed
+  };
+  for (int b = 0; b < nb; b += 2) {
+    process(b, bufA, bufB);
+    if (b + 1 < nb) process(b + 1, bufB, bufA);
   }
-  if (tid == 0) *num_keep = (long long)s_count;
+  if (tid == 0) *num_keep = (long long)count;
 }
 
 struct NmsWorkspace {

@@ -23,6 +23,31 @@ __device__ __forceinline__ float sample_coord(float p, float b0, float b1, float
   return ((g + 1.f) * M - 1.f) / 2.f;
 }
 
+// exact value of one output pixel (reference expression order, see file header)
+__device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask, int M, float fM, int px, int py,
+                                                float x0, float y0, float x1, float y1, float threshold) {
+  const float ix = sample_coord((float)px, x0, x1, fM);
+  const float iy = sample_coord((float)py, y0, y1, fM);
+  float v = 0.f;
+  // in-range test written so that NaN / inf (degenerate boxes) fall through to 0
+  if (ix > -1.f && ix < fM && iy > -1.f && iy < fM) {
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int xw = (int)fx, yn = (int)fy, xe = xw + 1, ys = yn + 1;
+    const float wx1 = ix - fx, wx0 = (float)xe - ix, wy1 = iy - fy, wy0 = (float)ys - iy;
+    const bool okw = xw >= 0, oke = xe < M, okn = yn >= 0, oks = ys < M;
+    if (okn && okw) v += smask[yn * M + xw] * (wx0 * wy0);
+    if (okn && oke) v += smask[yn * M + xe] * (wx1 * wy0);
+    if (oks && okw) v += smask[ys * M + xw] * (wx0 * wy1);
+    if (oks && oke) v += smask[ys * M + xe] * (wx1 * wy1);
+  }
+  return threshold >= 0.f ? (v >= threshold ? 1u : 0u) : (uint32_t)(uint8_t)(v * 255.f);
+}
+
+// grid (gx, N).  Two phases per mask:
+//   1. every 16-byte chunk of the output plane that cannot see the mask (conservative rectangle test) is written as
+//      one 128-bit store of the "outside" value -- this is ~90% of the bytes and runs at store bandwidth;
+//   2. the rows/columns of the conservative rectangle, widened to whole 16-byte chunks, are evaluated exactly with one
+//      pixel per lane, so a warp works on 32 neighbouring pixels (no divergence between inside / outside lanes).
 __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __restrict__ masks,
                                                                const float* __restrict__ boxes, int M, int H, int W,
                                                                float threshold, uint8_t* __restrict__ out,
@@ -34,59 +59,79 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
   const float x0 = boxes[4 * n], y0 = boxes[4 * n + 1], x1 = boxes[4 * n + 2], y1 = boxes[4 * n + 3];
   __syncthreads();
   const float fM = (float)M;
+  // Conservative support of the pasted mask: outside [cx0,cx1] x [ry0,ry1] every sample point lies >= 1.5 px beyond the
+  // mask's (-1, M) support, far more than fp32 rounding can move it, so the value there is exactly that of v = 0.
+  // Degenerate / non-finite boxes disable the shortcut (everything is evaluated exactly).
+  int cx0 = 0, cx1 = W - 1, ry0 = 0, ry1 = H - 1;
+  {
+    const float bw = x1 - x0, bh = y1 - y0;
+    if (W >= 2 * kPix && bw > 0.f && bh > 0.f && bw < 1e8f && bh < 1e8f && fabsf(x0) < 1e8f && fabsf(y0) < 1e8f) {
+      const float fx0 = floorf(x0 - bw / fM) - 2.f, fx1 = ceilf(x1 + bw / fM) + 2.f;
+      const float fy0 = floorf(y0 - bh / fM) - 2.f, fy1 = ceilf(y1 + bh / fM) + 2.f;
+      cx0 = (int)fmaxf(fx0, 0.f);
+      cx1 = (int)fminf(fx1, (float)(W - 1));
+      ry0 = (int)fmaxf(fy0, 0.f);
+      ry1 = (int)fminf(fy1, (float)(H - 1));
+    }
+  }
+  const bool empty = cx1 < cx0 || ry1 < ry0;  // rectangle entirely off the image
+  const uint32_t zbyte = threshold >= 0.f ? ((0.f >= threshold) ? 1u : 0u) : 0u;
+  const uint32_t zword = zbyte * 0x01010101u;
   const long long plane = (long long)H * W;
   uint8_t* __restrict__ obase = out + (size_t)n * plane;
-  // obase may be misaligned w.r.t. 16 B when H*W is not a multiple of 16: chunk 0 starts at the first aligned byte,
-  // the (<16 byte) head is handled by the last chunk id.
+  // obase may be misaligned w.r.t. 16 B when H*W is not a multiple of 16: chunk c covers [head + 16c, head + 16c + 16)
   const int head = (int)((16 - ((uintptr_t)obase & 15)) & 15);
-  for (long long chunk = (long long)blockIdx.x * kThreads + threadIdx.x; chunk <= chunks_per_mask;
-       chunk += (long long)gridDim.x * kThreads) {
-    long long start, end;
-    if (chunk == chunks_per_mask) {  // head
-      start = 0;
-      end = head < plane ? head : plane;
-    } else {
-      start = head + chunk * kPix;
-      end = start + kPix;
-      if (end > plane) end = plane;
-    }
-    if (start >= end) continue;
-    int py = (int)(start / W);
-    int px = (int)(start - (long long)py * W);
-    uint32_t pk[4] = {0u, 0u, 0u, 0u};
-    float iy = sample_coord((float)py, y0, y1, fM);
-    const int cnt = (int)(end - start);
-#pragma unroll
-    for (int j = 0; j < kPix; ++j) {
-      if (j >= cnt) break;
-      float ix = sample_coord((float)px, x0, x1, fM);
-      float v = 0.f;
-      // in-range test written so that NaN / inf (degenerate boxes) fall through to 0
-      if (ix > -1.f && ix < fM && iy > -1.f && iy < fM) {
-        float fx = floorf(ix), fy = floorf(iy);
-        int xw = (int)fx, yn = (int)fy, xe = xw + 1, ys = yn + 1;
-        float wx1 = ix - fx, wx0 = (float)xe - ix, wy1 = iy - fy, wy0 = (float)ys - iy;
-        bool okw = xw >= 0, oke = xe < M, okn = yn >= 0, oks = ys < M;
-        if (okn && okw) v += smask[yn * M + xw] * (wx0 * wy0);
-        if (okn && oke) v += smask[yn * M + xe] * (wx1 * wy0);
-        if (oks && okw) v += smask[ys * M + xw] * (wx0 * wy1);
-        if (oks && oke) v += smask[ys * M + xe] * (wx1 * wy1);
-      }
-      uint32_t byte = threshold >= 0.f ? (v >= threshold ? 1u : 0u) : (uint32_t)(uint8_t)(v * 255.f);
-      pk[j >> 2] |= byte << ((j & 3) * 8);
-      if (++px == W) {
-        px = 0;
-        ++py;
-        iy = sample_coord((float)py, y0, y1, fM);
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+
+  // ---- phase 1: chunks that cannot see the mask
+  for (long long chunk = gtid; chunk < chunks_per_mask; chunk += stride) {
+    const long long start = head + chunk * kPix;
+    if (start + kPix > plane) continue;  // ragged tail: phase 2b
+    const int py = (int)(start / W);
+    const int px = (int)(start - (long long)py * W);
+    bool active = false;
+    if (!empty) {
+      const int pxe = px + kPix - 1;
+      if (pxe < W) {
+        active = (py >= ry0 && py <= ry1 && pxe >= cx0 && px <= cx1);
+      } else {  // chunk wraps into the next row
+        active = (py >= ry0 && py <= ry1 && px <= cx1) || (py + 1 >= ry0 && py + 1 <= ry1 && pxe - W >= cx0);
       }
     }
-    uint8_t* dst = obase + start;
-    if (cnt == kPix) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < kPix; ++j)
-        if (j < cnt) dst[j] = (uint8_t)(pk[j >> 2] >> ((j & 3) * 8));
+    if (!active) *reinterpret_cast<uint4*>(obase + start) = make_uint4(zword, zword, zword, zword);
+  }
+  // ---- phase 2a: the rectangle, row by row, widened to chunk boundaries (one pixel per lane)
+  if (!empty) {
+    const int RL = (cx1 - cx0 + 1) + 2 * (kPix - 1) + 1;
+    const long long items = (long long)(ry1 - ry0 + 1) * RL;
+    for (long long it = gtid; it < items; it += stride) {
+      const int r = ry0 + (int)(it / RL);
+      const int t = (int)(it - (long long)(r - ry0) * RL);
+      const long long lo = (long long)r * W + cx0, hi = (long long)r * W + cx1;  // inclusive flat range of this row
+      long long A = lo - head;
+      A = (A >= 0 ? (A / kPix) * kPix : 0) + head;
+      if (lo < head) A = 0;
+      long long B = ((hi - head) / kPix + 1) * kPix + head;
+      if (hi < head) B = head;
+      if (B > plane) B = plane;
+      const long long byte = A + t;
+      if (byte >= B) continue;
+      const int py = (int)(byte / W), px = (int)(byte - (long long)py * W);
+      obase[byte] = (uint8_t)paste_pixel(smask, M, fM, px, py, x0, y0, x1, y1, threshold);
+    }
+  }
+  // ---- phase 2b: unaligned head and ragged tail bytes (< 32 bytes per mask)
+  if (blockIdx.x == 0) {
+    const long long tail0 = head + (long long)((plane - head) / kPix) * kPix;
+    for (long long byte = threadIdx.x; byte < head && byte < plane; byte += kThreads) {
+      const int py = (int)(byte / W), px = (int)(byte - (long long)py * W);
+      obase[byte] = (uint8_t)paste_pixel(smask, M, fM, px, py, x0, y0, x1, y1, threshold);
+    }
+    for (long long byte = tail0 + threadIdx.x; byte < plane; byte += kThreads) {
+      if (byte < 0) continue;
+      const int py = (int)(byte / W), px = (int)(byte - (long long)py * W);
+      obase[byte] = (uint8_t)paste_pixel(smask, M, fM, px, py, x0, y0, x1, y1, threshold);
     }
   }
 }
@@ -99,7 +144,7 @@ D2B_API int d2b_paste_masks(const float* masks, const float* boxes, int N, int M
   if (!masks || !boxes || !out || N < 0 || M <= 0 || H < 0 || W < 0) return D2B_EINVAL;
   if (M > kMaxM) return D2B_EUNSUPPORTED;
   long long plane = (long long)H * W;
-  int chunks = (int)((plane + kPix - 1) / kPix);
+  int chunks = (int)((plane + kPix - 1) / kPix);  // upper bound; chunks past the plane are skipped in-kernel
   int gx = d2b_cdiv(chunks + 1, kThreads);
   // enough CTAs per mask to fill the machine even for a single mask, capped to keep the smem mask staging amortised
   int want = d2b_cdiv(8LL * kNumSMs, N);

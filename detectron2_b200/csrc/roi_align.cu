@@ -305,6 +305,310 @@ __global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, co
   }
 }
 
+// ------------------------------------------------------------------ axis-aligned forward, v2 (staged)
+// One CTA per (RoI, group of 32-channel tiles).
+//   1. The sample grid of a RoI is a product grid, so the g_h x g_w bilinear samples of a bin collapse into a short
+//      list of (row, weight) x (column, weight) taps: <= g+1 distinct rows/columns per bin instead of 4*g*g taps.
+//      The lists are built once per RoI and shared by all channels.
+//   2. The RoI's pixel footprint of 32 channels is staged in shared memory with coalesced row reads and stored
+//      TRANSPOSED ([pixel][channel], pitch 33) so that in the compute phase lane == channel: every tap is one
+//      conflict-free LDS and the tap index / weight are warp-uniform (broadcast).
+//   3. Results go through a [channel][bin] smem tile and leave as one contiguous (coalesced) block per channel tile.
+// RoIs whose footprint does not fit are processed in bands of bin rows; degenerate cases (tap list overflow, a single
+// bin row larger than the staging buffer, pooled size > 16) take the direct path.
+constexpr int kTileC = 32;
+constexpr int kMaxE = 16;
+constexpr int kMaxP = 16;
+constexpr int kPitch = kTileC + 1;
+constexpr int kV2Threads = 512;  // 16 warps per CTA, 2 CTAs per SM -> 32 resident warps to cover LDS / L2 latency
+constexpr int kV2Warps = kV2Threads / 32;
+
+struct CTap {
+  int idx;
+  float w;
+};
+
+__device__ __forceinline__ void add_tap(CTap* list, int& n, int idx, float w, int& overflow) {
+  if (w == 0.f) return;
+  for (int e = 0; e < n; ++e)
+    if (list[e].idx == idx) {
+      list[e].w += w;
+      return;
+    }
+  if (n >= kMaxE) {
+    overflow = 1;
+    return;
+  }
+  list[n].idx = idx;
+  list[n].w = w;
+  ++n;
+}
+
+__global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const Pyr P, const float* __restrict__ rois,
+                                                                         int C, int PH, int PW, int sr, int aligned,
+                                                                         int tiles_per_cta, int cap_px, int ostride,
+                                                                         float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  // per-RoI tables, built once per CTA and shared by all channel tiles.  Lists are padded to a multiple of 4 entries
+  // with zero-weight taps so that the inner loops carry no bounds predicates.  xtab stores idx * kPitch.
+  __shared__ __align__(16) CTap ytab[kMaxP * kMaxE];
+  __shared__ __align__(16) CTap xtab[kMaxP * kMaxE];
+  __shared__ int yn[kMaxP], xn4[kMaxP], ylo[kMaxP], yhi[kMaxP];
+  __shared__ int band_ph0[kMaxP + 1], band_yb[kMaxP], band_npx[kMaxP];
+  __shared__ int s_overflow, s_xmin, s_xmax, s_nbands, s_direct;
+  int* rowoff = reinterpret_cast<int*>(dsm);
+  float* otile = reinterpret_cast<float*>(dsm + sizeof(int) * cap_px);
+  float* stage = otile + kTileC * ostride;
+
+  const int k = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const float* __restrict__ in = P.feat[lvl];
+  const int H = P.H[lvl], W = P.W[lvl];
+  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+  const int bins = PH * PW;
+  const int ntile = d2b_cdiv(C, kTileC);
+  const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(ntile, t_begin + tiles_per_cta);
+
+  if (tid == 0) {
+    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;
+    s_xmin = 1 << 30;
+    s_xmax = -1;
+  }
+  __syncthreads();
+  if (!s_overflow) {
+    if (tid < PH) {
+      CTap* list = ytab + tid * kMaxE;
+      int n = 0, ov = 0, lo = 1 << 30, hi = -1;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+        add_tap(list, n, t.lo, t.wl, ov);
+        add_tap(list, n, t.hi, t.wh, ov);
+      }
+      for (int e = 0; e < n; ++e) {
+        lo = min(lo, list[e].idx);
+        hi = max(hi, list[e].idx);
+      }
+      yn[tid] = n;
+      ylo[tid] = lo;
+      yhi[tid] = hi;
+      if (ov) s_overflow = 1;
+    } else if (tid >= 32 && tid < 32 + PW) {
+      const int pw = tid - 32;
+      CTap* list = xtab + pw * kMaxE;
+      int n = 0, ov = 0;
+      for (int ix = 0; ix < g.gw; ++ix) {
+        Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+        add_tap(list, n, t.lo, t.wl, ov);
+        add_tap(list, n, t.hi, t.wh, ov);
+      }
+      for (int e = 0; e < n; ++e) {
+        atomicMin(&s_xmin, list[e].idx);
+        atomicMax(&s_xmax, list[e].idx);
+      }
+      const int n4 = (n + 3) & ~3;  // pad with zero-weight taps on a valid column
+      for (int e = n; e < n4; ++e) {
+        list[e].idx = list[0].idx;
+        list[e].w = 0.f;
+      }
+      xn4[pw] = n4;
+      if (ov) s_overflow = 1;
+    }
+  }
+  __syncthreads();
+  const int xmin = s_xmin, fw = s_xmax - s_xmin + 1;
+  if (tid < PW && !s_overflow) {  // column taps -> stage offsets relative to the footprint's first column
+    CTap* list = xtab + tid * kMaxE;
+    for (int e = 0; e < xn4[tid]; ++e) list[e].idx = (list[e].idx - xmin) * kPitch;
+  }
+  if (tid == 0) {  // band schedule: consecutive bin rows whose pixel footprint fits the staging buffer
+    int direct = s_overflow;
+    int nb = 0;
+    if (!direct && fw > 0) {
+      int ph0 = 0;
+      while (ph0 < PH && !direct) {
+        int yb = 1 << 30, ye = -1, ph1 = ph0;
+        while (ph1 < PH) {
+          int nyb = yb, nye = ye;
+          if (yn[ph1] > 0) {
+            nyb = min(yb, ylo[ph1]);
+            nye = max(ye, yhi[ph1]);
+          }
+          if (nye >= nyb && (long long)(nye - nyb + 1) * fw > cap_px) {
+            if (ph1 == ph0) direct = 1;  // a single bin row does not fit
+            break;
+          }
+          yb = nyb;
+          ye = nye;
+          ++ph1;
+        }
+        band_ph0[nb] = ph0;
+        band_yb[nb] = yb;
+        band_npx[nb] = (ye >= yb) ? (ye - yb + 1) * fw : 0;
+        ++nb;
+        ph0 = ph1;
+      }
+    } else if (!direct) {  // no valid column at all: every output is 0
+      band_ph0[0] = 0;
+      band_yb[0] = 0;
+      band_npx[0] = 0;
+      nb = 1;
+    }
+    band_ph0[nb] = PH;
+    s_nbands = nb;
+    s_direct = direct;
+  }
+  __syncthreads();
+  const bool direct = s_direct != 0;
+  const int nbands = s_nbands;
+  int staged_band = -1;  // rowoff[] currently describes this band
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int c0 = tile * kTileC;
+    const int cn = min(kTileC, C - c0);
+    const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
+    float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
+    if (direct) {  // rare: taps on the fly, straight from global memory
+      for (int idx = tid; idx < cn * bins; idx += kV2Threads) {
+        const int c = idx / bins, bin = idx - c * bins;
+        const int ph = bin / PW, pw = bin - ph * PW;
+        const float* __restrict__ plane = base + (size_t)c * H * W;
+        float acc = 0.f;
+        for (int iy = 0; iy < g.gh; ++iy) {
+          Tap1 ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+          const float* __restrict__ r0 = plane + (size_t)ty.lo * W;
+          const float* __restrict__ r1 = plane + (size_t)ty.hi * W;
+          for (int ix = 0; ix < g.gw; ++ix) {
+            Tap1 tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+            acc += (ty.wl * tx.wl) * __ldg(r0 + tx.lo) + (ty.wl * tx.wh) * __ldg(r0 + tx.hi) +
+                   (ty.wh * tx.wl) * __ldg(r1 + tx.lo) + (ty.wh * tx.wh) * __ldg(r1 + tx.hi);
+          }
+        }
+        obase[idx] = acc * g.inv_count;
+      }
+      continue;
+    }
+    // channel planes this warp stages (clamped to a valid plane: surplus lanes of a ragged last tile load real data
+    // into columns nobody reads)
+    const float* __restrict__ pl0 = base + (size_t)min(warp, cn - 1) * H * W;
+    const float* __restrict__ pl1 = base + (size_t)min(warp + kV2Warps, cn - 1) * H * W;
+    for (int band = 0; band < nbands; ++band) {
+      const int ph0 = band_ph0[band], ph1 = band_ph0[band + 1];
+      const int yb = band_yb[band], npx = band_npx[band];
+      const int npx32 = (npx + 31) & ~31;  // <= cap_px (cap_px is a multiple of 32)
+      __syncthreads();  // previous band / tile finished reading stage
+      if (staged_band != band) {
+        for (int i = tid; i < npx32; i += kV2Threads) {
+          const int ii = i < npx ? i : 0;  // padding pixels re-read pixel 0
+          const int y = ii / fw, x = ii - y * fw;
+          rowoff[i] = (yb + y) * W + xmin + x;
+        }
+        staged_band = band;
+        __syncthreads();
+      }
+      // stage: warp w loads channels w and w+16; lanes run along the footprint pixels (coalesced rows).  No bounds
+      // predicates: 8 pixel strides x 2 channels = 16 independent loads in flight per lane in the main loop.
+      {
+        int pix = lane;
+        float* __restrict__ sdst = stage + pix * kPitch + warp;
+        for (; pix + 224 < npx32; pix += 256, sdst += 256 * kPitch) {
+          int off[8];
+          float a[8], b[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) off[u] = rowoff[pix + 32 * u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            a[u] = __ldg(pl0 + off[u]);
+            b[u] = __ldg(pl1 + off[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            sdst[32 * u * kPitch] = a[u];
+            sdst[32 * u * kPitch + kV2Warps] = b[u];
+          }
+        }
+        for (; pix < npx32; pix += 32, sdst += 32 * kPitch) {
+          const int off = rowoff[pix];
+          const float a = __ldg(pl0 + off), b = __ldg(pl1 + off);
+          sdst[0] = a;
+          sdst[kV2Warps] = b;
+        }
+      }
+      __syncthreads();
+      // compute: one warp per bin, lane == channel; per footprint row the column taps are consumed four at a time.
+      const int nb = (ph1 - ph0) * PW;
+      int ph = ph0, pw = warp;
+      while (pw >= PW) {
+        pw -= PW;
+        ++ph;
+      }
+      for (int bi = warp; bi < nb; bi += kV2Warps) {
+        float acc = 0.f;
+        const int ny = yn[ph], nx = xn4[pw];
+        const float4* __restrict__ xl = reinterpret_cast<const float4*>(xtab + pw * kMaxE);
+        for (int ey = 0; ey < ny; ++ey) {
+          const CTap ty = ytab[ph * kMaxE + ey];
+          const float* __restrict__ srow = stage + (ty.idx - yb) * fw * kPitch + lane;
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+          for (int ex = 0; ex < nx; ex += 4) {
+            const float4 p01 = xl[ex >> 1], p23 = xl[(ex >> 1) + 1];  // (idx,w),(idx,w) pairs
+            r0 = fmaf(p01.y, srow[__float_as_int(p01.x)], r0);
+            r1 = fmaf(p01.w, srow[__float_as_int(p01.z)], r1);
+            r2 = fmaf(p23.y, srow[__float_as_int(p23.x)], r2);
+            r3 = fmaf(p23.w, srow[__float_as_int(p23.z)], r3);
+          }
+          acc = fmaf(ty.w, (r0 + r1) + (r2 + r3), acc);
+        }
+        otile[lane * ostride + ph * PW + pw] = acc * g.inv_count;
+        pw += kV2Warps;
+        while (pw >= PW) {
+          pw -= PW;
+          ++ph;
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = warp; c < cn; c += kV2Warps) {
+      const float* __restrict__ orow = otile + c * ostride;
+      float* __restrict__ gdst = obase + c * bins;
+      for (int bin = lane; bin < bins; bin += 32) gdst[bin] = orow[bin];
+    }
+  }
+}
+
+// shared-memory plan of the staged kernel: returns dynamic smem bytes, fills cap_px / ostride
+static size_t v2_plan(int PH, int PW, int* cap_px, int* ostride) {
+  const int bins = PH * PW;
+  *ostride = bins | 1;  // odd pitch: conflict-free [channel][bin] tile
+  const size_t budget = 100 * 1024;  // two CTAs per SM
+  const size_t fixed = (size_t)kTileC * (*ostride) * sizeof(float);
+  long long cap = ((long long)budget - (long long)fixed) / (long long)(kPitch * sizeof(float) + sizeof(int));
+  cap &= ~31LL;  // multiple of 32: the staging loop pads the footprint to whole warps
+  if (cap < 64) cap = 64;
+  *cap_px = (int)cap;
+  return sizeof(int) * (size_t)cap + fixed + sizeof(float) * (size_t)cap * kPitch;
+}
+
+static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int PW, int sr, int aligned, float* out,
+                      cudaStream_t stream) {
+  int cap_px, ostride;
+  const size_t smem = v2_plan(PH, PW, &cap_px, &ostride);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int ntile = d2b_cdiv(C, kTileC);
+  int tiles_per_cta = ntile;  // split channel tiles until the grid is a few waves deep
+  while (tiles_per_cta > 1 && (long long)K * d2b_cdiv(ntile, tiles_per_cta) < 4LL * kNumSMs) tiles_per_cta = (tiles_per_cta + 1) / 2;
+  dim3 grid(K, d2b_cdiv(ntile, tiles_per_cta));
+  roi_align_fwd_v2_kernel<<<grid, kV2Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, tiles_per_cta, cap_px,
+                                                            ostride, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
 // channels per CTA: enough CTAs to fill 148 SMs a few times over without shrinking the per-CTA tap reuse.
 int pick_c_per_cta(int K, int C) {
   int cpc = C;
@@ -326,12 +630,7 @@ D2B_API int d2b_roi_align_forward(const float* input, int N, int C, int H, int W
   P.H[0] = H;
   P.W[0] = W;
   P.scale[0] = spatial_scale;
-  int cpc = pick_c_per_cta(K, C);
-  dim3 grid(K, d2b_cdiv(C, cpc));
-  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, rois, C, pooled_h, pooled_w,
-                                                                         sampling_ratio, aligned, cpc, out);
-  D2B_CHECK_LAUNCH();
-  return D2B_OK;
+  return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
 }
 
 static bool make_pyr(const d2b_pyramid* pyr, Pyr& P) {
@@ -361,12 +660,7 @@ D2B_API int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const f
   if (!make_pyr(pyr, P) || !rois || !out || N <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0) return D2B_EINVAL;
   for (int l = 0; l < P.num_levels; ++l)
     if (!P.feat[l]) return D2B_EINVAL;
-  int cpc = pick_c_per_cta(K, C);
-  dim3 grid(K, d2b_cdiv(C, cpc));
-  roi_align_fwd_kernel<512><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, rois, C, pooled_h, pooled_w,
-                                                                         sampling_ratio, aligned, cpc, out);
-  D2B_CHECK_LAUNCH();
-  return D2B_OK;
+  return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
 }
 
 D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,

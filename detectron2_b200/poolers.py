@@ -31,10 +31,10 @@ def assign_boxes_to_levels(box_lists, min_level: int, max_level: int, canonical_
 
 def convert_boxes_to_pooler_format(box_lists):
     """list of per-image (L_i, 4|5) boxes -> (M, 5|6) with the batch index in column 0 (poolers.py:72-98)."""
-    boxes = torch.cat([_tensor_of(b) for b in box_lists], dim=0)
-    sizes = torch.tensor([len(_tensor_of(b)) for b in box_lists], device=boxes.device)
-    idx = torch.repeat_interleave(torch.arange(len(box_lists), dtype=boxes.dtype, device=boxes.device), sizes)
-    return torch.cat([idx[:, None], boxes], dim=1)
+    tensors = [_tensor_of(b) for b in box_lists]
+    # batch-index column built from host-side lengths: no repeat_interleave / device sync (cf. poolers.py:64-69)
+    cols = [torch.cat([t.new_full((t.shape[0], 1), float(i)), t], dim=1) for i, t in enumerate(tensors)]
+    return cols[0] if len(cols) == 1 else torch.cat(cols, dim=0)
 
 
 class ROIPooler(nn.Module):

@@ -419,7 +419,7 @@ def test_roi_pooler_fused_vs_reference_loop(out, ptype):
     boxes_dev = [b.to(DEV) for b in per_img]
     y = pooler(fg, boxes_dev)
     assert torch.equal(assign_boxes_to_levels(boxes_dev, 2, 5, 224, 4).cpu(), lv)
-    ok, err = rel_close(y, ref)
+    ok, err = rel_close(y, ref, rtol=1e-4, atol=5e-5)  # randn features: O(1) values, sums of up to 64 taps
     assert ok, err
     go = torch.randn(y.shape, generator=g)
     y.backward(go.to(DEV))
