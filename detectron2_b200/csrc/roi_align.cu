@@ -305,60 +305,58 @@ __global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, co
   }
 }
 
-// ------------------------------------------------------------------ axis-aligned forward, v2 (staged)
-// One CTA per (RoI, group of 32-channel tiles).
-//   1. The sample grid of a RoI is a product grid, so the g_h x g_w bilinear samples of a bin collapse into a short
-//      list of (row, weight) x (column, weight) taps: <= g+1 distinct rows/columns per bin instead of 4*g*g taps.
-//      The lists are built once per RoI and shared by all channels.
-//   2. The RoI's pixel footprint of 32 channels is staged in shared memory with coalesced row reads and stored
-//      TRANSPOSED ([pixel][channel], pitch 33) so that in the compute phase lane == channel: every tap is one
-//      conflict-free LDS and the tap index / weight are warp-uniform (broadcast).
-//   3. Results go through a [channel][bin] smem tile and leave as one contiguous (coalesced) block per channel tile.
-// RoIs whose footprint does not fit are processed in bands of bin rows; degenerate cases (tap list overflow, a single
-// bin row larger than the staging buffer, pooled size > 16) take the direct path.
-constexpr int kTileC = 32;
-constexpr int kMaxE = 16;
-constexpr int kMaxP = 16;
-constexpr int kPitch = kTileC + 1;
-constexpr int kV2Threads = 512;  // 16 warps per CTA, 2 CTAs per SM -> 32 resident warps to cover LDS / L2 latency
-constexpr int kV2Warps = kV2Threads / 32;
+// ------------------------------------------------------------------ axis-aligned forward (staged, barrier-free)
+// One CTA per (RoI, slab of channels); every WARP owns kChW channels at a time and runs on its own:
+//   1. [once per CTA] the g_h x g_w bilinear samples of each bin collapse into short (row, weight) x (column, weight)
+//      tap lists (the sample grid is a product grid): <= g+1 distinct rows / columns per bin instead of 4*g*g taps.
+//      The lists live in shared memory, entry-major ([tap][bin row]) so that lanes of different bins read them
+//      without bank conflicts, and are padded to a uniform length with zero-weight taps (no divergence);
+//   2. a warp stages the RoI's pixel footprint of its kChW channel planes into its private slice of shared memory
+//      with coalesced row reads (many independent loads in flight per lane), __syncwarp()s, then evaluates the bins
+//      with lane == bin, reading taps from shared memory, and stores its outputs straight to global memory
+//      (lanes = consecutive bins -> coalesced).  There is no CTA-wide barrier in the channel loop, so the 24 resident
+//      warps per SM overlap each other's load latency freely.
+// RoIs whose footprint exceeds a warp's slice are processed in bands of bin rows; pathological RoIs (tap list
+// overflow, one bin row larger than the slice, pooled size > 16) take the direct path (taps on the fly from global).
+constexpr int kMaxE = 32;   // taps per bin row / column: covers sampling grids up to 31 (clipped, elongated RoIs)
+constexpr int kMaxP = 16;   // pooled size supported by the staged path
+constexpr int kChW = 4;     // channels per warp
+constexpr int kV3Warps = 8;
+constexpr int kV3Threads = kV3Warps * 32;
+constexpr int kCapPx = 448;   // pixels per channel in a warp's slice:  8 warps * 4 ch * 448 px * 4 B = 56 KB per CTA
+constexpr int kRowoffCap = 1536;  // largest whole-RoI footprint (pixels) with a precomputed offset table
 
 struct CTap {
   int idx;
   float w;
 };
 
-__device__ __forceinline__ void add_tap(CTap* list, int& n, int idx, float w, int& overflow) {
+__device__ __forceinline__ void add_tap(CTap* list, int stride, int& n, int idx, float w, int& overflow) {
   if (w == 0.f) return;
   for (int e = 0; e < n; ++e)
-    if (list[e].idx == idx) {
-      list[e].w += w;
+    if (list[e * stride].idx == idx) {
+      list[e * stride].w += w;
       return;
     }
   if (n >= kMaxE) {
     overflow = 1;
     return;
   }
-  list[n].idx = idx;
-  list[n].w = w;
+  list[n * stride].idx = idx;
+  list[n * stride].w = w;
   ++n;
 }
 
-__global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const Pyr P, const float* __restrict__ rois,
+__global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const Pyr P, const float* __restrict__ rois,
                                                                          int C, int PH, int PW, int sr, int aligned,
-                                                                         int tiles_per_cta, int cap_px, int ostride,
-                                                                         float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  // per-RoI tables, built once per CTA and shared by all channel tiles.  Lists are padded to a multiple of 4 entries
-  // with zero-weight taps so that the inner loops carry no bounds predicates.  xtab stores idx * kPitch.
-  __shared__ __align__(16) CTap ytab[kMaxP * kMaxE];
-  __shared__ __align__(16) CTap xtab[kMaxP * kMaxE];
-  __shared__ int yn[kMaxP], xn4[kMaxP], ylo[kMaxP], yhi[kMaxP];
+                                                                         int groups_per_cta, float* __restrict__ out) {
+  extern __shared__ __align__(16) float stage_all[];  // [warp][kChW][kCapPx]
+  __shared__ CTap ytab[kMaxE * kMaxP];  // [tap][ph]
+  __shared__ CTap xtab[kMaxE * kMaxP];  // [tap][pw]   (idx relative to the footprint's first column)
+  __shared__ int rowoff[kRowoffCap];    // global offset (y*W + x) of every footprint pixel, row-major
+  __shared__ int yn[kMaxP], xn[kMaxP], ylo[kMaxP], yhi[kMaxP];
   __shared__ int band_ph0[kMaxP + 1], band_yb[kMaxP], band_npx[kMaxP];
-  __shared__ int s_overflow, s_xmin, s_xmax, s_nbands, s_direct;
-  int* rowoff = reinterpret_cast<int*>(dsm);
-  float* otile = reinterpret_cast<float*>(dsm + sizeof(int) * cap_px);
-  float* stage = otile + kTileC * ostride;
+  __shared__ int s_overflow, s_xmin, s_xmax, s_nbands, s_direct, s_nyu, s_nxu, s_ymin, s_ymax;
 
   const int k = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,8 +365,8 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
   const int H = P.H[lvl], W = P.W[lvl];
   const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
   const int bins = PH * PW;
-  const int ntile = d2b_cdiv(C, kTileC);
-  const int t_begin = blockIdx.y * tiles_per_cta, t_end = min(ntile, t_begin + tiles_per_cta);
+  const int ngroup = d2b_cdiv(C, kChW);
+  const int g_begin = blockIdx.y * groups_per_cta, g_end = min(ngroup, g_begin + groups_per_cta);
 
   if (tid == 0) {
     s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;
@@ -378,16 +376,16 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
   __syncthreads();
   if (!s_overflow) {
     if (tid < PH) {
-      CTap* list = ytab + tid * kMaxE;
+      CTap* list = ytab + tid;
       int n = 0, ov = 0, lo = 1 << 30, hi = -1;
       for (int iy = 0; iy < g.gh; ++iy) {
         Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
-        add_tap(list, n, t.lo, t.wl, ov);
-        add_tap(list, n, t.hi, t.wh, ov);
+        add_tap(list, kMaxP, n, t.lo, t.wl, ov);
+        add_tap(list, kMaxP, n, t.hi, t.wh, ov);
       }
       for (int e = 0; e < n; ++e) {
-        lo = min(lo, list[e].idx);
-        hi = max(hi, list[e].idx);
+        lo = min(lo, list[e * kMaxP].idx);
+        hi = max(hi, list[e * kMaxP].idx);
       }
       yn[tid] = n;
       ylo[tid] = lo;
@@ -395,36 +393,37 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
       if (ov) s_overflow = 1;
     } else if (tid >= 32 && tid < 32 + PW) {
       const int pw = tid - 32;
-      CTap* list = xtab + pw * kMaxE;
+      CTap* list = xtab + pw;
       int n = 0, ov = 0;
       for (int ix = 0; ix < g.gw; ++ix) {
         Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
-        add_tap(list, n, t.lo, t.wl, ov);
-        add_tap(list, n, t.hi, t.wh, ov);
+        add_tap(list, kMaxP, n, t.lo, t.wl, ov);
+        add_tap(list, kMaxP, n, t.hi, t.wh, ov);
       }
       for (int e = 0; e < n; ++e) {
-        atomicMin(&s_xmin, list[e].idx);
-        atomicMax(&s_xmax, list[e].idx);
+        atomicMin(&s_xmin, list[e * kMaxP].idx);
+        atomicMax(&s_xmax, list[e * kMaxP].idx);
       }
-      const int n4 = (n + 3) & ~3;  // pad with zero-weight taps on a valid column
-      for (int e = n; e < n4; ++e) {
-        list[e].idx = list[0].idx;
-        list[e].w = 0.f;
-      }
-      xn4[pw] = n4;
+      xn[pw] = n;
       if (ov) s_overflow = 1;
     }
   }
   __syncthreads();
   const int xmin = s_xmin, fw = s_xmax - s_xmin + 1;
-  if (tid < PW && !s_overflow) {  // column taps -> stage offsets relative to the footprint's first column
-    CTap* list = xtab + tid * kMaxE;
-    for (int e = 0; e < xn4[tid]; ++e) list[e].idx = (list[e].idx - xmin) * kPitch;
-  }
-  if (tid == 0) {  // band schedule: consecutive bin rows whose pixel footprint fits the staging buffer
-    int direct = s_overflow;
-    int nb = 0;
-    if (!direct && fw > 0) {
+  if (tid == 0) {  // uniform list lengths, band schedule
+    int direct = s_overflow, nb = 0, nyu = 0, nxu = 0, ymin = 1 << 30, ymax = -1;
+    if (!direct) {
+      for (int ph = 0; ph < PH; ++ph) {
+        nyu = max(nyu, yn[ph]);
+        if (yn[ph] > 0) {
+          ymin = min(ymin, ylo[ph]);
+          ymax = max(ymax, yhi[ph]);
+        }
+      }
+      for (int pw = 0; pw < PW; ++pw) nxu = max(nxu, xn[pw]);
+    }
+    if (!direct && fw > 0 && ymax >= ymin) {
+      if ((long long)(ymax - ymin + 1) * fw > kRowoffCap) direct = 1;
       int ph0 = 0;
       while (ph0 < PH && !direct) {
         int yb = 1 << 30, ye = -1, ph1 = ph0;
@@ -434,7 +433,7 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
             nyb = min(yb, ylo[ph1]);
             nye = max(ye, yhi[ph1]);
           }
-          if (nye >= nyb && (long long)(nye - nyb + 1) * fw > cap_px) {
+          if (nye >= nyb && (nye - nyb + 1) * fw > kCapPx) {
             if (ph1 == ph0) direct = 1;  // a single bin row does not fit
             break;
           }
@@ -443,33 +442,60 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
           ++ph1;
         }
         band_ph0[nb] = ph0;
-        band_yb[nb] = yb;
+        band_yb[nb] = (ye >= yb) ? yb : ymin;
         band_npx[nb] = (ye >= yb) ? (ye - yb + 1) * fw : 0;
         ++nb;
         ph0 = ph1;
       }
-    } else if (!direct) {  // no valid column at all: every output is 0
+    } else if (!direct) {  // no valid sample at all: every output is 0
       band_ph0[0] = 0;
       band_yb[0] = 0;
       band_npx[0] = 0;
       nb = 1;
+      nyu = nxu = 0;
+      ymin = 0;
+      ymax = -1;
     }
     band_ph0[nb] = PH;
     s_nbands = nb;
     s_direct = direct;
+    s_nyu = nyu;
+    s_nxu = nxu;
+    s_ymin = ymin;
+    s_ymax = ymax;
   }
   __syncthreads();
   const bool direct = s_direct != 0;
-  const int nbands = s_nbands;
-  int staged_band = -1;  // rowoff[] currently describes this band
+  const int nbands = s_nbands, nyu = s_nyu, nxu = s_nxu, ymin = s_ymin;
+  if (!direct) {
+    // pad the lists to the uniform lengths with zero-weight taps on a valid row / column; make columns relative
+    if (tid < PH) {
+      const int n = yn[tid];
+      const int fill = n > 0 ? ytab[tid].idx : 0;  // rows are clamped into the band at use
+      for (int e = n; e < nyu; ++e) ytab[e * kMaxP + tid] = CTap{fill, 0.f};
+    } else if (tid >= 32 && tid < 32 + PW) {
+      const int pw = tid - 32, n = xn[pw];
+      for (int e = 0; e < n; ++e) xtab[e * kMaxP + pw].idx -= xmin;
+      for (int e = n; e < nxu; ++e) xtab[e * kMaxP + pw] = CTap{0, 0.f};
+    }
+    if (fw > 0 && s_ymax >= ymin) {
+      const int npx_all = (s_ymax - ymin + 1) * fw;  // <= kRowoffCap by construction
+      for (int i = tid; i < npx_all; i += kV3Threads) {
+        const int y = i / fw, x = i - y * fw;
+        rowoff[i] = (ymin + y) * W + xmin + x;
+      }
+    }
+  }
+  __syncthreads();
 
-  for (int tile = t_begin; tile < t_end; ++tile) {
-    const int c0 = tile * kTileC;
-    const int cn = min(kTileC, C - c0);
+  float* __restrict__ st = stage_all + (size_t)warp * kChW * kCapPx;
+  for (int grp = g_begin + warp; grp < g_end; grp += kV3Warps) {
+    const int c0 = grp * kChW;
+    const int cn = min(kChW, C - c0);
     const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
     float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
-    if (direct) {  // rare: taps on the fly, straight from global memory
-      for (int idx = tid; idx < cn * bins; idx += kV2Threads) {
+    if (direct) {  // rare: taps on the fly, straight from global memory (one warp: its kChW channels)
+      for (int idx = lane; idx < cn * bins; idx += 32) {
         const int c = idx / bins, bin = idx - c * bins;
         const int ph = bin / PW, pw = bin - ph * PW;
         const float* __restrict__ plane = base + (size_t)c * H * W;
@@ -488,123 +514,84 @@ __global__ void __launch_bounds__(kV2Threads, 2) roi_align_fwd_v2_kernel(const P
       }
       continue;
     }
-    // channel planes this warp stages (clamped to a valid plane: surplus lanes of a ragged last tile load real data
-    // into columns nobody reads)
-    const float* __restrict__ pl0 = base + (size_t)min(warp, cn - 1) * H * W;
-    const float* __restrict__ pl1 = base + (size_t)min(warp + kV2Warps, cn - 1) * H * W;
+    // channel planes of this warp (a ragged last group re-reads its last valid plane into unused slices)
+    const float* __restrict__ pl[kChW];
+#pragma unroll
+    for (int q = 0; q < kChW; ++q) pl[q] = base + (size_t)min(q, cn - 1) * H * W;
+
     for (int band = 0; band < nbands; ++band) {
       const int ph0 = band_ph0[band], ph1 = band_ph0[band + 1];
       const int yb = band_yb[band], npx = band_npx[band];
-      const int npx32 = (npx + 31) & ~31;  // <= cap_px (cap_px is a multiple of 32)
-      __syncthreads();  // previous band / tile finished reading stage
-      if (staged_band != band) {
-        for (int i = tid; i < npx32; i += kV2Threads) {
-          const int ii = i < npx ? i : 0;  // padding pixels re-read pixel 0
-          const int y = ii / fw, x = ii - y * fw;
-          rowoff[i] = (yb + y) * W + xmin + x;
+      const int ylast = yb + (fw > 0 ? npx / fw : 0) - 1;
+      const int* __restrict__ ro = rowoff + (yb - ymin) * fw;
+      __syncwarp();  // the previous band's / group's reads of `st` are complete
+      // ---- stage: 2 pixel strides x kChW channels = 8 independent loads in flight per lane
+      for (int pix = lane; pix < npx; pix += 64) {
+        const bool two = pix + 32 < npx;
+        const int o0 = ro[pix], o1 = two ? ro[pix + 32] : o0;
+        float a[kChW], b[kChW];
+#pragma unroll
+        for (int q = 0; q < kChW; ++q) {
+          a[q] = __ldg(pl[q] + o0);
+          b[q] = __ldg(pl[q] + o1);
         }
-        staged_band = band;
-        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kChW; ++q) {
+          st[q * kCapPx + pix] = a[q];
+          if (two) st[q * kCapPx + pix + 32] = b[q];
+        }
       }
-      // stage: warp w loads channels w and w+16; lanes run along the footprint pixels (coalesced rows).  No bounds
-      // predicates: 8 pixel strides x 2 channels = 16 independent loads in flight per lane in the main loop.
-      {
-        int pix = lane;
-        float* __restrict__ sdst = stage + pix * kPitch + warp;
-        for (; pix + 224 < npx32; pix += 256, sdst += 256 * kPitch) {
-          int off[8];
-          float a[8], b[8];
+      __syncwarp();
+      // ---- compute: lane == bin
+      const int nbin = (ph1 - ph0) * PW;
+      for (int b0 = 0; b0 < nbin; b0 += 32) {
+        const int bin = b0 + lane;
+        const bool live = bin < nbin;
+        const int bb = live ? bin : 0;
+        const int dph = bb / PW;
+        const int ph = ph0 + dph, pw = bb - dph * PW;
+        float acc[kChW];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) off[u] = rowoff[pix + 32 * u];
+        for (int q = 0; q < kChW; ++q) acc[q] = 0.f;
+        for (int ey = 0; ey < nyu; ++ey) {
+          const CTap ty = ytab[ey * kMaxP + ph];
+          const float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw;  // pad taps (w = 0) stay in-band
+          float r[kChW];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            a[u] = __ldg(pl0 + off[u]);
-            b[u] = __ldg(pl1 + off[u]);
+          for (int q = 0; q < kChW; ++q) r[q] = 0.f;
+          for (int ex = 0; ex < nxu; ++ex) {
+            const CTap tx = xtab[ex * kMaxP + pw];
+#pragma unroll
+            for (int q = 0; q < kChW; ++q) r[q] = fmaf(tx.w, srow[q * kCapPx + tx.idx], r[q]);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            sdst[32 * u * kPitch] = a[u];
-            sdst[32 * u * kPitch + kV2Warps] = b[u];
-          }
+          for (int q = 0; q < kChW; ++q) acc[q] = fmaf(ty.w, r[q], acc[q]);
         }
-        for (; pix < npx32; pix += 32, sdst += 32 * kPitch) {
-          const int off = rowoff[pix];
-          const float a = __ldg(pl0 + off), b = __ldg(pl1 + off);
-          sdst[0] = a;
-          sdst[kV2Warps] = b;
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < kChW; ++q)
+            if (q < cn) obase[q * bins + ph * PW + pw] = acc[q] * g.inv_count;
         }
       }
-      __syncthreads();
-      // compute: one warp per bin, lane == channel; per footprint row the column taps are consumed four at a time.
-      const int nb = (ph1 - ph0) * PW;
-      int ph = ph0, pw = warp;
-      while (pw >= PW) {
-        pw -= PW;
-        ++ph;
-      }
-      for (int bi = warp; bi < nb; bi += kV2Warps) {
-        float acc = 0.f;
-        const int ny = yn[ph], nx = xn4[pw];
-        const float4* __restrict__ xl = reinterpret_cast<const float4*>(xtab + pw * kMaxE);
-        for (int ey = 0; ey < ny; ++ey) {
-          const CTap ty = ytab[ph * kMaxE + ey];
-          const float* __restrict__ srow = stage + (ty.idx - yb) * fw * kPitch + lane;
-          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-          for (int ex = 0; ex < nx; ex += 4) {
-            const float4 p01 = xl[ex >> 1], p23 = xl[(ex >> 1) + 1];  // (idx,w),(idx,w) pairs
-            r0 = fmaf(p01.y, srow[__float_as_int(p01.x)], r0);
-            r1 = fmaf(p01.w, srow[__float_as_int(p01.z)], r1);
-            r2 = fmaf(p23.y, srow[__float_as_int(p23.x)], r2);
-            r3 = fmaf(p23.w, srow[__float_as_int(p23.z)], r3);
-          }
-          acc = fmaf(ty.w, (r0 + r1) + (r2 + r3), acc);
-        }
-        otile[lane * ostride + ph * PW + pw] = acc * g.inv_count;
-        pw += kV2Warps;
-        while (pw >= PW) {
-          pw -= PW;
-          ++ph;
-        }
-      }
-    }
-    __syncthreads();
-    for (int c = warp; c < cn; c += kV2Warps) {
-      const float* __restrict__ orow = otile + c * ostride;
-      float* __restrict__ gdst = obase + c * bins;
-      for (int bin = lane; bin < bins; bin += 32) gdst[bin] = orow[bin];
     }
   }
-}
-
-// shared-memory plan of the staged kernel: returns dynamic smem bytes, fills cap_px / ostride
-static size_t v2_plan(int PH, int PW, int* cap_px, int* ostride) {
-  const int bins = PH * PW;
-  *ostride = bins | 1;  // odd pitch: conflict-free [channel][bin] tile
-  const size_t budget = 100 * 1024;  // two CTAs per SM
-  const size_t fixed = (size_t)kTileC * (*ostride) * sizeof(float);
-  long long cap = ((long long)budget - (long long)fixed) / (long long)(kPitch * sizeof(float) + sizeof(int));
-  cap &= ~31LL;  // multiple of 32: the staging loop pads the footprint to whole warps
-  if (cap < 64) cap = 64;
-  *cap_px = (int)cap;
-  return sizeof(int) * (size_t)cap + fixed + sizeof(float) * (size_t)cap * kPitch;
 }
 
 static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int PW, int sr, int aligned, float* out,
                       cudaStream_t stream) {
-  int cap_px, ostride;
-  const size_t smem = v2_plan(PH, PW, &cap_px, &ostride);
+  const size_t smem = sizeof(float) * (size_t)kV3Warps * kChW * kCapPx;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int ntile = d2b_cdiv(C, kTileC);
-  int tiles_per_cta = ntile;  // split channel tiles until the grid is a few waves deep
-  while (tiles_per_cta > 1 && (long long)K * d2b_cdiv(ntile, tiles_per_cta) < 4LL * kNumSMs) tiles_per_cta = (tiles_per_cta + 1) / 2;
-  dim3 grid(K, d2b_cdiv(ntile, tiles_per_cta));
-  roi_align_fwd_v2_kernel<<<grid, kV2Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, tiles_per_cta, cap_px,
-                                                            ostride, out);
+  const int ngroup = d2b_cdiv(C, kChW);
+  int groups_per_cta = ngroup;  // split the channel groups until the grid is several waves deep
+  while (groups_per_cta > kV3Warps && (long long)K * d2b_cdiv(ngroup, groups_per_cta) < 12LL * kNumSMs)
+    groups_per_cta = (groups_per_cta + 1) / 2;
+  dim3 grid(K, d2b_cdiv(ngroup, groups_per_cta));
+  roi_align_fwd_v3_kernel<<<grid, kV3Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, groups_per_cta, out);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
