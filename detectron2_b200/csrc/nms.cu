@@ -228,13 +228,21 @@ __global__ void __launch_bounds__(1024) coord_range_kernel(const float* __restri
   }
 }
 
+// class id (as int32) of the box at score rank r
+__global__ void class_of_rank_kernel(const int64_t* __restrict__ idxs, const int* __restrict__ order, int M,
+                                     int* __restrict__ cls) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < M) cls[r] = (int)idxs[order[r]];
+}
+
+// sorted[p] = boxes[order[pos2 ? pos2[p] : p]]  (+ the batched-NMS coordinate offset of its class)
 template <bool ROT>
 __global__ void gather_boxes_kernel(const float* __restrict__ boxes, const int* __restrict__ order,
-                                    const int64_t* __restrict__ idxs, const float* __restrict__ mm, int M,
-                                    float* __restrict__ sorted) {
+                                    const int* __restrict__ pos2, const int64_t* __restrict__ idxs,
+                                    const float* __restrict__ mm, int M, float* __restrict__ sorted) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= M) return;
-  const int src = order[r];
+  const int src = order[pos2 ? pos2[r] : r];
   constexpr int D = ROT ? 5 : 4;
   float b[D];
 #pragma unroll
@@ -256,16 +264,21 @@ __global__ void gather_boxes_kernel(const float* __restrict__ boxes, const int* 
 
 // 64x64 IoU tile -> one 64-bit word per row.  grid (col_block, row_block); only col_block >= row_block does work.
 // maskT[(size_t)col_block * M + row]  (column-word-major).
+// cls (optional): class of every position of the class-major order; only same-class pairs can suppress each other, and a
+// tile whose row block and column block share no class is skipped altogether (never read by the scan).
 template <bool ROT>
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sb, int M, double thr,
-                                                      unsigned long long* __restrict__ maskT) {
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ cls, int M,
+                                                      double thr, unsigned long long* __restrict__ maskT) {
   const int cb = blockIdx.x, rb = blockIdx.y;
   if (cb < rb) return;
+  if (cls && cb > rb && cls[min(rb * 64 + 63, M - 1)] != cls[cb * 64]) return;  // classes ascend with position
   constexpr int D = ROT ? 5 : 4;
   __shared__ float cbox[64 * D];
   const int c0 = cb * 64, r0 = rb * 64;
   const int nc = min(64, M - c0);
   for (int t = threadIdx.x; t < nc * D; t += 64) cbox[t] = sb[(size_t)c0 * D + t];
+  __shared__ int ccls[64];
+  if (cls && (int)threadIdx.x < nc) ccls[threadIdx.x] = cls[c0 + threadIdx.x];
   __syncthreads();
   const int row = r0 + threadIdx.x;
   if (row >= M) return;
@@ -274,14 +287,17 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   for (int c = 0; c < D; ++c) a[c] = sb[(size_t)row * D + c];
   unsigned long long bits = 0ull;
   const int start = (cb == rb) ? threadIdx.x + 1 : 0;
+  const int my_cls = cls ? cls[row] : 0;
   if (ROT) {
     for (int j = start; j < nc; ++j) {
+      if (cls && ccls[j] != my_cls) continue;
       float iou = rotated_iou(a, cbox + j * 5);
       if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
     }
   } else {
     const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
     for (int j = start; j < nc; ++j) {
+      if (cls && ccls[j] != my_cls) continue;
       const float* b = cbox + j * 4;
       float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
       float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
@@ -297,145 +313,221 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
 
 constexpr int kScanThreads = 512;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kMaxColsPerWarp = 10;  // register-prefetched column words per warp (covers M <= 64*16*10 = 10240)
+constexpr int kMaxColsPerWarp = 10;  // register-prefetched column words per warp (covers segments <= 64*16*10 = 10240)
 
-// Greedy scan over the bitmask.  dynamic smem: removed[nb] (uint64).
-// Per 64-box block b:  (B) thread 0 resolves the intra-block chain from removed[b] and the diagonal word of each row;
-// (C) the warps OR the kept rows into the `removed` words of the later column blocks.  Everything the next block needs
-// from global memory (its diagonal words, its rows of the later columns) is requested one full iteration ahead and
-// parked in registers, so the serial chain never waits on L2.
+// segment table of the class-major order: seg_start[0..nseg], seg_start[nseg] = M.  Single CTA.
+__global__ void __launch_bounds__(1024) nms_segments_kernel(const int* __restrict__ cls, int M, int* __restrict__ seg_start,
+                                                            int* __restrict__ nseg) {
+  __shared__ int warp_tot[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int p0 = 0; p0 < M; p0 += 1024) {
+    const int p = p0 + tid;
+    const int flag = (p < M) && (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1]));
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int t = warp_tot[w];
+      if (w < warp) before += t;
+      total += t;
+    }
+    const int base = s_base;
+    if (flag) seg_start[base + before + in_warp] = p;
+    __syncthreads();
+    if (tid == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    seg_start[s_base] = M;
+    *nseg = s_base;
+  }
+}
+
+// Greedy scan over the bitmask, one CTA per class segment (plain NMS = one segment covering everything).
+// dynamic smem: removed[nb] (uint64).  Per 64-box block b of the segment: (B) thread 0 resolves the intra-block chain from
+// removed[b] and the diagonal word of each row; (C) the warps OR the kept rows into the `removed` words of the later
+// column blocks of the segment.  Everything the next block needs from global memory (its diagonal words, its rows of
+// the later columns) is requested one full iteration ahead and parked in registers, so the serial chain never waits on
+// L2.  Output: keepflag[rank] = 1 for every kept box, rank = its position in the global score order.
 __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigned long long* __restrict__ maskT,
-                                                                   const int* __restrict__ order, int M, int nb,
-                                                                   long long* __restrict__ keep,
-                                                                   long long* __restrict__ num_keep) {
+                                                                   const int* __restrict__ pos2,
+                                                                   const int* __restrict__ seg_start,
+                                                                   const int* __restrict__ nseg_ptr, int M,
+                                                                   unsigned char* __restrict__ keepflag) {
   extern __shared__ unsigned long long removed[];
   __shared__ __align__(16) unsigned long long s_diag[2][64];
   __shared__ unsigned long long s_kept;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < nb; i += kScanThreads) removed[i] = 0ull;
-  int count = 0;  // kept so far; every thread tracks it from the broadcast `kept` words
+  const int nseg = *nseg_ptr;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int p0 = seg_start[seg], p1 = seg_start[seg + 1];
+    const int b0 = p0 >> 6, nb = ((p1 - 1) >> 6) + 1;  // blocks [b0, nb) of the global tiling touch this segment
+    __syncthreads();                                     // previous segment done with removed[] / s_diag
+    for (int i = b0 + tid; i < nb; i += kScanThreads) removed[i] = 0ull;
 
-  // rows 2*lane, 2*lane+1 of block b, column words w = b + 1 + warp + kScanWarps*c
-  auto fetch = [&](int b, ulonglong2 (&dst)[kMaxColsPerWarp]) {
-    const int r = b * 64 + 2 * lane;
-#pragma unroll
-    for (int c = 0; c < kMaxColsPerWarp; ++c) {
-      const int w = b + 1 + warp + kScanWarps * c;
-      dst[c] = make_ulonglong2(0ull, 0ull);
-      if (b < nb && w < nb) {
-        const unsigned long long* p = maskT + (size_t)w * M + r;
-        if (r + 1 < M) {
-          if ((M & 1) == 0) dst[c] = *reinterpret_cast<const ulonglong2*>(p);  // 16 B aligned when M is even
-          else dst[c] = make_ulonglong2(p[0], p[1]);
-        } else if (r < M) {
-          dst[c].x = p[0];
-        }
-      }
-    }
-  };
-  auto diag_word = [&](int b) -> unsigned long long {
-    const int r = b * 64 + tid;
-    return (b < nb && tid < 64 && r < M) ? maskT[(size_t)b * M + r] : 0ull;
-  };
-  ulonglong2 bufA[kMaxColsPerWarp], bufB[kMaxColsPerWarp];
-  fetch(0, bufA);
-  if (tid < 64) s_diag[0][tid] = diag_word(0);
-  unsigned long long dnext = diag_word(1);
-  __syncthreads();
-
-  // one block of 64 boxes; `cur` holds its rows (requested one iteration ago), `nxt` receives the next block's rows.
-  // The two register buffers ping-pong (no copies: a copy would be a use and would expose the load latency).
-  auto process = [&](int b, ulonglong2 (&cur)[kMaxColsPerWarp], ulonglong2 (&nxt)[kMaxColsPerWarp]) {
-    const int nrow = min(64, M - b * 64);
-    // ---- step B: intra-block chain.  One thread, branch-free: per row the dependent path is
-    //      bit test -> mask -> and/or (about four ALU latencies); the diagonal words are pre-read from shared memory
-    //      sixteen rows at a time so that no load sits on the chain.
-    if (tid == 0) {
-      const unsigned long long rem = removed[b];
-      unsigned rlo = (unsigned)rem, rhi = (unsigned)(rem >> 32), klo = 0u, khi = 0u;
-      const ulonglong2* dg = reinterpret_cast<const ulonglong2*>(s_diag[b & 1]);
-      const unsigned vlo = nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u);               // valid rows 0..31
-      const unsigned vhi = nrow >= 64 ? 0xffffffffu : (nrow > 32 ? ((1u << (nrow - 32)) - 1u) : 0u);  // rows 32..63
-#pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        ulonglong2 d[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int i = blk * 16 + q;
-          const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
-          const unsigned m = 0u - ((~rlo & vlo) >> i & 1u);  // all-ones when row i is alive
-          klo |= m & (1u << i);
-          rlo |= m & (unsigned)dw;
-          rhi |= m & (unsigned)(dw >> 32);
-        }
-      }
-#pragma unroll
-      for (int blk = 2; blk < 4; ++blk) {
-        ulonglong2 d[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int i = (blk - 2) * 16 + q;
-          const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
-          const unsigned m = 0u - ((~rhi & vhi) >> i & 1u);
-          khi |= m & (1u << i);
-          rhi |= m & (unsigned)(dw >> 32);
-        }
-      }
-      s_kept = ((unsigned long long)khi << 32) | klo;
-    }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    const int base = count;
-    // requests for block b+1 / b+2 go out now and are consumed one iteration later
-    fetch(b + 1, nxt);
-    if (tid < 64) s_diag[(b + 1) & 1][tid] = dnext;
-    dnext = diag_word(b + 2);
-    // ---- emit kept indices of this block in score order
-    if (tid < 64 && ((kept >> tid) & 1ull)) {
-      const int rank = __popcll(kept & ((1ull << tid) - 1ull));
-      keep[base + rank] = (long long)order[b * 64 + tid];
-    }
-    // ---- step C: OR kept rows into later column words
-    const unsigned long long k0 = (kept >> (2 * lane)) & 1ull ? ~0ull : 0ull;
-    const unsigned long long k1 = (kept >> (2 * lane + 1)) & 1ull ? ~0ull : 0ull;
-#pragma unroll
-    for (int c = 0; c < kMaxColsPerWarp; ++c) {
-      const int w = b + 1 + warp + kScanWarps * c;
-      if (w < nb) {  // warp-uniform
-        unsigned long long v = (cur[c].x & k0) | (cur[c].y & k1);
-        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
-      }
-    }
-    // columns beyond the register-prefetched window (very large M): plain loads
-    for (int w = b + 1 + warp + kScanWarps * kMaxColsPerWarp; w < nb; w += kScanWarps) {
+    // rows 2*lane, 2*lane+1 of block b, column words w = b + 1 + warp + kScanWarps*c
+    auto fetch = [&](int b, ulonglong2 (&dst)[kMaxColsPerWarp]) {
       const int r = b * 64 + 2 * lane;
-      unsigned long long v = 0ull;
-      if (r < M) v |= maskT[(size_t)w * M + r] & k0;
-      if (r + 1 < M) v |= maskT[(size_t)w * M + r + 1] & k1;
-      unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-      unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-      if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
+#pragma unroll
+      for (int c = 0; c < kMaxColsPerWarp; ++c) {
+        const int w = b + 1 + warp + kScanWarps * c;
+        dst[c] = make_ulonglong2(0ull, 0ull);
+        if (b < nb && w < nb) {
+          const unsigned long long* p = maskT + (size_t)w * M + r;
+          if (r + 1 < M) {
+            if ((M & 1) == 0) dst[c] = *reinterpret_cast<const ulonglong2*>(p);  // 16 B aligned when M is even
+            else dst[c] = make_ulonglong2(p[0], p[1]);
+          } else if (r < M) {
+            dst[c].x = p[0];
+          }
+        }
+      }
+    };
+    auto diag_word = [&](int b) -> unsigned long long {
+      const int r = b * 64 + tid;
+      return (b < nb && tid < 64 && r >= p0 && r < p1) ? maskT[(size_t)b * M + r] : 0ull;
+    };
+    ulonglong2 bufA[kMaxColsPerWarp], bufB[kMaxColsPerWarp];
+    fetch(b0, bufA);
+    if (tid < 64) s_diag[b0 & 1][tid] = diag_word(b0);
+    unsigned long long dnext = diag_word(b0 + 1);
+    __syncthreads();
+
+    // one block of 64 boxes; `cur` holds its rows (requested one iteration ago), `nxt` receives the next block's rows.
+    // The two register buffers ping-pong (no copies: a copy would be a use and would expose the load latency).
+    auto process = [&](int b, ulonglong2 (&cur)[kMaxColsPerWarp], ulonglong2 (&nxt)[kMaxColsPerWarp]) {
+      // rows of this block that belong to the segment
+      const int lo = max(p0 - b * 64, 0), hi = min(p1 - b * 64, 64);  // [lo, hi)
+      const unsigned long long vmask =
+          (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+      // ---- step B: intra-block chain.  One thread, branch-free: per row the dependent path is
+      //      bit test -> mask -> and/or (about four ALU latencies); the diagonal words are pre-read from shared memory
+      //      sixteen rows at a time so that no load sits on the chain.
+      if (tid == 0) {
+        const unsigned long long rem = removed[b];
+        unsigned rlo = (unsigned)rem, rhi = (unsigned)(rem >> 32), klo = 0u, khi = 0u;
+        const ulonglong2* dg = reinterpret_cast<const ulonglong2*>(s_diag[b & 1]);
+        const unsigned vlo = (unsigned)vmask, vhi = (unsigned)(vmask >> 32);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          ulonglong2 d[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int i = blk * 16 + q;
+            const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
+            const unsigned m = 0u - ((~rlo & vlo) >> i & 1u);  // all-ones when row i is alive
+            klo |= m & (1u << i);
+            rlo |= m & (unsigned)dw;
+            rhi |= m & (unsigned)(dw >> 32);
+          }
+        }
+#pragma unroll
+        for (int blk = 2; blk < 4; ++blk) {
+          ulonglong2 d[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int i = (blk - 2) * 16 + q;
+            const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
+            const unsigned m = 0u - ((~rhi & vhi) >> i & 1u);
+            khi |= m & (1u << i);
+            rhi |= m & (unsigned)(dw >> 32);
+          }
+        }
+        s_kept = ((unsigned long long)khi << 32) | klo;
+      }
+      __syncthreads();
+      const unsigned long long kept = s_kept;
+      // requests for block b+1 / b+2 go out now and are consumed one iteration later
+      fetch(b + 1, nxt);
+      if (tid < 64) s_diag[(b + 1) & 1][tid] = dnext;
+      dnext = diag_word(b + 2);
+      // ---- publish the kept boxes of this block at their score rank
+      if (tid < 64 && ((kept >> tid) & 1ull)) {
+        const int p = b * 64 + tid;
+        keepflag[pos2 ? pos2[p] : p] = 1;
+      }
+      // ---- step C: OR kept rows into later column words
+      const unsigned long long k0 = (kept >> (2 * lane)) & 1ull ? ~0ull : 0ull;
+      const unsigned long long k1 = (kept >> (2 * lane + 1)) & 1ull ? ~0ull : 0ull;
+#pragma unroll
+      for (int c = 0; c < kMaxColsPerWarp; ++c) {
+        const int w = b + 1 + warp + kScanWarps * c;
+        if (w < nb) {  // warp-uniform
+          unsigned long long v = (cur[c].x & k0) | (cur[c].y & k1);
+          unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)v);
+          unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+          if (lane == 0) removed[w] |= ((unsigned long long)hi32 << 32) | lo32;
+        }
+      }
+      // columns beyond the register-prefetched window (very large segments): plain loads
+      for (int w = b + 1 + warp + kScanWarps * kMaxColsPerWarp; w < nb; w += kScanWarps) {
+        const int r = b * 64 + 2 * lane;
+        unsigned long long v = 0ull;
+        if (r < M) v |= maskT[(size_t)w * M + r] & k0;
+        if (r + 1 < M) v |= maskT[(size_t)w * M + r + 1] & k1;
+        unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)v);
+        unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0) removed[w] |= ((unsigned long long)hi32 << 32) | lo32;
+      }
+      __syncthreads();  // removed[], s_diag[(b+1)&1] visible; s_kept consumed
+    };
+    for (int b = b0; b < nb; b += 2) {
+      process(b, bufA, bufB);
+      if (b + 1 < nb) process(b + 1, bufB, bufA);
     }
-    count = base + __popcll(kept);
-    __syncthreads();  // removed[], s_diag[(b+1)&1] visible; s_kept consumed
-  };
-  for (int b = 0; b < nb; b += 2) {
-    process(b, bufA, bufB);
-    if (b + 1 < nb) process(b + 1, bufB, bufA);
   }
-  if (tid == 0) *num_keep = (long long)count;
+}
+
+// keep[] = original indices of the flagged ranks, in rank (= score) order; single CTA.
+__global__ void __launch_bounds__(1024) nms_compact_kernel(const unsigned char* __restrict__ keepflag,
+                                                           const int* __restrict__ order, int M,
+                                                           long long* __restrict__ keep, long long* __restrict__ num_keep) {
+  __shared__ int warp_tot[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < M; r0 += 1024) {
+    const int r = r0 + tid;
+    const int flag = (r < M) && keepflag[r];
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int t = warp_tot[w];
+      if (w < warp) before += t;
+      total += t;
+    }
+    const int base = s_base;
+    if (flag) keep[base + before + in_warp] = (long long)order[r];
+    __syncthreads();
+    if (tid == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) *num_keep = (long long)s_base;
 }
 
 struct NmsWorkspace {
   float* sorted_scores;
   int* iota;
   int* order;
+  int* cls;
+  int* cls_sorted;
+  int* pos2;
+  int* seg_start;
+  int* nseg;
+  unsigned char* keepflag;
   float* sorted_boxes;
   float* mm;
   unsigned long long* maskT;
@@ -460,12 +552,21 @@ NmsWorkspace carve(void* base, int64_t M, int rotated) {
   w.sorted_scores = (float*)take(m * 4);
   w.iota = (int*)take(m * 4);
   w.order = (int*)take(m * 4);
+  w.cls = (int*)take(m * 4);
+  w.cls_sorted = (int*)take(m * 4);
+  w.pos2 = (int*)take(m * 4);
+  w.seg_start = (int*)take((m + 1) * 4);
+  w.nseg = (int*)take(16);
+  w.keepflag = (unsigned char*)take(m);
   w.sorted_boxes = (float*)take(m * (rotated ? 5 : 4) * 4);
   w.mm = (float*)take(16);
   w.maskT = (unsigned long long*)take(nb * m * 8);
-  w.cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
-                                            (const int*)nullptr, (int*)nullptr, (int)m);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                            (int*)nullptr, (int)m);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr,
+                                  (int)m);
+  w.cub_bytes = b1 > b2 ? b1 : b2;
   w.cub_temp = take(w.cub_bytes);
   w.total = off;
   return w;
@@ -489,28 +590,47 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   NmsWorkspace w = carve(workspace, M, rotated);
   if (workspace_bytes < w.total) return D2B_EWORKSPACE;
   const int m = (int)M, nb = (m + 63) / 64;
+  const size_t smem = (size_t)nb * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return D2B_EUNSUPPORTED;
+  // 1. global stable descending score order
   iota_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(w.iota, m);
   D2B_CHECK_LAUNCH();
+  size_t cub_bytes = w.cub_bytes;
+  D2B_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, scores, w.sorted_scores, w.iota, w.order, m,
+                                                     0, 32, stream));
+  // 2. batched: class-major order (stable, so scores stay descending inside each class) + segment table
+  const int* cls_sorted = nullptr;
+  const int* pos2 = nullptr;
   if (idxs) {
     if (rotated) coord_range_kernel<true><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
     else coord_range_kernel<false><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
     D2B_CHECK_LAUNCH();
+    class_of_rank_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(idxs, w.order, m, w.cls);
+    D2B_CHECK_LAUNCH();
+    cub_bytes = w.cub_bytes;
+    D2B_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, w.cls, w.cls_sorted, w.iota, w.pos2, m, 0, 32, stream));
+    cls_sorted = w.cls_sorted;
+    pos2 = w.pos2;
   }
-  size_t cub_bytes = w.cub_bytes;
-  D2B_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, scores, w.sorted_scores, w.iota, w.order, m,
-                                                     0, 32, stream));
-  if (rotated) gather_boxes_kernel<true><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, idxs, w.mm, m, w.sorted_boxes);
-  else gather_boxes_kernel<false><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, idxs, w.mm, m, w.sorted_boxes);
+  nms_segments_kernel<<<1, 1024, 0, stream>>>(cls_sorted, m, w.seg_start, w.nseg);
   D2B_CHECK_LAUNCH();
+  // 3. boxes in that order (coordinate offsets of the reference's batched-NMS trick applied in fp32)
+  if (rotated) gather_boxes_kernel<true><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, idxs, w.mm, m, w.sorted_boxes);
+  else gather_boxes_kernel<false><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, idxs, w.mm, m, w.sorted_boxes);
+  D2B_CHECK_LAUNCH();
+  // 4. IoU bitmask (same-class tiles only)
   dim3 grid(nb, nb);
-  if (rotated) nms_mask_kernel<true><<<grid, 64, 0, stream>>>(w.sorted_boxes, m, iou_threshold, w.maskT);
-  else nms_mask_kernel<false><<<grid, 64, 0, stream>>>(w.sorted_boxes, m, iou_threshold, w.maskT);
+  if (rotated) nms_mask_kernel<true><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
+  else nms_mask_kernel<false><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
-  size_t smem = (size_t)nb * sizeof(unsigned long long);
-  if (smem > 200 * 1024) return D2B_EUNSUPPORTED;
+  // 5. per-segment greedy scans in parallel, then compaction in global score order
+  D2B_CUDA(cudaMemsetAsync(w.keepflag, 0, (size_t)m, stream));
   if (smem > 40 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_scan_kernel<<<1, kScanThreads, smem, stream>>>(w.maskT, w.order, m, nb, (long long*)keep, (long long*)num_keep);
+  const int scan_grid = idxs ? (m < 2 * kNumSMs ? m : 2 * kNumSMs) : 1;
+  nms_scan_kernel<<<scan_grid, kScanThreads, smem, stream>>>(w.maskT, pos2, w.seg_start, w.nseg, m, w.keepflag);
+  D2B_CHECK_LAUNCH();
+  nms_compact_kernel<<<1, 1024, 0, stream>>>(w.keepflag, w.order, m, (long long*)keep, (long long*)num_keep);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
