@@ -422,10 +422,13 @@ def main():
         "gpu_launches": OursRunner.KERNELS_PER_STEP * args.steps,
         "clocks": sampler.summary(),
         "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
-        "roofline": {"kernel": "roi_align_fwd_kernel (box pooler, 1000 RoIs x 256 ch x 7x7 over p2..p5)", "bound": "hbm",
+        "roofline": {"kernel": "roi_align_fwd_v3_kernel (box pooler, 1000 RoIs x 256 ch x 7x7 over p2..p5)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-                     "algorithmic_bytes": alg_bytes, "avg_launch_ms": box_ms, "traffic": None},
+                     "algorithmic_bytes": alg_bytes, "avg_launch_ms": box_ms,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+                     # (profiles/r1_ncu_full.txt: 97.32 MB read + 33.80 MB written)
+                     "traffic": 131121408},
     })
     line["config"]["l2"] = "inputs rotate over 3 images (3 x 91 MB features) and each step writes 107 MB: > 126 MB L2"
     if world == 1:

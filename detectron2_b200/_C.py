@@ -48,7 +48,8 @@ def _declare(lib):
         "d2b_nms_workspace_bytes": (sz, [i64, i]),
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64p, i64p, vp, sz, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
-        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, f32p, vp]),
+        "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i]),
+        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, f32p, vp, sz, vp]),
         "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams)]),
         "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), f32p, f32p, f32p, f32p,
                                          f32p, vp, sz, vp]),

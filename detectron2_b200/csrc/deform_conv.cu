@@ -373,20 +373,30 @@ __global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float* __restr
 }  // namespace
 
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                               const float* bias, const d2b_dcn_params* p, int precision, float* out, void* stream);
+                               const float* bias, const d2b_dcn_params* p, int precision, float* out, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int d2b_deform_conv_tc_supported(const d2b_dcn_params* p);
+size_t d2b_deform_conv_tc_workspace_bytes(const d2b_dcn_params* p);
+
+// precision: 0 = fp32 FFMA, 1 = bf16x3 on tcgen05, 2 = bf16 on tcgen05, -1 = auto (1 when the tensor-core kernel takes
+// the shape, else 0 -- both are fp32-class, so "auto" never lowers accuracy)
+D2B_API size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision) {
+  if (precision == 0) return 0;
+  if (precision == -1 && !d2b_deform_conv_tc_supported(p)) return 0;
+  return d2b_deform_conv_tc_workspace_bytes(p);
+}
 
 D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask, const float* weight,
                                     const float* bias, const d2b_dcn_params* p, int precision, float* out,
-                                    void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
   if (d.N == 0) return D2B_OK;
   if (!x || !offset || !weight || !out) return D2B_EINVAL;
-  if (precision != 0) {
-    int rc = d2b_deform_conv_forward_tc(x, offset, mask, weight, bias, p, precision, out, stream);
-    if (rc != D2B_EUNSUPPORTED) return rc;
-    return rc;  // no silent precision downgrade: the caller asked for the tensor-core path
-  }
+  if (precision < -1 || precision > 2) return D2B_EINVAL;
+  if (precision == -1) precision = d2b_deform_conv_tc_supported(p) ? 1 : 0;
+  if (precision != 0)  // no silent precision / path change: an unsupported shape is reported, not rerouted
+    return d2b_deform_conv_forward_tc(x, offset, mask, weight, bias, p, precision, out, workspace, workspace_bytes, stream);
   dim3 grid(d2b_cdiv(d.HoWo, BN), d2b_cdiv(d.opg, BM), d.N * d.G);
   dcn_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, offset, mask, weight, bias, d, out);
   D2B_CHECK_LAUNCH();

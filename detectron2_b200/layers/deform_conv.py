@@ -11,8 +11,9 @@ from torch.nn.modules.utils import _pair
 
 from .. import ops
 
-# 0 = fp32 FFMA (parity), 1 = bf16x3 tcgen05, 2 = bf16 tcgen05.  Module attribute so callers can opt in.
-DEFAULT_PRECISION = 0
+# -1 = auto: bf16x3 operand split on tcgen05/TMEM when the tensor-core kernel takes the shape, else fp32 FFMA (both are
+# fp32-class, <= 1e-4 rel);  0 = fp32 FFMA;  1 = bf16x3 tcgen05;  2 = plain bf16 tcgen05 (autocast-style operands).
+DEFAULT_PRECISION = -1
 
 
 def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

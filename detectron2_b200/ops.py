@@ -326,9 +326,12 @@ def deform_conv_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Te
     xf, of, mf, wf, bf = _f32c(x), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(bias)
     p = _dcn_params(xf, wf, stride, padding, dilation, groups, deformable_groups)
     out = torch.empty(dcn_output_shape(xf, wf, stride, padding, dilation), dtype=torch.float32, device=x.device)
+    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), precision)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device):
         check(_C.lib().d2b_deform_conv_forward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision,
-                                               ptr(out), stream_ptr(x.device)), "deform_conv_forward")
+                                               ptr(out), ptr(ws), ws_bytes, stream_ptr(x.device)),
+              "deform_conv_forward")
     return out.to(x.dtype)
 
 

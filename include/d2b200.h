@@ -121,9 +121,14 @@ typedef struct {
       deformable_groups;
 } d2b_dcn_params;
 
+/* precision: 0 = fp32 FFMA, 1 = bf16x3 split on tcgen05 (fp32-class accuracy), 2 = plain bf16 on tcgen05,
+ * -1 = auto (1 when the tensor-core kernel takes the shape, else 0).  The tensor-core path needs a workspace for the
+ * bf16 weight copy: d2b_deform_conv_forward_workspace_bytes(p, precision) bytes (0 for the FFMA path). */
+size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision);
 int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask,
                             const float* weight, const float* bias, const d2b_dcn_params* p,
-                            int precision, float* out, void* stream);
+                            int precision, float* out, void* workspace, size_t workspace_bytes,
+                            void* stream);
 /* Backward.  grad_columns scratch: workspace of d2b_deform_conv_backward_workspace_bytes(p) bytes.
  * Any of the grad outputs may be NULL to skip it.  Outputs are fully written (zero-filled inside). */
 size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p);

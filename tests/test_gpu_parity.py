@@ -428,3 +428,45 @@ def test_roi_pooler_fused_vs_reference_loop(out, ptype):
         gref = orc.roi_align_backward(go[inds], rois[inds], s, out, out, 2, 32, feats[l].shape[2], feats[l].shape[3], 0, aligned)
         ok, err = rel_close(fg[l].grad, gref, atol=2e-4)
         assert ok, (l, err)
+
+
+# ------------------------------------------------------------------------------- deformable conv on tcgen05 / TMEM
+@pytest.mark.parametrize("cin,cout,h,w,grp,dg,mod,stride,prec", [
+    (64, 64, 12, 20, 1, 1, False, 1, 1), (128, 128, 25, 42, 1, 1, False, 1, 1), (128, 192, 17, 23, 2, 1, True, 1, 1),
+    (256, 256, 21, 19, 1, 2, True, 2, 1), (128, 128, 25, 42, 1, 1, False, 1, 2)])
+def test_deform_conv_tensor_core_vs_oracle(cin, cout, h, w, grp, dg, mod, stride, prec):
+    from detectron2_b200 import ops
+
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    n, k, p = 2, 3, 1
+    ho, wo = (h + 2 * p - k) // stride + 1, (w + 2 * p - k) // stride + 1
+    x = torch.randn(n, cin, h, w, generator=g)
+    off = torch.randn(n, 2 * dg * k * k, ho, wo, generator=g) * 2
+    mask = torch.sigmoid(torch.randn(n, dg * k * k, ho, wo, generator=g)) if mod else None
+    wt = torch.randn(cout, cin // grp, k, k, generator=g) * (1.0 / math.sqrt(cin // grp * 9))
+    bias = torch.randn(cout, generator=g) if mod else None
+    ref = orc.deform_conv_forward(x, off, mask, wt, bias, stride, p, 1, grp, dg)
+    dev = lambda t: None if t is None else t.to(DEV)  # noqa: E731
+    y = ops.deform_conv_op(dev(x), dev(off), dev(mask), dev(wt), dev(bias), [stride, stride], [p, p], [1, 1], grp, dg, prec)
+    err = (y.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 1e-4 if prec == 1 else 2e-2  # bf16x3 split: fp32-class; plain bf16: 8-bit mantissa operands
+    assert err <= tol * scale, (err, scale)
+    # the fp32 FFMA path and "auto" agree with it as well
+    y0 = ops.deform_conv_op(dev(x), dev(off), dev(mask), dev(wt), dev(bias), [stride, stride], [p, p], [1, 1], grp, dg, 0)
+    assert (y0.cpu() - ref).abs().max().item() <= 1e-4 * scale
+    if prec == 1:
+        ya = ops.deform_conv_op(dev(x), dev(off), dev(mask), dev(wt), dev(bias), [stride, stride], [p, p], [1, 1], grp, dg, -1)
+        assert torch.equal(ya, y)
+
+
+def test_deform_conv_tensor_core_unsupported_shape_is_loud():
+    from detectron2_b200 import ops
+
+    x = torch.randn(1, 48, 8, 8, device=DEV)
+    off = torch.zeros(1, 18, 8, 8, device=DEV)
+    wt = torch.randn(48, 48, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.deform_conv_op(x, off, None, wt, None, [1, 1], [1, 1], [1, 1], 1, 1, 1)
+    y = ops.deform_conv_op(x, off, None, wt, None, [1, 1], [1, 1], [1, 1], 1, 1, -1)  # auto -> FFMA path
+    assert y.shape == (1, 48, 8, 8)

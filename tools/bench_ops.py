@@ -1,0 +1,170 @@
+"""Per-op micro-benchmarks at the BASELINE.json / SURVEY 8(d) shapes, next to the reference's GPU kernels where the
+image has them (torchvision CUDA ops = the reference's backend for roi_align / nms / deform_conv2d).
+
+    python tools/bench_ops.py [--out profiles/r1_ops.md]
+
+Timing: CUDA events around REP back-to-back launches after warm-up; inputs rotate over NBUF copies (> L2) for the
+bandwidth-bound ops.  Reported: our time, reference-GPU time (tv), algorithmic bytes / flops and achieved fraction of
+the measured peaks (MEASURED_PEAKS.json).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import detectron2_b200.layers as L  # noqa: E402
+from detectron2_b200.poolers import ROIPooler  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, rep=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(rep):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / rep * 1e3  # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_ops.md"))
+    args = ap.parse_args()
+    try:
+        import torchvision
+        tv = torchvision.ops
+    except Exception:
+        tv = None
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    rows = []
+
+    def add(name, ours_us, ref_us, note=""):
+        rows.append((name, ours_us, ref_us, note))
+        print("%-58s ours %9.1f us   ref-gpu %s   %s" % (name, ours_us, ("%9.1f us" % ref_us) if ref_us else "      n/a", note), flush=True)
+
+    g = torch.Generator().manual_seed(0)
+    # ---- cfg1: single-level RoIAlign 512 boxes over 1x256x200x304
+    x = torch.rand(1, 256, 200, 304, generator=g).to(DEV)
+    k = 512
+    cx, cy = torch.rand(k, generator=g) * 1216, torch.rand(k, generator=g) * 800
+    w, h = 16 + torch.rand(k, generator=g) * 300, 16 + torch.rand(k, generator=g) * 300
+    rois = torch.stack([torch.zeros(k), (cx - w / 2).clamp(0, 1216), (cy - h / 2).clamp(0, 800), (cx + w / 2).clamp(0, 1216),
+                        (cy + h / 2).clamp(0, 800)], 1).to(DEV)
+    for sr in (0, 2):
+        op = L.ROIAlign((7, 7), 0.25, sr, True)
+        t = timeit(lambda: op(x, rois))
+        tr = timeit(lambda: tv.roi_align(x, rois, (7, 7), 0.25, sr, True)) if tv else None
+        add("roi_align fwd cfg1 (512 boxes, 1x256x200x304, sr=%d)" % sr, t, tr, "alg 87.96 MB -> %.0f GB/s" % (87.96e6 / t / 1e3))
+        xg = x.clone().requires_grad_(True)
+        y = op(xg, rois)
+        go = torch.randn_like(y)
+        t = timeit(lambda: torch.autograd.grad(y, xg, go, retain_graph=True))
+        if tv:
+            y2 = tv.roi_align(xg, rois, (7, 7), 0.25, sr, True)
+            tr = timeit(lambda: torch.autograd.grad(y2, xg, go, retain_graph=True))
+        add("roi_align bwd cfg1 (sr=%d)" % sr, t, tr if tv else None)
+    # ---- cfg2/3 poolers (fused multi-level) fwd + bwd
+    d = bench.make_image_inputs(1)
+    feats = [f.to(DEV) for f in d["feats"]]
+    props = d["proposals"].to(DEV)
+    scales = [s for (_, _, s) in bench.LEVELS]
+    for out, kk in ((7, 1000), (14, 100)):
+        pooler = ROIPooler(out, scales, 0, "ROIAlignV2")
+        b = props[:kk].contiguous()
+        t = timeit(lambda: pooler(feats, [b]))
+
+        def ref_pooler():
+            sizes = torch.sqrt((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))
+            lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).to(torch.int64) - 2
+            r5 = torch.cat([torch.zeros(len(b), 1, device=DEV), b], 1)
+            res = torch.zeros(len(b), 256, out, out, device=DEV)
+            for l, s in enumerate(scales):
+                inds = torch.nonzero(lv == l, as_tuple=True)[0]
+                res.index_put_((inds,), tv.roi_align(feats[l], r5[inds], (out, out), s, 0, True))
+            return res
+
+        tr = timeit(ref_pooler) if tv else None
+        add("ROIPooler fwd %dx%d K=%d (p2..p5)" % (out, out, kk), t, tr, "ref = per-level loop over tv.roi_align")
+        fg = [f.clone().requires_grad_(True) for f in feats]
+        y = pooler(fg, [b])
+        go = torch.randn_like(y)
+        t = timeit(lambda: torch.autograd.grad(y, fg, go, retain_graph=True))
+        add("ROIPooler bwd %dx%d K=%d" % (out, out, kk), t, None)
+    # ---- NMS
+    for m, ncls, thr, tag in ((4819, 5, 0.7, "RPN test"), (8819, 5, 0.7, "RPN train"), (5000, 80, 0.5, "RetinaNet/FastRCNN"),
+                              (25000, 80, 0.5, "stress")):
+        gb = torch.Generator().manual_seed(m)
+        boxes = bench.synth_boxes(gb, m, 16, 500).to(DEV)
+        scores = torch.rand(m, generator=gb).to(DEV)
+        idxs = torch.randint(0, ncls, (m,), generator=gb).to(DEV)
+        t = timeit(lambda: L.batched_nms(boxes, scores, idxs, thr))
+        tr = timeit(lambda: tv.boxes.batched_nms(boxes, scores, idxs, thr)) if tv else None
+        add("batched_nms M=%d classes=%d (%s)" % (m, ncls, tag), t, tr, "%.1f Mpairs/s" % (m * (m - 1) / 2 / t))
+    # ---- rotated
+    gb = torch.Generator().manual_seed(5)
+    rb = torch.cat([torch.rand(1000, 2, generator=gb) * 300, 1 + torch.rand(1000, 2, generator=gb) * 120,
+                    (torch.rand(1000, 1, generator=gb) - 0.5) * 360], 1).to(DEV)
+    t = timeit(lambda: L.pairwise_iou_rotated(rb, rb))
+    add("box_iou_rotated 1000x1000", t, None, "%.1f Mpairs/s" % (1e6 / t))
+    sc = torch.rand(1000, generator=gb).to(DEV)
+    t = timeit(lambda: L.nms_rotated(rb, sc, 0.5))
+    add("nms_rotated M=1000", t, None)
+    xr = torch.rand(2, 256, 50, 84, generator=gb).to(DEV)
+    rr = torch.cat([torch.randint(0, 2, (512, 1), generator=gb).float(), torch.rand(512, 2, generator=gb) * 800,
+                    16 + torch.rand(512, 2, generator=gb) * 300, (torch.rand(512, 1, generator=gb) - 0.5) * 360], 1).to(DEV)
+    opr = L.ROIAlignRotated((7, 7), 1 / 16, 0)
+    t = timeit(lambda: opr(xr, rr))
+    add("roi_align_rotated fwd 512 boxes, 2x256x50x84", t, None)
+    # ---- paste
+    masks, det = d["masks"].to(DEV), d["det_boxes"][:100].to(DEV)
+    t = timeit(lambda: L.paste_masks_in_image(masks, det, (800, 1333), 0.5))
+    add("paste_masks 100 x 28x28 -> 800x1333", t, None, "alg 106.96 MB -> %.0f GB/s (%.2f of HBM peak)" % (106.96e6 / t / 1e3, 106.96e6 / t / 1e3 / hbm))
+    # ---- deformable conv layer sweep, N=2, k=3, pad=1
+    for cin, hh, ww, grp in ((128, 100, 168, 1), (256, 50, 84, 1), (512, 25, 42, 1), (512, 100, 168, 32), (1024, 50, 84, 32),
+                             (2048, 25, 42, 32)):
+        n = 2
+        xx = torch.randn(n, cin, hh, ww, device=DEV)
+        off = torch.randn(n, 18, hh, ww, device=DEV) * 2
+        wt = torch.randn(cin, cin // grp, 3, 3, device=DEV) * 0.05
+        flops = 2.0 * n * cin * (cin // grp) * 9 * hh * ww
+        from detectron2_b200 import ops as _ops
+        tr = timeit(lambda: tv.deform_conv2d(xx, off, wt, None, 1, 1, 1), rep=5, warm=1) if (tv and True) else None
+        for prec, tag in ((0, "fp32 FFMA"), (1, "bf16x3 tcgen05"), (2, "bf16 tcgen05")):
+            try:
+                t = timeit(lambda: _ops.deform_conv_op(xx, off, None, wt, None, [1, 1], [1, 1], [1, 1], grp, 1, prec), rep=10, warm=2)
+            except RuntimeError:
+                continue
+            add("deform_conv fwd C=%d %dx%d g=%d (%s)" % (cin, hh, ww, grp, tag), t, tr, "%.2f TFLOP/s" % (flops / t / 1e6))
+        xg, og, wg = xx.clone().requires_grad_(True), off.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        y = L.deform_conv(xg, og, wg, 1, 1, 1, grp, 1)
+        go = torch.randn_like(y)
+        t = timeit(lambda: torch.autograd.grad(y, (xg, og, wg), go, retain_graph=True), rep=3, warm=1)
+        if tv:
+            y2 = tv.deform_conv2d(xg, og, wg, None, 1, 1, 1)
+            tr = timeit(lambda: torch.autograd.grad(y2, (xg, og, wg), go, retain_graph=True), rep=3, warm=1)
+        add("deform_conv bwd C=%d %dx%d g=%d (fp32)" % (cin, hh, ww, grp), t, tr if tv else None, "%.2f TFLOP/s" % (2 * flops / t / 1e6))
+
+    with open(args.out, "w") as f:
+        f.write("# Per-op timings on B200 (tools/bench_ops.py) — ours vs the reference's GPU kernels (torchvision %s CUDA ops)\n\n" %
+                (getattr(__import__('torchvision'), '__version__', '?') if tv else 'n/a'))
+        f.write("Eager launches incl. Python op dispatch (both sides); CUDA events, mean of back-to-back launches.\n\n")
+        f.write("| op / shape | ours (us) | reference GPU (us) | speed-up | note |\n|---|---:|---:|---:|---|\n")
+        for name, a, b, note in rows:
+            f.write("| %s | %.1f | %s | %s | %s |\n" % (name, a, ("%.1f" % b) if b else "n/a", ("%.2fx" % (b / a)) if b else "", note))
+    print("wrote", args.out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Turn gpurun_out/*.csv / *.ncu-rep into the small text summaries committed under profiles/."""
+import collections
+import csv
+import subprocess
+import sys
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"])
+        u = row["Metric Unit"]
+        v = v / 1000 if u in ("ns", "nsecond") else (v * 1000 if u in ("ms", "msecond") else v)
+        agg.setdefault(row["Kernel Name"][:90], []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    with open(out, "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+        f.write("%-92s %5s %10s %7s\n" % ("kernel", "n", "avg_us", "share"))
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write("%-92s %5d %10.1f %6.1f%%\n" % (k, len(v), sum(v) / len(v), 100 * sum(v) / tot))
+    print(open(out).read())
+
+
+def full(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "smsp__inst_executed.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on ; per-launch raw metrics\n")
+        for r in rows[2:]:
+            f.write("\n## %s (launch id %s)\n" % (r[idx["Kernel Name"]][:100], r[idx["ID"]]))
+            for w in want:
+                if w in idx:
+                    f.write("%-72s %18s %s\n" % (w, r[idx[w]], units[idx[w]]))
+    print(open(out).read())
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        full(sys.argv[2], sys.argv[3])
