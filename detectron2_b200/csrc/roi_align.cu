@@ -316,8 +316,10 @@ __global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, co
 //      with lane == bin, reading taps from shared memory, and stores its outputs straight to global memory
 //      (lanes = consecutive bins -> coalesced).  There is no CTA-wide barrier in the channel loop, so the 24 resident
 //      warps per SM overlap each other's load latency freely.
-// RoIs whose footprint exceeds a warp's slice are processed in bands of bin rows; pathological RoIs (tap list
-// overflow, one bin row larger than the slice, pooled size > 16) take the direct path (taps on the fly from global).
+// RoIs whose footprint exceeds a warp's slice are processed in bands of bin rows.  Very large or sparsely sampled RoIs
+// (fixed sampling_ratio on a big box: far fewer taps than footprint pixels) skip the staging and read their taps
+// straight from global memory through the same lists; only a tap-list overflow (sampling grid > 31) or a pooled size
+// > 16 falls back to computing taps on the fly.
 constexpr int kMaxE = 32;   // taps per bin row / column: covers sampling grids up to 31 (clipped, elongated RoIs)
 constexpr int kMaxP = 16;   // pooled size supported by the staged path
 constexpr int kChW = 4;     // channels per warp
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
         }
       }
       for (int pw = 0; pw < PW; ++pw) nxu = max(nxu, xn[pw]);
+      nxu = (nxu + 3) & ~3;  // multiple of 4 (<= kMaxE): the global-gather path consumes column taps four at a time
     }
     if (!direct && fw > 0 && ymax >= ymin) {
       if ((long long)(ymax - ymin + 1) * fw > kRowoffCap) direct = 1;
@@ -458,6 +461,16 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
     }
     band_ph0[nb] = PH;
     s_nbands = nb;
+    // mode 0: staged footprint; 1: tap lists + loads straight from global (footprint too large for a warp's slice, or
+    // sparsely sampled: fewer distinct taps than half the footprint pixels); 2: tap lists overflowed -> taps on the fly
+    int mode = s_overflow ? 2 : (direct ? 1 : 0);
+    if (mode == 0 && fw > 0 && ymax >= ymin) {
+      int sy = 0, sx = 0;
+      for (int ph = 0; ph < PH; ++ph) sy += yn[ph];
+      for (int pw = 0; pw < PW; ++pw) sx += xn[pw];
+      if (2LL * sy * sx < (long long)(ymax - ymin + 1) * fw) mode = 1;
+    }
+    direct = mode;
     s_direct = direct;
     s_nyu = nyu;
     s_nxu = nxu;
@@ -465,9 +478,10 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
     s_ymax = ymax;
   }
   __syncthreads();
-  const bool direct = s_direct != 0;
+  const int mode = s_direct;
+  const bool direct = mode == 2;
   const int nbands = s_nbands, nyu = s_nyu, nxu = s_nxu, ymin = s_ymin;
-  if (!direct) {
+  if (mode != 2) {
     // pad the lists to the uniform lengths with zero-weight taps on a valid row / column; make columns relative
     if (tid < PH) {
       const int n = yn[tid];
@@ -478,7 +492,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
       for (int e = 0; e < n; ++e) xtab[e * kMaxP + pw].idx -= xmin;
       for (int e = n; e < nxu; ++e) xtab[e * kMaxP + pw] = CTap{0, 0.f};
     }
-    if (fw > 0 && s_ymax >= ymin) {
+    if (mode == 0 && fw > 0 && s_ymax >= ymin) {
       const int npx_all = (s_ymax - ymin + 1) * fw;  // <= kRowoffCap by construction
       for (int i = tid; i < npx_all; i += kV3Threads) {
         const int y = i / fw, x = i - y * fw;
@@ -518,6 +532,47 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
     const float* __restrict__ pl[kChW];
 #pragma unroll
     for (int q = 0; q < kChW; ++q) pl[q] = base + (size_t)min(q, cn - 1) * H * W;
+
+    if (mode == 1) {  // tap lists, data straight from global / L2 (large or sparsely sampled RoIs)
+      for (int b0 = 0; b0 < bins; b0 += 32) {
+        const int bin = b0 + lane;
+        const bool live = bin < bins;
+        const int bb = live ? bin : 0;
+        const int ph = bb / PW, pw = bb - (bb / PW) * PW;
+        float acc[kChW];
+#pragma unroll
+        for (int q = 0; q < kChW; ++q) acc[q] = 0.f;
+        for (int ey = 0; ey < nyu; ++ey) {
+          const CTap ty = ytab[ey * kMaxP + ph];
+          const int rbase = ty.idx * W + xmin;
+          float r[kChW];
+#pragma unroll
+          for (int q = 0; q < kChW; ++q) r[q] = 0.f;
+          for (int ex = 0; ex < nxu; ex += 4) {  // 4 taps x kChW channels = 16 independent loads in flight
+            CTap tx[4];
+            float v[4][kChW];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tx[e] = xtab[(ex + e) * kMaxP + pw];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+              for (int q = 0; q < kChW; ++q) v[e][q] = __ldg(pl[q] + rbase + tx[e].idx);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+              for (int q = 0; q < kChW; ++q) r[q] = fmaf(tx[e].w, v[e][q], r[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < kChW; ++q) acc[q] = fmaf(ty.w, r[q], acc[q]);
+        }
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < kChW; ++q)
+            if (q < cn) obase[q * bins + bin] = acc[q] * g.inv_count;
+        }
+      }
+      continue;
+    }
 
     for (int band = 0; band < nbands; ++band) {
       const int ph0 = band_ph0[band], ph1 = band_ph0[band + 1];
