@@ -122,64 +122,6 @@ __device__ __forceinline__ Tap1 make_tap1(float v, int size) {
   return t;
 }
 
-// ------------------------------------------------------------------ axis-aligned forward
-// smem: ytab[PH*gh], xtab[PW*gw]  (Tap1 each). Falls back to on-the-fly taps when the tables do not fit.
-template <int MAXTAB>
-__global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const Pyr P, const float* __restrict__ rois, int C,
-                                                                 int PH, int PW, int sr, int aligned, int c_per_cta,
-                                                                 float* __restrict__ out) {
-  __shared__ Tap1 ytab[MAXTAB];
-  __shared__ Tap1 xtab[MAXTAB];
-  const int k = blockIdx.x;
-  const int c0 = blockIdx.y * c_per_cta;
-  const int cn = min(c_per_cta, C - c0);
-  const int lvl = pick_level(P, rois + (size_t)k * 5);
-  const float* __restrict__ in = P.feat[lvl];
-  const int H = P.H[lvl], W = P.W[lvl];
-  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
-  const int ny = PH * g.gh, nx = PW * g.gw;
-  const bool tab = (ny <= MAXTAB) && (nx <= MAXTAB);
-  if (tab) {
-    for (int i = threadIdx.x; i < ny; i += kThreads) {
-      int ph = i / g.gh, iy = i - ph * g.gh;
-      float y = g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh;
-      ytab[i] = make_tap1(y, H);
-    }
-    for (int i = threadIdx.x; i < nx; i += kThreads) {
-      int pw = i / g.gw, ix = i - pw * g.gw;
-      float x = g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw;
-      xtab[i] = make_tap1(x, W);
-    }
-    __syncthreads();
-  }
-  const int bins = PH * PW;
-  const int total = cn * bins;
-  const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
-  float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
-  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-    int c = idx / bins;
-    int bin = idx - c * bins;
-    int ph = bin / PW, pw = bin - ph * PW;
-    const float* __restrict__ plane = base + (size_t)c * H * W;
-    float acc = 0.f;
-    for (int iy = 0; iy < g.gh; ++iy) {
-      Tap1 ty;
-      if (tab) ty = ytab[ph * g.gh + iy];
-      else ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
-      const float* __restrict__ r0 = plane + (size_t)ty.lo * W;
-      const float* __restrict__ r1 = plane + (size_t)ty.hi * W;
-      for (int ix = 0; ix < g.gw; ++ix) {
-        Tap1 tx;
-        if (tab) tx = xtab[pw * g.gw + ix];
-        else tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
-        float v1 = __ldg(r0 + tx.lo), v2 = __ldg(r0 + tx.hi), v3 = __ldg(r1 + tx.lo), v4 = __ldg(r1 + tx.hi);
-        acc += (ty.wl * tx.wl) * v1 + (ty.wl * tx.wh) * v2 + (ty.wh * tx.wl) * v3 + (ty.wh * tx.wh) * v4;
-      }
-    }
-    obase[idx] = acc * g.inv_count;
-  }
-}
-
 // ------------------------------------------------------------------ rotated forward
 struct Tap2 {
   int p1, p2, p3, p4;
@@ -349,9 +291,15 @@ __device__ __forceinline__ void add_tap(CTap* list, int stride, int& n, int idx,
   ++n;
 }
 
-__global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const Pyr P, const float* __restrict__ rois,
-                                                                         int C, int PH, int PW, int sr, int aligned,
-                                                                         int groups_per_cta, float* __restrict__ out) {
+// BWD = false: out[k,c,bin] = pooled value.   BWD = true: the transpose -- gout[k,c,bin] is scattered with the same tap
+// weights into the level's gradient map; a warp accumulates the footprint of its kChW channels in its shared-memory
+// slice (shared-memory atomics between the bins of one RoI) and flushes every touched pixel with ONE red.global.add,
+// instead of the reference's 4*g*g global atomics per output element (ROIAlignRotated_cuda.cu:311-318).
+template <bool BWD>
+__global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P, const float* __restrict__ rois, int C,
+                                                                     int PH, int PW, int sr, int aligned,
+                                                                     int groups_per_cta, const float* __restrict__ gout,
+                                                                     float* __restrict__ out) {
   extern __shared__ __align__(16) float stage_all[];  // [warp][kChW][kCapPx]
   __shared__ CTap ytab[kMaxE * kMaxP];  // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];  // [tap][pw]   (idx relative to the footprint's first column)
@@ -363,7 +311,8 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
   const int k = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lvl = pick_level(P, rois + (size_t)k * 5);
-  const float* __restrict__ in = P.feat[lvl];
+  const float* __restrict__ in = BWD ? nullptr : P.feat[lvl];
+  float* __restrict__ gin = BWD ? P.grad[lvl] : nullptr;
   const int H = P.H[lvl], W = P.W[lvl];
   const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
   const int bins = PH * PW;
@@ -423,7 +372,6 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
         }
       }
       for (int pw = 0; pw < PW; ++pw) nxu = max(nxu, xn[pw]);
-      nxu = (nxu + 3) & ~3;  // multiple of 4 (<= kMaxE): the global-gather path consumes column taps four at a time
     }
     if (!direct && fw > 0 && ymax >= ymin) {
       if ((long long)(ymax - ymin + 1) * fw > kRowoffCap) direct = 1;
@@ -490,7 +438,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
     } else if (tid >= 32 && tid < 32 + PW) {
       const int pw = tid - 32, n = xn[pw];
       for (int e = 0; e < n; ++e) xtab[e * kMaxP + pw].idx -= xmin;
-      for (int e = n; e < nxu; ++e) xtab[e * kMaxP + pw] = CTap{0, 0.f};
+      for (int e = n; e < ((nxu + 3) & ~3); ++e) xtab[e * kMaxP + pw] = CTap{0, 0.f};  // gather path reads 4 at a time
     }
     if (mode == 0 && fw > 0 && s_ymax >= ymin) {
       const int npx_all = (s_ymax - ymin + 1) * fw;  // <= kRowoffCap by construction
@@ -506,8 +454,29 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
   for (int grp = g_begin + warp; grp < g_end; grp += kV3Warps) {
     const int c0 = grp * kChW;
     const int cn = min(kChW, C - c0);
-    const float* __restrict__ base = in + ((size_t)g.b * C + c0) * H * W;
-    float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
+    const float* __restrict__ base = BWD ? nullptr : in + ((size_t)g.b * C + c0) * H * W;
+    float* __restrict__ gbase = BWD ? gin + ((size_t)g.b * C + c0) * H * W : nullptr;
+    float* __restrict__ obase = BWD ? nullptr : out + ((size_t)k * C + c0) * bins;
+    const float* __restrict__ gobase = BWD ? gout + ((size_t)k * C + c0) * bins : nullptr;
+    if (direct && BWD) {  // rare: taps on the fly, global atomics per sample
+      for (int idx = lane; idx < cn * bins; idx += 32) {
+        const int c = idx / bins, bin = idx - c * bins;
+        const int ph = bin / PW, pw = bin - ph * PW;
+        float* __restrict__ plane = gbase + (size_t)c * H * W;
+        const float gv = gobase[idx] * g.inv_count;
+        for (int iy = 0; iy < g.gh; ++iy) {
+          Tap1 ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+          for (int ix = 0; ix < g.gw; ++ix) {
+            Tap1 tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+            atomicAdd(plane + ty.lo * W + tx.lo, gv * ty.wl * tx.wl);
+            atomicAdd(plane + ty.lo * W + tx.hi, gv * ty.wl * tx.wh);
+            atomicAdd(plane + ty.hi * W + tx.lo, gv * ty.wh * tx.wl);
+            atomicAdd(plane + ty.hi * W + tx.hi, gv * ty.wh * tx.wh);
+          }
+        }
+      }
+      continue;
+    }
     if (direct) {  // rare: taps on the fly, straight from global memory (one warp: its kChW channels)
       for (int idx = lane; idx < cn * bins; idx += 32) {
         const int c = idx / bins, bin = idx - c * bins;
@@ -530,8 +499,83 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
     }
     // channel planes of this warp (a ragged last group re-reads its last valid plane into unused slices)
     const float* __restrict__ pl[kChW];
+    float* __restrict__ gpl[kChW];
 #pragma unroll
-    for (int q = 0; q < kChW; ++q) pl[q] = base + (size_t)min(q, cn - 1) * H * W;
+    for (int q = 0; q < kChW; ++q) {
+      pl[q] = BWD ? nullptr : base + (size_t)min(q, cn - 1) * H * W;
+      gpl[q] = BWD ? gbase + (size_t)min(q, cn - 1) * H * W : nullptr;
+    }
+
+    if (BWD && mode == 1) {  // tap lists, one global atomic per (tap, channel)
+      for (int b0 = 0; b0 < bins; b0 += 32) {
+        const int bin = b0 + lane;
+        if (bin >= bins) continue;
+        const int ph = bin / PW, pw = bin - (bin / PW) * PW;
+        float gv[kChW];
+#pragma unroll
+        for (int q = 0; q < kChW; ++q) gv[q] = q < cn ? gobase[q * bins + bin] * g.inv_count : 0.f;
+        for (int ey = 0; ey < nyu; ++ey) {
+          const CTap ty = ytab[ey * kMaxP + ph];
+          if (ty.w == 0.f) continue;
+          const int rbase = ty.idx * W + xmin;
+          for (int ex = 0; ex < nxu; ++ex) {
+            const CTap tx = xtab[ex * kMaxP + pw];
+            const float wgt = ty.w * tx.w;
+            if (wgt == 0.f) continue;
+#pragma unroll
+            for (int q = 0; q < kChW; ++q)
+              if (q < cn) atomicAdd(gpl[q] + rbase + tx.idx, wgt * gv[q]);
+          }
+        }
+      }
+      continue;
+    }
+    if (BWD) {  // staged: accumulate the footprint in the warp's slice, flush each touched pixel once
+      for (int band = 0; band < nbands; ++band) {
+        const int ph0 = band_ph0[band], ph1 = band_ph0[band + 1];
+        const int yb = band_yb[band], npx = band_npx[band];
+        const int ylast = yb + (fw > 0 ? npx / fw : 0) - 1;
+        const int* __restrict__ ro = rowoff + (yb - ymin) * fw;
+        __syncwarp();
+        for (int i = lane; i < npx; i += 32) {
+#pragma unroll
+          for (int q = 0; q < kChW; ++q) st[q * kCapPx + i] = 0.f;
+        }
+        __syncwarp();
+        const int nbin = (ph1 - ph0) * PW;
+        for (int b0 = 0; b0 < nbin; b0 += 32) {
+          const int bin = b0 + lane;
+          if (bin >= nbin) continue;
+          const int dph = bin / PW;
+          const int ph = ph0 + dph, pw = bin - dph * PW;
+          float gv[kChW];
+#pragma unroll
+          for (int q = 0; q < kChW; ++q) gv[q] = q < cn ? gobase[q * bins + ph * PW + pw] * g.inv_count : 0.f;
+          for (int ey = 0; ey < nyu; ++ey) {
+            const CTap ty = ytab[ey * kMaxP + ph];
+            if (ty.w == 0.f) continue;
+            float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw;
+            for (int ex = 0; ex < nxu; ++ex) {
+              const CTap tx = xtab[ex * kMaxP + pw];
+              const float wgt = ty.w * tx.w;
+              if (wgt == 0.f) continue;
+#pragma unroll
+              for (int q = 0; q < kChW; ++q) atomicAdd(srow + q * kCapPx + tx.idx, wgt * gv[q]);
+            }
+          }
+        }
+        __syncwarp();
+        for (int i = lane; i < npx; i += 32) {
+          const int off = ro[i];
+#pragma unroll
+          for (int q = 0; q < kChW; ++q) {
+            const float v = st[q * kCapPx + i];
+            if (q < cn && v != 0.f) atomicAdd(gpl[q] + off, v);
+          }
+        }
+      }
+      continue;
+    }
 
     if (mode == 1) {  // tap lists, data straight from global / L2 (large or sparsely sampled RoIs)
       for (int b0 = 0; b0 < bins; b0 += 32) {
@@ -548,7 +592,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
           float r[kChW];
 #pragma unroll
           for (int q = 0; q < kChW; ++q) r[q] = 0.f;
-          for (int ex = 0; ex < nxu; ex += 4) {  // 4 taps x kChW channels = 16 independent loads in flight
+          for (int ex = 0; ex < nxu; ex += 4) {  // 4 taps x kChW channels = 16 independent loads in flight (lists padded)
             CTap tx[4];
             float v[4][kChW];
 #pragma unroll
@@ -633,11 +677,12 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_fwd_v3_kernel(const P
 }
 
 static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int PW, int sr, int aligned, float* out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const float* gout = nullptr) {
   const size_t smem = sizeof(float) * (size_t)kV3Warps * kChW * kCapPx;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(roi_align_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -646,7 +691,8 @@ static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int
   while (groups_per_cta > kV3Warps && (long long)K * d2b_cdiv(ngroup, groups_per_cta) < 12LL * kNumSMs)
     groups_per_cta = (groups_per_cta + 1) / 2;
   dim3 grid(K, d2b_cdiv(ngroup, groups_per_cta));
-  roi_align_fwd_v3_kernel<<<grid, kV3Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, groups_per_cta, out);
+  if (gout) roi_align_v3_kernel<true><<<grid, kV3Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, groups_per_cta, gout, nullptr);
+  else roi_align_v3_kernel<false><<<grid, kV3Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, groups_per_cta, nullptr, out);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
@@ -716,12 +762,7 @@ D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const 
   }
   if (K == 0 || C == 0 || N == 0) return D2B_OK;
   if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
-  int cpc = pick_c_per_cta(K, C);
-  dim3 grid(K, d2b_cdiv(C, cpc));
-  roi_align_bwd_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, grad_out, rois, C, pooled_h, pooled_w,
-                                                                           sampling_ratio, aligned, cpc);
-  D2B_CHECK_LAUNCH();
-  return D2B_OK;
+  return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, nullptr, (cudaStream_t)stream, grad_out);
 }
 
 D2B_API int d2b_roi_align_rotated_forward(const float* input, int N, int C, int H, int W, const float* rois, int K,
@@ -753,6 +794,8 @@ static int roi_bwd_launch(const float* grad_out, const float* rois, int K, float
   P.H[0] = H;
   P.W[0] = W;
   P.scale[0] = spatial_scale;
+  if (!ROT)
+    return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, nullptr, (cudaStream_t)stream, grad_out);
   int cpc = pick_c_per_cta(K, C);
   dim3 grid(K, d2b_cdiv(C, cpc));
   roi_align_bwd_kernel<ROT><<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, grad_out, rois, C, pooled_h, pooled_w,
