@@ -220,6 +220,25 @@ def time_reference(steps, warmup, budget_s=150.0):
     return frac * steps / dt, dt / steps * 1e3, frac, torch.get_num_threads()
 
 
+# ----------------------------------------------------------------------------------------- multi-GPU aggregation
+def image_seeds(rank, nbuf):
+    """Synthetic-image seeds of one rank: replicas never share an image (image-parallel sharding, no data-path collective)."""
+    return [1000 * rank + i for i in range(nbuf)]
+
+
+def max_over_ranks(values_ms, dist, device):
+    """Element-wise MAX over ranks of per-rank elapsed times (the only collective of the benchmark)."""
+    t = torch.tensor(list(values_ms), dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def aggregate_throughput(world, steps, elapsed_ms):
+    """Whole-job images/s: every rank processed `steps` images in (max over ranks) elapsed_ms."""
+    return world * steps / (elapsed_ms / 1e3)
+
+
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -293,7 +312,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     runner = OursRunner(dev)
     NBUF = 3  # rotate over 3 distinct images so that every step reads cold feature maps (3 x 91 MB > 126 MB L2)
-    host = [make_image_inputs(1000 * rank + i) for i in range(NBUF)]
+    host = [make_image_inputs(sd) for sd in image_seeds(rank, NBUF)]
     devin = [runner.to_device(h) for h in host]
     torch.cuda.synchronize()
 
@@ -474,17 +493,14 @@ def main():
     except Exception as e:  # supplementary only: never hide the headline numbers
         train_ms = "failed: %s" % type(e).__name__
 
-    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = times.tolist()
+    elapsed_ms, e2e_ms = max_over_ranks([elapsed_ms, e2e_ms], dist, dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    value = world * args.steps / (elapsed_ms / 1e3)
-    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    value = aggregate_throughput(world, args.steps, elapsed_ms)
+    e2e_value = aggregate_throughput(world, args.steps, e2e_ms)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) dcn_fwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ backward: data
-// grid (pixel tiles, 1, N*G).  For every (dg segment, kp, 16-channel chunk): gcol[16 x 64] = W^T . gout, then the
+// grid (pixel tiles, channel-chunk splits, N*G).  For every (dg segment, kp, 16-channel chunk): gcol[16 x 64] = W^T . gout, then the
 // scatter epilogue.  Thread mapping in the epilogue: n = tid % 64 (pixel), kk = tid / 64 + 4*i (channel).
 __global__ void __launch_bounds__(kThreads) dcn_bwd_data_kernel(const float* __restrict__ x,
                                                                 const float* __restrict__ offset,
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) dcn_bwd_data_kernel(const float* __r
       build_taps(taps, d, offset, mask, b, dg, kp, p0);
       __syncthreads();
       float s_h = 0.f, s_w = 0.f, s_m = 0.f;
-      for (int c0 = sbeg; c0 < send; c0 += BK) {
+      for (int c0 = sbeg + (int)blockIdx.y * BK; c0 < send; c0 += BK * (int)gridDim.y) {  // channel chunks are split over blockIdx.y
         float acc[4] = {0.f, 0.f, 0.f, 0.f};  // gcol for channels kq + 4*i, pixel n
         for (int mm0 = 0; mm0 < d.opg; mm0 += BK) {
           {  // Ws[m][c] : 16 x 16
@@ -427,7 +427,14 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
   if (d.N == 0) return D2B_OK;
   if (!x || !offset || !weight || !grad_out) return D2B_EINVAL;
   if (grad_x || grad_offset || grad_mask) {
-    dim3 grid(d2b_cdiv(d.HoWo, BN), 1, d.N * d.G);
+    // few pixel tiles (small maps) -> split the channel chunks over blockIdx.y so that the grid still fills 148 SMs;
+    // grad_offset / grad_mask partial sums meet through the atomics the kernel already uses
+    const int base_ctas = d2b_cdiv(d.HoWo, BN) * d.N * d.G;
+    int csplit = d2b_cdiv(3LL * kNumSMs, base_ctas);
+    const int nchunks = d2b_cdiv(d.cpg, BK);
+    if (csplit > nchunks) csplit = nchunks;
+    if (csplit < 1) csplit = 1;
+    dim3 grid(d2b_cdiv(d.HoWo, BN), csplit, d.N * d.G);
     dcn_bwd_data_kernel<<<grid, kThreads, 0, stream>>>(x, offset, mask, weight, grad_out, d, grad_x, grad_offset,
                                                        grad_mask);
     D2B_CHECK_LAUNCH();

@@ -84,40 +84,61 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
   const long long stride = (long long)gridDim.x * kThreads;
   const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
 
-  // ---- phase 1: chunks that cannot see the mask
-  for (long long chunk = gtid; chunk < chunks_per_mask; chunk += stride) {
-    const long long start = head + chunk * kPix;
-    if (start + kPix > plane) continue;  // ragged tail: phase 2b
-    const int py = (int)(start / W);
-    const int px = (int)(start - (long long)py * W);
-    bool active = false;
-    if (!empty) {
-      const int pxe = px + kPix - 1;
-      if (pxe < W) {
-        active = (py >= ry0 && py <= ry1 && pxe >= cx0 && px <= cx1);
-      } else {  // chunk wraps into the next row
-        active = (py >= ry0 && py <= ry1 && px <= cx1) || (py + 1 >= ry0 && py + 1 <= ry1 && pxe - W >= cx0);
+  // ---- phase 1: chunks that cannot see the mask.  (py, px) of a thread's chunk advance incrementally: one 32-bit
+  //      division per thread instead of one 64-bit division per chunk -- this loop is instruction-bound, not HBM-bound.
+  {
+    const unsigned uW = (unsigned)W;
+    const unsigned long long first = (unsigned long long)head + (unsigned long long)gtid * kPix;
+    unsigned py = (unsigned)(first / uW), px = (unsigned)(first - (unsigned long long)py * uW);
+    const unsigned long long step_bytes = (unsigned long long)stride * kPix;
+    const unsigned dpy = (unsigned)(step_bytes / uW), dpx = (unsigned)(step_bytes - (unsigned long long)dpy * uW);
+    const uint4 zz = make_uint4(zword, zword, zword, zword);
+    const long long last_full = (plane - head) / kPix;  // chunks [0, last_full) lie completely inside the plane
+    uint8_t* __restrict__ dst = obase + first;
+    for (long long chunk = gtid; chunk < last_full; chunk += stride, dst += step_bytes) {
+      bool active = false;
+      if (!empty) {
+        const int ipy = (int)py, ipx = (int)px, pxe = ipx + kPix - 1;
+        if (pxe < W) {
+          active = (ipy >= ry0 && ipy <= ry1 && pxe >= cx0 && ipx <= cx1);
+        } else {  // chunk wraps into the next row
+          active = (ipy >= ry0 && ipy <= ry1 && ipx <= cx1) || (ipy + 1 >= ry0 && ipy + 1 <= ry1 && pxe - W >= cx0);
+        }
+      }
+      if (!active) *reinterpret_cast<uint4*>(dst) = zz;
+      px += dpx;
+      py += dpy;
+      if (px >= uW) {
+        px -= uW;
+        ++py;
       }
     }
-    if (!active) *reinterpret_cast<uint4*>(obase + start) = make_uint4(zword, zword, zword, zword);
   }
-  // ---- phase 2a: the rectangle, row by row, widened to chunk boundaries (one pixel per lane)
+  // ---- phase 2a: the rectangle, row by row, widened to chunk boundaries (one pixel per lane).  32-bit index math; the
+  //      byte -> (py, px) mapping needs no division because a widened range spills at most 15 bytes into a neighbour row.
   if (!empty) {
     const int RL = (cx1 - cx0 + 1) + 2 * (kPix - 1) + 1;
-    const long long items = (long long)(ry1 - ry0 + 1) * RL;
-    for (long long it = gtid; it < items; it += stride) {
-      const int r = ry0 + (int)(it / RL);
-      const int t = (int)(it - (long long)(r - ry0) * RL);
-      const long long lo = (long long)r * W + cx0, hi = (long long)r * W + cx1;  // inclusive flat range of this row
-      long long A = lo - head;
-      A = (A >= 0 ? (A / kPix) * kPix : 0) + head;
-      if (lo < head) A = 0;
-      long long B = ((hi - head) / kPix + 1) * kPix + head;
-      if (hi < head) B = head;
-      if (B > plane) B = plane;
-      const long long byte = A + t;
+    const int nrows = ry1 - ry0 + 1;
+    const int iplane = (int)plane;  // H*W < 2^31 (checked on the host)
+    const unsigned items = (unsigned)nrows * (unsigned)RL;
+    for (unsigned it = (unsigned)gtid; it < items; it += (unsigned)stride) {
+      const int dr = (int)(it / (unsigned)RL);
+      const int t = (int)(it - (unsigned)dr * (unsigned)RL);
+      const int r = ry0 + dr;
+      const int lo = r * W + cx0, hi = r * W + cx1;  // inclusive flat range of this row
+      const int A = lo < head ? 0 : ((lo - head) & ~(kPix - 1)) + head;
+      int B = hi < head ? head : (((hi - head) >> 4) + 1) * kPix + head;
+      if (B > iplane) B = iplane;
+      const int byte = A + t;
       if (byte >= B) continue;
-      const int py = (int)(byte / W), px = (int)(byte - (long long)py * W);
+      int py = r, px = byte - r * W;
+      if (px < 0) {
+        px += W;
+        --py;
+      } else if (px >= W) {
+        px -= W;
+        ++py;
+      }
       obase[byte] = (uint8_t)paste_pixel(smask, M, fM, px, py, x0, y0, x1, y1, threshold);
     }
   }
@@ -144,6 +165,7 @@ D2B_API int d2b_paste_masks(const float* masks, const float* boxes, int N, int M
   if (!masks || !boxes || !out || N < 0 || M <= 0 || H < 0 || W < 0) return D2B_EINVAL;
   if (M > kMaxM) return D2B_EUNSUPPORTED;
   long long plane = (long long)H * W;
+  if (plane >= (1LL << 30)) return D2B_EUNSUPPORTED;  // 32-bit pixel indices inside one mask plane
   int chunks = (int)((plane + kPix - 1) / kPix);  // upper bound; chunks past the plane are skipped in-kernel
   int gx = d2b_cdiv(chunks + 1, kThreads);
   // enough CTAs per mask to fill the machine even for a single mask, capped to keep the smem mask staging amortised
