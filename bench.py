@@ -519,13 +519,13 @@ def main():
         "gpu_launches": OursRunner.KERNELS_PER_STEP * args.steps,
         "clocks": sampler.summary(),
         "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
-        "roofline": {"kernel": "roi_align_fwd_v3_kernel (box pooler, 1000 RoIs x 256 ch x 7x7 over p2..p5)", "bound": "hbm",
+        "roofline": {"kernel": "roi_align_v3_kernel<false> (box pooler, 1000 RoIs x 256 ch x 7x7 over p2..p5)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                      "algorithmic_bytes": alg_bytes, "avg_launch_ms": box_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                     # (profiles/r1_ncu_full.txt: 97.32 MB read + 33.80 MB written)
-                     "traffic": 131121408},
+                     # (profiles/r1_ncu_full.txt, launch id 3: 97.53 MB read + 34.13 MB written)
+                     "traffic": 131659520},
     })
     line["extra"] = {"train_hot_path": {"ms_per_step_2img": train_ms, "img_s": (2e3 / train_ms * world) if isinstance(train_ms, float) else None,
                                         "what": "per GPU and step: 2 x batched_nms(8819 boxes, 5 levels) + box pooler fwd+bwd (1024 RoIs, 7x7) + mask pooler fwd+bwd (256 RoIs, 14x14), eager launches"}}

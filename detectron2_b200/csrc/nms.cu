@@ -266,49 +266,58 @@ __global__ void gather_boxes_kernel(const float* __restrict__ boxes, const int* 
 // maskT[(size_t)col_block * M + row]  (column-word-major).
 // cls (optional): class of every position of the class-major order; only same-class pairs can suppress each other, and a
 // tile whose row block and column block share no class is skipped altogether (never read by the scan).
-template <bool ROT>
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ cls, int M,
-                                                      double thr, unsigned long long* __restrict__ maskT) {
+// Thread layout: kSub threads per row, each testing 64/kSub columns, partial words OR-ed with warp shuffles.  The rotated
+// IoU is ~50x the work of the axis-aligned one, so it gets 8 threads per row (512-thread CTAs), the cheap one gets 1.
+template <bool ROT, int kSub>
+__global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ cls,
+                                                             int M, double thr, unsigned long long* __restrict__ maskT) {
   const int cb = blockIdx.x, rb = blockIdx.y;
   if (cb < rb) return;
   if (cls && cb > rb && cls[min(rb * 64 + 63, M - 1)] != cls[cb * 64]) return;  // classes ascend with position
   constexpr int D = ROT ? 5 : 4;
+  constexpr int kCols = 64 / kSub;
   __shared__ float cbox[64 * D];
+  __shared__ int ccls[64];
   const int c0 = cb * 64, r0 = rb * 64;
   const int nc = min(64, M - c0);
-  for (int t = threadIdx.x; t < nc * D; t += 64) cbox[t] = sb[(size_t)c0 * D + t];
-  __shared__ int ccls[64];
+  for (int t = threadIdx.x; t < nc * D; t += 64 * kSub) cbox[t] = sb[(size_t)c0 * D + t];
   if (cls && (int)threadIdx.x < nc) ccls[threadIdx.x] = cls[c0 + threadIdx.x];
   __syncthreads();
-  const int row = r0 + threadIdx.x;
-  if (row >= M) return;
+  const int lrow = threadIdx.x / kSub, sub = threadIdx.x % kSub;
+  const int row = r0 + lrow;
+  const bool row_ok = row < M;
   float a[D];
 #pragma unroll
-  for (int c = 0; c < D; ++c) a[c] = sb[(size_t)row * D + c];
+  for (int c = 0; c < D; ++c) a[c] = sb[(size_t)(row_ok ? row : M - 1) * D + c];
   unsigned long long bits = 0ull;
-  const int start = (cb == rb) ? threadIdx.x + 1 : 0;
-  const int my_cls = cls ? cls[row] : 0;
-  if (ROT) {
-    for (int j = start; j < nc; ++j) {
-      if (cls && ccls[j] != my_cls) continue;
-      float iou = rotated_iou(a, cbox + j * 5);
-      if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
-    }
-  } else {
-    const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
-    for (int j = start; j < nc; ++j) {
-      if (cls && ccls[j] != my_cls) continue;
-      const float* b = cbox + j * 4;
-      float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
-      float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
-      float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
-      float inter = w * h;
-      float area_b = (b[2] - b[0]) * (b[3] - b[1]);
-      float ovr = inter / (area_a + area_b - inter);
-      if ((double)ovr > thr) bits |= 1ull << j;  // torchvision nms: strict
+  const int start = (cb == rb) ? lrow + 1 : 0;
+  const int my_cls = cls ? cls[row_ok ? row : M - 1] : 0;
+  const int jbeg = max(start, sub * kCols), jend = min(nc, (sub + 1) * kCols);
+  if (row_ok) {
+    if (ROT) {
+      for (int j = jbeg; j < jend; ++j) {
+        if (cls && ccls[j] != my_cls) continue;
+        float iou = rotated_iou(a, cbox + j * 5);
+        if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
+      }
+    } else {
+      const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
+      for (int j = jbeg; j < jend; ++j) {
+        if (cls && ccls[j] != my_cls) continue;
+        const float* b = cbox + j * 4;
+        float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
+        float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
+        float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+        float inter = w * h;
+        float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+        float ovr = inter / (area_a + area_b - inter);
+        if ((double)ovr > thr) bits |= 1ull << j;  // torchvision nms: strict
+      }
     }
   }
-  maskT[(size_t)cb * M + row] = bits;
+#pragma unroll
+  for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
+  if (row_ok && sub == 0) maskT[(size_t)cb * M + row] = bits;
 }
 
 constexpr int kScanThreads = 512;
@@ -620,8 +629,8 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   D2B_CHECK_LAUNCH();
   // 4. IoU bitmask (same-class tiles only)
   dim3 grid(nb, nb);
-  if (rotated) nms_mask_kernel<true><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
-  else nms_mask_kernel<false><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
+  if (rotated) nms_mask_kernel<true, 8><<<grid, 512, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
+  else nms_mask_kernel<false, 1><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 5. per-segment greedy scans in parallel, then compaction in global score order
   D2B_CUDA(cudaMemsetAsync(w.keepflag, 0, (size_t)m, stream));
