@@ -583,12 +583,14 @@ NmsWorkspace carve(void* base, int64_t M, int rotated) {
 
 }  // namespace
 
-D2B_API size_t d2b_nms_workspace_bytes(int64_t M, int rotated) { return carve(nullptr, M, rotated).total; }
+D2B_API size_t d2b_nms_workspace_bytes(int64_t M, int flags) { return carve(nullptr, M, (flags & D2B_NMS_ROTATED) ? 1 : 0).total; }
 
 D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
-                    int rotated, int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes,
+                    int flags, int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes,
                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int rotated = (flags & D2B_NMS_ROTATED) ? 1 : 0;
+  const bool no_offset = (flags & D2B_NMS_NO_OFFSET) != 0;  // idxs only segment the boxes; coordinates are used as given
   if (!num_keep || M < 0) return D2B_EINVAL;
   if (M == 0) {
     D2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), stream));
@@ -611,9 +613,11 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   const int* cls_sorted = nullptr;
   const int* pos2 = nullptr;
   if (idxs) {
-    if (rotated) coord_range_kernel<true><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
-    else coord_range_kernel<false><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
-    D2B_CHECK_LAUNCH();
+    if (!no_offset) {
+      if (rotated) coord_range_kernel<true><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
+      else coord_range_kernel<false><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
+      D2B_CHECK_LAUNCH();
+    }
     class_of_rank_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(idxs, w.order, m, w.cls);
     D2B_CHECK_LAUNCH();
     cub_bytes = w.cub_bytes;
@@ -624,8 +628,9 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   nms_segments_kernel<<<1, 1024, 0, stream>>>(cls_sorted, m, w.seg_start, w.nseg);
   D2B_CHECK_LAUNCH();
   // 3. boxes in that order (coordinate offsets of the reference's batched-NMS trick applied in fp32)
-  if (rotated) gather_boxes_kernel<true><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, idxs, w.mm, m, w.sorted_boxes);
-  else gather_boxes_kernel<false><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, idxs, w.mm, m, w.sorted_boxes);
+  const int64_t* off_idxs = no_offset ? nullptr : idxs;
+  if (rotated) gather_boxes_kernel<true><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, off_idxs, w.mm, m, w.sorted_boxes);
+  else gather_boxes_kernel<false><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, off_idxs, w.mm, m, w.sorted_boxes);
   D2B_CHECK_LAUNCH();
   // 4. IoU bitmask (same-class tiles only)
   dim3 grid(nb, nb);

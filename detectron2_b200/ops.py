@@ -231,7 +231,7 @@ roi_align_rotated_op.register_autograd(_roi_rot_bwd, setup_context=_roi_rot_setu
 
 # =================================================================================== NMS / rotated IoU
 def nms_fixed(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,
-              rotated: bool) -> Tuple[Tensor, Tensor]:
+              rotated: bool, apply_offsets: bool = True) -> Tuple[Tensor, Tensor]:
     """Sync-free NMS: returns (keep[M] int64 padded buffer, num_keep[1] int64 device tensor).
     keep[:num_keep] are the kept original indices in descending-score order.  CUDA-graph friendly."""
     _C.require_cuda(boxes, scores, idxs)
@@ -241,10 +241,11 @@ def nms_fixed(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_thresho
     keep = torch.empty((m,), dtype=torch.int64, device=b.device)
     num = torch.zeros((1,), dtype=torch.int64, device=b.device)
     if m:
-        ws_bytes = _C.lib().d2b_nms_workspace_bytes(m, int(rotated))
+        flags = (1 if rotated else 0) | (0 if apply_offsets else 2)  # D2B_NMS_ROTATED | D2B_NMS_NO_OFFSET
+        ws_bytes = _C.lib().d2b_nms_workspace_bytes(m, flags)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=b.device)
         with torch.cuda.device(b.device):
-            check(_C.lib().d2b_nms(ptr(b), ptr(s), ptr(ix), m, float(iou_threshold), int(rotated), ptr(keep),
+            check(_C.lib().d2b_nms(ptr(b), ptr(s), ptr(ix), m, float(iou_threshold), flags, ptr(keep),
                                    ptr(num), ptr(ws), ws_bytes, stream_ptr(b.device)), "nms")
     return keep, num
 

@@ -1,0 +1,122 @@
+"""find_top_rpn_proposals -- batched RPN proposal selection, same signature and results as
+detectron2/modeling/proposal_generator/proposal_utils.py:22-135.
+
+The reference loops over images in Python: per image it filters non-finite / small boxes with boolean indexing, calls
+`.item()` (host sync, :118), runs one `batched_nms` and slices.  Here all images go through ONE NMS pipeline:
+
+  * the NMS category of a candidate is `image * L + level`, so one `d2b_nms` call (per-class segments scanned by
+    parallel CTAs) covers every (image, level) pair;
+  * boxes the reference removes before NMS (non-finite, or smaller than `min_box_size` after clipping) are not
+    removed -- which would need a data-dependent shape -- but moved to a private dummy category with score -inf:
+    they cannot suppress anything and are dropped from the output, which gives the same kept set and order;
+  * the per-image top `post_nms_topk` of the score-ordered keep list is extracted on the device; the only host
+    synchronisation is the final read of the N output lengths.
+"""
+from typing import List, Tuple
+
+import torch
+
+from . import ops
+
+__all__ = ["find_top_rpn_proposals", "ProposalBoxes", "Proposals"]
+
+
+class ProposalBoxes:
+    """Minimal stand-in for detectron2.structures.Boxes (the containers are out of scope): `.tensor`, `len()`."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+
+class Proposals:
+    """Minimal stand-in for detectron2.structures.Instances with the two fields RPN produces."""
+
+    def __init__(self, image_size, proposal_boxes: ProposalBoxes, objectness_logits: torch.Tensor):
+        self.image_size = image_size
+        self.proposal_boxes = proposal_boxes
+        self.objectness_logits = objectness_logits
+
+    def __len__(self):
+        return len(self.proposal_boxes)
+
+
+def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits: List[torch.Tensor],
+                           image_sizes: List[Tuple[int, int]], nms_thresh: float, pre_nms_topk: int,
+                           post_nms_topk: int, min_box_size: float, training: bool):
+    num_images = len(image_sizes)
+    device = proposals[0].device
+    num_levels = len(proposals)
+    # 1. top-k per level and image (proposal_utils.py:70-94)
+    batch_idx = torch.arange(num_images, device=device)
+    boxes_l, scores_l, level_l = [], [], []
+    for level_id, (proposals_i, logits_i) in enumerate(zip(proposals, pred_objectness_logits)):
+        k = min(logits_i.shape[1], pre_nms_topk)
+        topk_scores_i, topk_idx = logits_i.topk(k, dim=1)
+        boxes_l.append(proposals_i[batch_idx[:, None], topk_idx])
+        scores_l.append(topk_scores_i)
+        level_l.append(torch.full((k,), level_id, dtype=torch.int64, device=device))
+    boxes = torch.cat(boxes_l, dim=1).float()   # N x T x 4
+    scores = torch.cat(scores_l, dim=1)         # N x T
+    levels = torch.cat(level_l, dim=0)          # T
+    n, t = scores.shape
+
+    # 2. validity, clip, small-box filter -- as masks, not as shape changes (:104-120)
+    finite = torch.isfinite(boxes).all(dim=2) & torch.isfinite(scores)
+    if training and not bool(finite.all()):  # same failure mode as the reference (:106-110); training only
+        raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+    hw = torch.tensor([[float(h), float(w)] for (h, w) in image_sizes], device=device)  # N x 2
+    x1 = torch.minimum(boxes[..., 0].clamp(min=0), hw[:, 1:2])
+    y1 = torch.minimum(boxes[..., 1].clamp(min=0), hw[:, 0:1])
+    x2 = torch.minimum(boxes[..., 2].clamp(min=0), hw[:, 1:2])
+    y2 = torch.minimum(boxes[..., 3].clamp(min=0), hw[:, 0:1])
+    clipped = torch.stack([x1, y1, x2, y2], dim=2)
+    nonempty = ((x2 - x1) > min_box_size) & ((y2 - y1) > min_box_size)
+    valid = finite & nonempty
+
+    # 3. one NMS over all images: category = image * L + level; removed boxes go to a dummy category with score -inf
+    img_of = batch_idx[:, None].expand(n, t)
+    cat_ids = img_of * num_levels + levels[None, :]
+    dummy = num_images * num_levels
+    cat_ids = torch.where(valid, cat_ids, torch.full_like(cat_ids, dummy)).reshape(-1)
+    flat_boxes = torch.where(valid[..., None], clipped, torch.zeros_like(clipped)).reshape(-1, 4)
+    flat_scores = torch.where(valid, scores.float(), torch.full_like(scores, float("-inf"), dtype=torch.float32)).reshape(-1)
+    # torchvision's batched_nms (reached per image from proposal_utils.py:121) shifts the boxes of level l by
+    # l * (max coordinate of THAT image's boxes + 1) in fp32 before computing IoU, as long as the image has at most
+    # 25 000 candidates; reproduce exactly those per-image offsets so that every IoU rounds like the reference's.
+    neg = torch.full_like(clipped, float("-inf"))
+    max_img = torch.where(valid[..., None], clipped, neg).reshape(n, -1).max(dim=1).values  # N
+    if t * 4 <= 100_000:
+        offs = levels[None, :].to(torch.float32) * (max_img[:, None] + 1.0)                # N x T
+        nms_boxes = (clipped + offs[..., None])
+        nms_boxes = torch.where(valid[..., None], nms_boxes, torch.zeros_like(nms_boxes)).reshape(-1, 4)
+    else:
+        nms_boxes = flat_boxes
+    keep, num_keep = ops.nms_fixed(nms_boxes, flat_scores, cat_ids, float(nms_thresh), False, apply_offsets=False)
+
+    # 4. per-image top post_nms_topk of the score-ordered keep list (:129), on the device
+    m = keep.shape[0]
+    live = torch.arange(m, device=device) < num_keep          # keep[] beyond num_keep is padding
+    kidx = torch.where(live, keep, torch.zeros_like(keep))
+    kimg = torch.div(kidx, t, rounding_mode="floor")
+    kvalid = live & valid.reshape(-1)[kidx]
+    onehot = (kimg[None, :] == batch_idx[:, None]) & kvalid[None, :]          # N x M
+    rank = torch.cumsum(onehot.to(torch.int32), dim=1) - 1
+    sel = onehot & (rank < post_nms_topk)
+    counts = sel.sum(dim=1)
+    # scatter without data-dependent shapes: unselected entries are routed to a trash column
+    out_idx = torch.zeros((num_images, post_nms_topk + 1), dtype=torch.int64, device=device)
+    col = torch.where(sel, rank.long(), torch.full_like(rank, post_nms_topk, dtype=torch.int64))
+    out_idx.scatter_(1, col, kidx[None, :].expand(n, m))
+    out_idx = out_idx[:, :post_nms_topk].contiguous()
+    out_boxes = flat_boxes[out_idx.reshape(-1)].reshape(num_images, post_nms_topk, 4)
+    out_scores = scores.reshape(-1)[out_idx.reshape(-1)].reshape(num_images, post_nms_topk)
+
+    counts_host = counts.tolist()  # the one host sync: the reference contract returns exactly-sized results
+    results = []
+    for i, image_size in enumerate(image_sizes):
+        c = counts_host[i]
+        results.append(Proposals(image_size, ProposalBoxes(out_boxes[i, :c]), out_scores[i, :c]))
+    return results

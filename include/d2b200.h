@@ -95,10 +95,15 @@ int d2b_roi_align_rotated_backward(const float* grad_out, const float* rois, int
  *          (detectron2/layers/nms.py:137-146), all in fp32 like the reference.
  *   keep   [M] int64 out: kept ORIGINAL indices, score-descending; num_keep [1] int64 out (device).
  * Suppression rule: axis-aligned  iou >  thr (torchvision);  rotated  iou >= thr (nms_rotated_cpu.cpp:54).
- * workspace: d2b_nms_workspace_bytes(M, rotated) bytes of device scratch. */
-size_t d2b_nms_workspace_bytes(int64_t M, int rotated);
+ * flags: D2B_NMS_ROTATED selects the rotated variant; D2B_NMS_NO_OFFSET makes `idxs` pure segment ids -- the
+ *        coordinates are used as given (the caller already applied whatever offsets it wants, e.g. the per-image offsets
+ *        of a multi-image RPN batch, detectron2_b200/proposal_utils.py).
+ * workspace: d2b_nms_workspace_bytes(M, flags) bytes of device scratch. */
+#define D2B_NMS_ROTATED 1
+#define D2B_NMS_NO_OFFSET 2
+size_t d2b_nms_workspace_bytes(int64_t M, int flags);
 int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
-            double iou_threshold, int rotated, int64_t* keep, int64_t* num_keep, void* workspace,
+            double iou_threshold, int flags, int64_t* keep, int64_t* num_keep, void* workspace,
             size_t workspace_bytes, void* stream);
 
 /* ---- Rotated-box IoU --------------------------------------------------------------------

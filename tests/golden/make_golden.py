@@ -206,6 +206,60 @@ def gen_paste_masks():
     save("paste_masks", masks=masks, boxes=boxes, hw=np.asarray([h, w]), out_bool=out_bool, out_u8=out_u8, soft=soft)
 
 
+def _import_reference_proposal_utils():
+    """The real detectron2 find_top_rpn_proposals, imported with stub fvcore / pycocotools."""
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    sys.path.insert(0, "/root/reference")
+    fv = stub("fvcore", __version__="0.1.5")
+    fv.__path__ = []
+    nn_ = stub("fvcore.nn")
+    nn_.__path__ = []
+    stub("fvcore.nn.distributed", differentiable_all_reduce=lambda x: x)
+    nn_.weight_init = stub("fvcore.nn.weight_init", c2_msra_fill=lambda m: None, c2_xavier_fill=lambda m: None)
+    pc = stub("pycocotools")
+    pc.__path__ = []
+    stub("pycocotools.mask")
+    spec = importlib.util.spec_from_file_location(
+        "ref_proposal_utils", "/root/reference/detectron2/modeling/proposal_generator/proposal_utils.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def gen_rpn_proposals():
+    ref = _import_reference_proposal_utils()
+    g = torch.Generator().manual_seed(77)
+    n, sizes = 2, [(120, 160), (100, 200)]
+    per_level = [600, 300, 100]
+    props, logits = [], []
+    for a in per_level:
+        ctr = torch.rand(n, a, 2, generator=g) * torch.tensor([220.0, 140.0]) - 10
+        wh = torch.rand(n, a, 2, generator=g) * 60 + 0.5
+        b = torch.cat([ctr - wh / 2, ctr + wh / 2], 2)
+        props.append(b)
+        logits.append(torch.randn(n, a, generator=g))
+    props[0][0, 3] = float("nan")          # non-finite box
+    logits[1][1, 5] = float("inf")         # non-finite score
+    props[2][1, 7] = torch.tensor([50.0, 50.0, 50.5, 80.0])  # narrower than min_box_size
+    logits[0][0, 10:14] = logits[0][0, 10]  # score ties
+    out = {"sizes": np.asarray(sizes), "per_level": np.asarray(per_level), "cfg": np.asarray([0.7, 150, 60, 2.0])}
+    for l in range(3):
+        out[f"props{l}"] = props[l]
+        out[f"logits{l}"] = logits[l]
+    res = ref.find_top_rpn_proposals([p.clone() for p in props], [x.clone() for x in logits], sizes, 0.7, 150, 60, 2.0, False)
+    for i, r in enumerate(res):
+        out[f"boxes_img{i}"] = r.proposal_boxes.tensor
+        out[f"scores_img{i}"] = r.objectness_logits
+    save("rpn_proposals", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     gen_roi_align()
@@ -214,3 +268,4 @@ if __name__ == "__main__":
     gen_rotated_iou_nms()
     gen_deform_conv()
     gen_paste_masks()
+    gen_rpn_proposals()

@@ -264,3 +264,22 @@ def test_paste_port_matches_fixture_and_reference(golden):
         boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
         assert torch.equal(paste_ref.paste_masks_in_image_cpu(masks, boxes, (150, 200), 0.5),
                            mo.paste_masks_in_image(masks, boxes, (150, 200), 0.5))
+
+
+def _rpn_fixture(golden):
+    d = golden("rpn_proposals")
+    props = [T(d[f"props{l}"]) for l in range(3)]
+    logits = [T(d[f"logits{l}"]) for l in range(3)]
+    sizes = [tuple(int(v) for v in r) for r in d["sizes"]]
+    thr, pre, post, mbs = d["cfg"]
+    return d, props, logits, sizes, float(thr), int(pre), int(post), float(mbs)
+
+
+def test_golden_rpn_proposals(golden):
+    """oracle/proposals_ref.py against the REAL detectron2 find_top_rpn_proposals (fixture from make_golden.py)."""
+    from oracle import proposals_ref
+
+    d, props, logits, sizes, thr, pre, post, mbs = _rpn_fixture(golden)
+    res = proposals_ref.find_top_rpn_proposals(props, logits, sizes, thr, pre, post, mbs, False)
+    for i, (b, s) in enumerate(res):
+        assert torch.equal(b, T(d[f"boxes_img{i}"])) and torch.equal(s, T(d[f"scores_img{i}"])), i

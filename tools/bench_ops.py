@@ -112,6 +112,43 @@ def main():
         t = timeit(lambda: L.batched_nms(boxes, scores, idxs, thr))
         tr = timeit(lambda: tv.boxes.batched_nms(boxes, scores, idxs, thr)) if tv else None
         add("batched_nms M=%d classes=%d (%s)" % (m, ncls, tag), t, tr, "%.1f Mpairs/s" % (m * (m - 1) / 2 / t))
+    # ---- batched RPN proposal selection (2 images, 5 FPN levels, pre-NMS top 1000 per level)
+    from detectron2_b200.proposal_utils import find_top_rpn_proposals
+    gb = torch.Generator().manual_seed(9)
+    per_level = [3 * 200 * 336, 3 * 100 * 168, 3 * 50 * 84, 3 * 25 * 42, 3 * 13 * 21]
+    pp, ll = [], []
+    for a in per_level:
+        ctr = torch.rand(2, a, 2, generator=gb) * torch.tensor([1400.0, 850.0]) - 20
+        wh = torch.exp(torch.rand(2, a, 2, generator=gb) * 5.0) + 0.5
+        pp.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 2).to(DEV))
+        ll.append(torch.randn(2, a, generator=gb).to(DEV))
+    szs = [(800, 1333), (800, 1333)]
+    t = timeit(lambda: find_top_rpn_proposals(pp, ll, szs, 0.7, 1000, 1000, 0.0, False), rep=10)
+
+    def ref_rpn():  # the reference's structure on the GPU: per-image loop, boolean filtering, tv batched_nms
+        bi = torch.arange(2, device=DEV)
+        ts, tp, lv = [], [], []
+        for lid, (p_i, l_i) in enumerate(zip(pp, ll)):
+            k = min(l_i.shape[1], 1000)
+            s_i, idx = l_i.topk(k, dim=1)
+            tp.append(p_i[bi[:, None], idx]); ts.append(s_i); lv.append(torch.full((k,), lid, dtype=torch.int64, device=DEV))
+        ts, tp, lv = torch.cat(ts, 1), torch.cat(tp, 1), torch.cat(lv, 0)
+        outs = []
+        for n_, (h_, w_) in enumerate(szs):
+            b_, s_, l_ = tp[n_].clone(), ts[n_], lv
+            v_ = torch.isfinite(b_).all(1) & torch.isfinite(s_)
+            if not v_.all():
+                b_, s_, l_ = b_[v_], s_[v_], l_[v_]
+            b_[:, 0::2].clamp_(0, w_); b_[:, 1::2].clamp_(0, h_)
+            kp = ((b_[:, 2] - b_[:, 0]) > 0) & ((b_[:, 3] - b_[:, 1]) > 0)
+            if kp.sum().item() != len(b_):
+                b_, s_, l_ = b_[kp], s_[kp], l_[kp]
+            kk_ = tv.boxes.batched_nms(b_, s_, l_, 0.7)[:1000]
+            outs.append((b_[kk_], s_[kk_]))
+        return outs
+
+    tr = timeit(ref_rpn, rep=10) if tv else None
+    add("find_top_rpn_proposals 2 img x 5 levels (242k anchors/img)", t, tr, "ref = reference loop structure with tv CUDA nms")
     # ---- rotated
     gb = torch.Generator().manual_seed(5)
     rb = torch.cat([torch.rand(1000, 2, generator=gb) * 300, 1 + torch.rand(1000, 2, generator=gb) * 120,
