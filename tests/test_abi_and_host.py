@@ -91,3 +91,26 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "import torchvision" not in src and "from torchvision" not in src, f
+
+
+def test_fake_kernels_trace_shapes():
+    """Every custom op has a fake (meta) kernel, so the ops trace / compile without touching the GPU library."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from detectron2_b200 import ops
+
+    with FakeTensorMode():
+        x = torch.empty(2, 16, 20, 30, device="cuda")
+        rois = torch.empty(7, 5, device="cuda")
+        assert ops.roi_align_op(x, rois, 0.25, 7, 7, 0, True).shape == (7, 16, 7, 7)
+        assert ops.roi_align_rotated_op(x, torch.empty(7, 6, device="cuda"), 0.25, 5, 4, 2).shape == (7, 16, 5, 4)
+        feats = [torch.empty(2, 16, 40 // 2 ** i, 60 // 2 ** i, device="cuda") for i in range(4)]
+        y = ops.roi_pooler_op(feats, rois, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 14, 14, 0, True, 2, 5, 4, 224.0)
+        assert y.shape == (7, 16, 14, 14)
+        w = torch.empty(24, 8, 3, 3, device="cuda")
+        off = torch.empty(2, 18, 10, 15, device="cuda")
+        out = ops.deform_conv_op(x, off, None, w, None, [2, 2], [1, 1], [1, 1], 2, 1, -1)
+        assert out.shape == (2, 24, 10, 15)
+        assert ops.box_iou_rotated_op(torch.empty(5, 5, device="cuda"), torch.empty(9, 5, device="cuda")).shape == (5, 9)
+        pm = ops.paste_masks_op(torch.empty(3, 28, 28, device="cuda"), torch.empty(3, 4, device="cuda"), 40, 50, 0.5)
+        assert pm.shape == (3, 40, 50) and pm.dtype == torch.uint8
