@@ -102,7 +102,9 @@ def roi_align_algorithmic_bytes(rois_img, ph, pw):
 
 # ----------------------------------------------------------------------------------------- our arm
 class OursRunner:
-    KERNELS_PER_STEP = 13  # nms: iota+range+gather+mask+scan (x2), pooler (x2), paste (x1); CUB's sort kernels not counted
+    # our own kernels per step: 2 x NMS (iota, coord_range, class_of_rank, segments, gather, mask, scan, compact = 8),
+    # 2 x fused pooler, 1 x paste; CUB's radix-sort kernels (2 per NMS) are library code and not counted
+    KERNELS_PER_STEP = 19
 
     def __init__(self, device):
         import detectron2_b200.layers as L

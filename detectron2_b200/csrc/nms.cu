@@ -181,9 +181,13 @@ __global__ void __launch_bounds__(128) box_iou_rotated_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // NMS
 // ------------------------------------------------------------------------------------------------
-__global__ void iota_kernel(int* __restrict__ v, int n) {
+// v[i] = i (value array of the radix sorts) and keepflag[i] = 0 (output of the scans), one launch
+__global__ void iota_kernel(int* __restrict__ v, unsigned char* __restrict__ keepflag, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = i;
+  if (i < n) {
+    v[i] = i;
+    keepflag[i] = 0;
+  }
 }
 
 // coordinate range for the batched-NMS offset trick.  mm[0] = max, mm[1] = min.
@@ -604,7 +608,7 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   const size_t smem = (size_t)nb * sizeof(unsigned long long);
   if (smem > 200 * 1024) return D2B_EUNSUPPORTED;
   // 1. global stable descending score order
-  iota_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(w.iota, m);
+  iota_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(w.iota, w.keepflag, m);
   D2B_CHECK_LAUNCH();
   size_t cub_bytes = w.cub_bytes;
   D2B_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, scores, w.sorted_scores, w.iota, w.order, m,
@@ -638,7 +642,6 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   else nms_mask_kernel<false, 1><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 5. per-segment greedy scans in parallel, then compaction in global score order
-  D2B_CUDA(cudaMemsetAsync(w.keepflag, 0, (size_t)m, stream));
   if (smem > 40 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int scan_grid = idxs ? (m < 2 * kNumSMs ? m : 2 * kNumSMs) : 1;

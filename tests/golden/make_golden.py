@@ -260,6 +260,59 @@ def gen_rpn_proposals():
     save("rpn_proposals", **out)
 
 
+def _import_reference_fast_rcnn():
+    """The real detectron2 fast_rcnn_inference_single_image, imported with stubs for its unrelated dependencies."""
+    import types
+
+    _import_reference_proposal_utils()  # fvcore / pycocotools stubs + sys.path
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    sys.modules["fvcore.nn"].giou_loss = sys.modules["fvcore.nn"].smooth_l1_loss = lambda *a, **k: None
+    stub("detectron2.config", configurable=lambda f=None, **k: (f if f else (lambda g: g)))
+    stub("detectron2.utils.events", get_event_storage=lambda: None)
+    d = stub("detectron2.data")
+    d.__path__ = []
+    stub("detectron2.data.detection_utils", get_fed_loss_cls_weights=None)
+    import detectron2.layers  # noqa: F401
+    import detectron2.structures  # noqa: F401
+
+    mm = stub("detectron2.modeling")
+    mm.__path__ = []
+    stub("detectron2.modeling.box_regression", Box2BoxTransform=object, _dense_box_regression_loss=None)
+    spec = importlib.util.spec_from_file_location("ref_fast_rcnn", "/root/reference/detectron2/modeling/roi_heads/fast_rcnn.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def gen_fast_rcnn_inference():
+    ref = _import_reference_fast_rcnn()
+    g = torch.Generator().manual_seed(31)
+    out = {"cfg": np.asarray([0.05, 0.5, 25])}
+    shapes = [(120, 160), (90, 200)]
+    out["shapes"] = np.asarray(shapes)
+    for i, (r, k, agnostic) in enumerate([(80, 6, False), (50, 6, True)]):
+        base = torch.rand(12, 4, generator=g) * torch.tensor([150.0, 100.0, 60.0, 50.0])
+        base[:, 2:] += base[:, :2] + 5
+        pick = torch.randint(0, 12, (r,), generator=g)
+        nb = 1 if agnostic else k
+        boxes = (base[pick][:, None, :] + torch.randn(r, nb, 4, generator=g) * 4).reshape(r, nb * 4)
+        scores = torch.softmax(torch.randn(r, k + 1, generator=g) * 2.5, dim=1)
+        if i == 0:
+            boxes[7, 2] = float("inf")       # invalid row (dropped before everything else)
+            scores[9] = float("nan")
+            scores[20, 1] = scores[21, 1]    # tie
+        res, rows = ref.fast_rcnn_inference_single_image(boxes.clone(), scores.clone(), shapes[i], 0.05, 0.5, 25)
+        out.update({f"boxes{i}": boxes, f"scores{i}": scores, f"out_boxes{i}": res.pred_boxes.tensor,
+                    f"out_scores{i}": res.scores, f"out_classes{i}": res.pred_classes, f"out_rows{i}": rows})
+    save("fast_rcnn_inference", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     gen_roi_align()
@@ -269,3 +322,4 @@ if __name__ == "__main__":
     gen_deform_conv()
     gen_paste_masks()
     gen_rpn_proposals()
+    gen_fast_rcnn_inference()

@@ -511,3 +511,41 @@ def test_find_top_rpn_proposals_fpn_size_vs_oracle():
         mism = (gs[:same] != rs[:same]).sum().item()
         assert abs(len(rb) - len(gb)) <= 2 and mism <= 4, (i, len(rb), len(gb), mism)
         assert (gs[:-1] >= gs[1:]).all()
+
+
+# ------------------------------------------------------------------------------- batched Fast R-CNN inference (8f-2)
+def _frcnn_fixture(golden):
+    d = golden("fast_rcnn_inference")
+    thr, nms_thr, topk = d["cfg"]
+    shapes = [tuple(int(v) for v in r) for r in d["shapes"]]
+    return d, shapes, float(thr), float(nms_thr), int(topk)
+
+
+def _check_frcnn(d, res, rows, idxs):
+    for j, i in enumerate(idxs):
+        assert torch.equal(res[j].pred_boxes.cpu(), T(d[f"out_boxes{i}"])), i
+        assert torch.equal(res[j].scores.cpu(), T(d[f"out_scores{i}"])), i
+        assert torch.equal(res[j].pred_classes.cpu(), T(d[f"out_classes{i}"])), i
+        assert torch.equal(rows[j].cpu(), T(d[f"out_rows{i}"])), i
+
+
+def test_fast_rcnn_inference_golden(golden):
+    """Bit-exact against the REAL detectron2 fast_rcnn_inference_single_image (fixture from make_golden.py)."""
+    from detectron2_b200 import fast_rcnn_inference as fri
+
+    d, shapes, thr, nms_thr, topk = _frcnn_fixture(golden)
+    for i in range(2):  # per image (class-specific boxes, class-agnostic boxes)
+        res, rows = fri.fast_rcnn_inference([T(d[f"boxes{i}"]).to(DEV)], [T(d[f"scores{i}"]).to(DEV)], [shapes[i]], thr, nms_thr, topk)
+        _check_frcnn(d, res, rows, [i])
+    # a batch of two images with the same layout in one call, and the candidate-cap overflow path
+    res, rows = fri.fast_rcnn_inference([T(d["boxes0"]).to(DEV)] * 2, [T(d["scores0"]).to(DEV)] * 2, [shapes[0]] * 2, thr, nms_thr, topk)
+    _check_frcnn(d, res, rows, [0, 0])
+    old = fri.CANDIDATE_CAP
+    try:
+        fri.CANDIDATE_CAP = 16  # force truncation -> exact recomputation
+        res, rows = fri.fast_rcnn_inference([T(d["boxes0"]).to(DEV)], [T(d["scores0"]).to(DEV)], [shapes[0]], thr, nms_thr, topk)
+        _check_frcnn(d, res, rows, [0])
+    finally:
+        fri.CANDIDATE_CAP = old
+    det, r = fri.fast_rcnn_inference_single_image(torch.zeros(0, 24, device=DEV), torch.zeros(0, 7, device=DEV), (10, 10), thr, nms_thr, topk)
+    assert len(det) == 0 and r.numel() == 0
