@@ -7,13 +7,16 @@
 //
 // Pipeline of d2b_nms (all on the caller's stream, no host round trip -- the reference copies the N x N/64 bitmask
 // to the host and scans it there, nms_rotated_cuda.cu:114-137):
-//   1. stable descending radix sort of the scores (CUB)            -> order[r]
-//   2. gather boxes in score order, applying the batched-NMS coordinate offsets in fp32 on the fly
-//   3. IoU bitmask, 64x64 tiles, upper triangle only, stored COLUMN-WORD-MAJOR maskT[w][i] so that both the tile
-//      writes and the scan's reads are coalesced
-//   4. single-CTA greedy scan: per 64-box block one thread resolves the intra-block chain from the diagonal word,
-//      then 32 warps OR the kept rows into the `removed` words (rows prefetched one block ahead), and the kept
-//      original indices are written in score order together with the device-side count.
+//   1. stable descending radix sort of the scores (CUB)                              -> order[rank]
+//   2. batched NMS: stable radix sort of the ranks by category (CUB) -> class-major order with descending scores
+//      inside each class; a single-CTA kernel derives the segment table
+//   3. gather boxes in that order, applying the batched-NMS coordinate offsets in fp32 on the fly
+//   4. IoU bitmask, 64x64 tiles, upper triangle and same-class tiles only, stored COLUMN-WORD-MAJOR maskT[w][i] so that
+//      both the tile writes and the scan's reads are coalesced
+//   5. greedy scan, one CTA per class segment in parallel: per 64-box block one thread resolves the intra-block chain
+//      (branch-free) from the diagonal word, then 16 warps OR the kept rows into the `removed` words (rows prefetched
+//      one block ahead in ping-pong registers); kept boxes are flagged at their global score rank
+//   6. single-CTA compaction of the flags in score order -> kept original indices + device-side count.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -271,7 +274,7 @@ __global__ void gather_boxes_kernel(const float* __restrict__ boxes, const int* 
 // cls (optional): class of every position of the class-major order; only same-class pairs can suppress each other, and a
 // tile whose row block and column block share no class is skipped altogether (never read by the scan).
 // Thread layout: kSub threads per row, each testing 64/kSub columns, partial words OR-ed with warp shuffles.  The rotated
-// IoU is ~50x the work of the axis-aligned one, so it gets 8 threads per row (512-thread CTAs), the cheap one gets 1.
+// IoU is ~50x the work of the axis-aligned one, so it gets 8 threads per row (512-thread CTAs), the cheap one gets 4.
 template <bool ROT, int kSub>
 __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ cls,
                                                              int M, double thr, unsigned long long* __restrict__ maskT) {
@@ -639,7 +642,7 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   // 4. IoU bitmask (same-class tiles only)
   dim3 grid(nb, nb);
   if (rotated) nms_mask_kernel<true, 8><<<grid, 512, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
-  else nms_mask_kernel<false, 1><<<grid, 64, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
+  else nms_mask_kernel<false, 4><<<grid, 256, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 5. per-segment greedy scans in parallel, then compaction in global score order
   if (smem > 40 * 1024)

@@ -4,13 +4,13 @@
 // torchvision/ops/roi_align.py::_roi_align) and detectron2/layers/csrc/ROIAlignRotated/ROIAlignRotated_cuda.cu:143-323.
 //
 // Design (differs from the reference's one-thread-per-output grid-stride loop):
-//   * one CTA per (RoI, channel slab).  The bilinear taps of a RoI are shared by all C channels, so they are
-//     computed ONCE per CTA into shared memory -- as two separable 1-D tables (rows, columns) for the axis-aligned
-//     op, as a 2-D table for the rotated op -- instead of once per output element (256x redundant in the reference);
-//   * threads are mapped to (channel, bin) with bins fastest, so a warp reads neighbouring pixels of one plane
-//     and writes 128 contiguous output bytes;
-//   * backward accumulates a RoI's gradient footprint in shared memory first and flushes it with one red.global
-//     per touched pixel instead of 4*g^2 global atomics per output element.
+//   * axis-aligned forward AND backward: roi_align_v3_kernel<BWD> below -- per-RoI separable tap lists built once per CTA,
+//     every warp stages (forward) or accumulates (backward) the RoI's pixel footprint of 4 channel planes in its private
+//     shared-memory slice, lane == bin, no CTA barrier in the channel loop; the FPN level of a RoI is picked in-kernel so
+//     that a whole multi-level ROIPooler call is one launch;
+//   * rotated forward: one CTA per (RoI, channel slab) with a 2-D tap table in shared memory (the sample grid of a
+//     rotated RoI is not a product grid), threads mapped to (channel, bin);
+//   * rotated backward: thread per (channel, bin), red.global.add per tap.
 #include "common.cuh"
 
 namespace {
