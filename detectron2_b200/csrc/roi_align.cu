@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
                                                                      int PH, int PW, int sr, int aligned,
                                                                      int groups_per_cta, const float* __restrict__ gout,
                                                                      float* __restrict__ out) {
-  extern __shared__ __align__(16) float stage_all[];  // [warp][kChW][kCapPx]
+  extern __shared__ __align__(16) float stage_all[];  // [warp][kCapPx][kChW]: the kChW channels of a pixel are one 16-byte word
   __shared__ CTap ytab[kMaxE * kMaxP];  // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];  // [tap][pw]   (idx relative to the footprint's first column)
   __shared__ int rowoff[kRowoffCap];    // global offset (y*W + x) of every footprint pixel, row-major
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
         __syncwarp();
         for (int i = lane; i < npx; i += 32) {
 #pragma unroll
-          for (int q = 0; q < kChW; ++q) st[q * kCapPx + i] = 0.f;
+          for (int q = 0; q < kChW; ++q) st[i * kChW + q] = 0.f;
         }
         __syncwarp();
         const int nbin = (ph1 - ph0) * PW;
@@ -554,13 +554,13 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
           for (int ey = 0; ey < nyu; ++ey) {
             const CTap ty = ytab[ey * kMaxP + ph];
             if (ty.w == 0.f) continue;
-            float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw;
+            float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw * kChW;
             for (int ex = 0; ex < nxu; ++ex) {
               const CTap tx = xtab[ex * kMaxP + pw];
               const float wgt = ty.w * tx.w;
               if (wgt == 0.f) continue;
 #pragma unroll
-              for (int q = 0; q < kChW; ++q) atomicAdd(srow + q * kCapPx + tx.idx, wgt * gv[q]);
+              for (int q = 0; q < kChW; ++q) atomicAdd(srow + tx.idx * kChW + q, wgt * gv[q]);
             }
           }
         }
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
           const int off = ro[i];
 #pragma unroll
           for (int q = 0; q < kChW; ++q) {
-            const float v = st[q * kCapPx + i];
+            const float v = st[i * kChW + q];
             if (q < cn && v != 0.f) atomicAdd(gpl[q] + off, v);
           }
         }
@@ -634,11 +634,9 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
           a[q] = __ldg(pl[q] + o0);
           b[q] = __ldg(pl[q] + o1);
         }
-#pragma unroll
-        for (int q = 0; q < kChW; ++q) {
-          st[q * kCapPx + pix] = a[q];
-          if (two) st[q * kCapPx + pix + 32] = b[q];
-        }
+        static_assert(kChW == 4, "one float4 per pixel");
+        *reinterpret_cast<float4*>(st + pix * kChW) = make_float4(a[0], a[1], a[2], a[3]);
+        if (two) *reinterpret_cast<float4*>(st + (pix + 32) * kChW) = make_float4(b[0], b[1], b[2], b[3]);
       }
       __syncwarp();
       // ---- compute: lane == bin
@@ -654,14 +652,17 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
         for (int q = 0; q < kChW; ++q) acc[q] = 0.f;
         for (int ey = 0; ey < nyu; ++ey) {
           const CTap ty = ytab[ey * kMaxP + ph];
-          const float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw;  // pad taps (w = 0) stay in-band
+          const float* __restrict__ srow = st + (min(max(ty.idx, yb), ylast) - yb) * fw * kChW;  // pad taps (w = 0) stay in-band
           float r[kChW];
 #pragma unroll
           for (int q = 0; q < kChW; ++q) r[q] = 0.f;
           for (int ex = 0; ex < nxu; ++ex) {
             const CTap tx = xtab[ex * kMaxP + pw];
-#pragma unroll
-            for (int q = 0; q < kChW; ++q) r[q] = fmaf(tx.w, srow[q * kCapPx + tx.idx], r[q]);
+            const float4 dv = *reinterpret_cast<const float4*>(srow + tx.idx * kChW);  // 4 channels of the tap pixel
+            r[0] = fmaf(tx.w, dv.x, r[0]);
+            r[1] = fmaf(tx.w, dv.y, r[1]);
+            r[2] = fmaf(tx.w, dv.z, r[2]);
+            r[3] = fmaf(tx.w, dv.w, r[3]);
           }
 #pragma unroll
           for (int q = 0; q < kChW; ++q) acc[q] = fmaf(ty.w, r[q], acc[q]);
