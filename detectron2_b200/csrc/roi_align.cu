@@ -689,7 +689,7 @@ static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int
   }
   const int ngroup = d2b_cdiv(C, kChW);
   int groups_per_cta = ngroup;  // split the channel groups until the grid is several waves deep
-  while (groups_per_cta > kV3Warps && (long long)K * d2b_cdiv(ngroup, groups_per_cta) < 12LL * kNumSMs)
+  while (groups_per_cta > kV3Warps && (long long)K * d2b_cdiv(ngroup, groups_per_cta) < 24LL * kNumSMs)
     groups_per_cta = (groups_per_cta + 1) / 2;
   dim3 grid(K, d2b_cdiv(ngroup, groups_per_cta));
   if (gout) roi_align_v3_kernel<true><<<grid, kV3Threads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, groups_per_cta, gout, nullptr);
