@@ -11,6 +11,8 @@
 //   * rotated forward: one CTA per (RoI, channel slab) with a 2-D tap table in shared memory (the sample grid of a
 //     rotated RoI is not a product grid), threads mapped to (channel, bin);
 //   * rotated backward: thread per (channel, bin), red.global.add per tap.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -705,7 +707,257 @@ int pick_c_per_cta(int K, int C) {
   return cpc;
 }
 
+// ------------------------------------------------------------------ channels-last (NHWC) forward
+// With the channels innermost the roles flip: lane == 4 channels (one 16-byte word), so a warp reads the 128
+// channels of a tap pixel as one coalesced 512-byte LDG.128 and the tap index / weight are warp-uniform (no per-lane
+// address arithmetic, no shared-memory staging of the footprint: L1 is the staging buffer, the 7 or 8 warps of a CTA
+// walk neighbouring bins of the same RoI at the same time).  One warp owns one bin at a time; the [bin] x [channel]
+// results are transposed through shared memory so that the NCHW-shaped output is written in contiguous runs.
+constexpr int kNhwcCh = 128;    // channels per CTA
+constexpr int kNhwcChunk = 64;  // bins per output chunk (shared-memory transpose tile: 128 ch x chunk)
+
+// One bin: XC x-taps (offsets / weights held in registers) times RY rows per step = XC * RY independent 512-byte loads in
+// flight per warp.  Table entries hold element offsets premultiplied for the NHWC layout (row: y*W*C/4, column: x*C/4).
+template <int XC, int RY>
+__device__ __forceinline__ void nhwc_bin(const float4* __restrict__ base, const CTap* __restrict__ yt0,
+                                         const CTap* __restrict__ xt0, int ny, int nx, float4& acc) {
+  for (int x0 = 0; x0 < nx; x0 += XC) {
+    int xo[XC];
+    float xw[XC];
+#pragma unroll
+    for (int e = 0; e < XC; ++e) {
+      const CTap t = xt0[min(x0 + e, nx - 1) * kMaxP];
+      xo[e] = t.idx;
+      xw[e] = (x0 + e < nx) ? t.w : 0.f;
+    }
+    for (int ey = 0; ey < ny; ey += RY) {
+      int yo[RY];
+      float wy[RY];
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const CTap t = yt0[min(ey + j, ny - 1) * kMaxP];
+        yo[j] = t.idx;
+        wy[j] = (ey + j < ny) ? t.w : 0.f;
+      }
+      float4 v[RY][XC];
+#pragma unroll
+      for (int j = 0; j < RY; ++j)
+#pragma unroll
+        for (int e = 0; e < XC; ++e) {  // 32-bit element offset inside the image, one IMAD.WIDE to the address
+          const unsigned off = (unsigned)(yo[j] + xo[e]);
+          v[j][e] = (x0 + e < nx) ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(base) + (size_t)off * 16u))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < XC; ++e) {
+          r.x = fmaf(xw[e], v[j][e].x, r.x);
+          r.y = fmaf(xw[e], v[j][e].y, r.y);
+          r.z = fmaf(xw[e], v[j][e].z, r.z);
+          r.w = fmaf(xw[e], v[j][e].w, r.w);
+        }
+        acc.x = fmaf(wy[j], r.x, acc.x);
+        acc.y = fmaf(wy[j], r.y, acc.y);
+        acc.z = fmaf(wy[j], r.z, acc.z);
+        acc.w = fmaf(wy[j], r.w, acc.w);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
+                                                             int PW, int sr, int aligned, int chunk, int chunk_pad,
+                                                             float* __restrict__ out) {
+  extern __shared__ __align__(16) float otile[];  // [4 (channel of the quad)][32 (lane)][chunk_pad]
+  __shared__ CTap ytab[kMaxE * kMaxP];            // [tap][ph]
+  __shared__ CTap xtab[kMaxE * kMaxP];            // [tap][pw]
+  __shared__ int yn[kMaxP], xn[kMaxP];
+  __shared__ int s_overflow;
+  __shared__ RoiGeom sg;  // read from shared memory where needed: keeps the tap loop's register budget small
+
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * kNhwcCh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const int H = P.H[lvl], W = P.W[lvl];
+  const int bins = PH * PW;
+  const int C4 = C >> 2;
+  const int ncta = min(kNhwcCh, C - c0);  // channels of this CTA
+  const bool lane_live = lane * 4 < ncta;
+  // a dead lane (ragged last slab) re-reads the slab's first quad and is never stored
+  if (tid == 0) {
+    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;
+    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+  }
+  __syncthreads();
+  const float4* __restrict__ base =
+      reinterpret_cast<const float4*>(P.feat[lvl]) + (size_t)sg.b * H * W * C4 + (c0 >> 2) + (lane_live ? lane : 0);
+  if (!s_overflow) {
+    if (tid < PH) {
+      const RoiGeom g = sg;
+      CTap* list = ytab + tid;
+      int n = 0, ov = 0;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+        add_tap(list, kMaxP, n, t.lo, t.wl, ov);
+        add_tap(list, kMaxP, n, t.hi, t.wh, ov);
+      }
+      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= W * C4;  // row offset in float4 units
+      yn[tid] = n;
+      if (ov) s_overflow = 1;
+    } else if (tid >= 32 && tid < 32 + PW) {
+      const int pw = tid - 32;
+      const RoiGeom g = sg;
+      CTap* list = xtab + pw;
+      int n = 0, ov = 0;
+      for (int ix = 0; ix < g.gw; ++ix) {
+        Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+        add_tap(list, kMaxP, n, t.lo, t.wl, ov);
+        add_tap(list, kMaxP, n, t.hi, t.wh, ov);
+      }
+      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4;
+      xn[pw] = n;
+      if (ov) s_overflow = 1;
+    }
+  }
+  __syncthreads();
+  const bool onfly = s_overflow != 0;
+
+  {
+    const int bin0 = blockIdx.z * chunk;  // one output chunk per CTA
+    const int nb = min(chunk, bins - bin0);
+    for (int bl = warp; bl < nb; bl += nwarps) {
+      const int bin = bin0 + bl;
+      const int ph = bin / PW, pw = bin - ph * PW;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!onfly) {
+        const int ny = yn[ph], nx = xn[pw];
+        if (nx <= 4) nhwc_bin<4, 2>(base, ytab + ph, xtab + pw, ny, nx, acc);
+        else nhwc_bin<8, 1>(base, ytab + ph, xtab + pw, ny, nx, acc);
+      } else {  // rare: sampling grid too large for the tap lists (or pooled size > 16): taps on the fly
+        const RoiGeom g = sg;
+        for (int iy = 0; iy < g.gh; ++iy) {
+          const Tap1 ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+          const float4* __restrict__ r0 = base + ty.lo * W * C4;
+          const float4* __restrict__ r1 = base + ty.hi * W * C4;
+          for (int ix = 0; ix < g.gw; ++ix) {
+            const Tap1 tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+            const float4 v1 = __ldg(r0 + tx.lo * C4), v2 = __ldg(r0 + tx.hi * C4);
+            const float4 v3 = __ldg(r1 + tx.lo * C4), v4 = __ldg(r1 + tx.hi * C4);
+            const float w1 = ty.wl * tx.wl, w2 = ty.wl * tx.wh, w3 = ty.wh * tx.wl, w4 = ty.wh * tx.wh;
+            acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+            acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+            acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+            acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+          }
+        }
+      }
+      float* __restrict__ o = otile + lane * chunk_pad + bl;  // odd pitch: the 32 lanes hit 32 banks
+      const float inv_count = sg.inv_count;
+      o[0] = acc.x * inv_count;
+      o[32 * chunk_pad] = acc.y * inv_count;
+      o[64 * chunk_pad] = acc.z * inv_count;
+      o[96 * chunk_pad] = acc.w * inv_count;
+    }
+    __syncthreads();
+    // channel-major write-out: channel c0+cl, bins [bin0, bin0+nb) -- one contiguous run of the output per channel
+    float* __restrict__ obase = out + ((size_t)k * C + c0) * bins + bin0;
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)nb + 1u;  // i / nb == umulhi(i, magic) for i < 2^16 (i < 128 * 64 here)
+    for (int i = tid; i < ncta * nb; i += blockDim.x) {
+      const int cl = (int)__umulhi((unsigned)i, magic), bl = i - cl * nb;
+      obase[(size_t)cl * bins + bl] = otile[((cl & 3) * 32 + (cl >> 2)) * chunk_pad + bl];
+    }
+  }
+}
+
+static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C, int PH, int PW, int sr, int aligned,
+                           float* out, cudaStream_t stream) {
+  if (C % 4 != 0) return D2B_EUNSUPPORTED;
+  for (int l = 0; l < P.num_levels; ++l) {
+    if ((long long)P.H[l] * P.W[l] * (C / 4) >= (1LL << 28)) return D2B_EUNSUPPORTED;  // 32-bit byte offsets inside an image
+    if ((reinterpret_cast<uintptr_t>(P.feat[l]) & 15) != 0) return D2B_EINVAL;
+  }
+  (void)N;
+  const int bins = PH * PW;
+  const int slabs = d2b_cdiv(C, kNhwcCh);
+  // bins of a RoI are split into chunks (grid.z): at least enough for the transpose tile, more when K x slabs alone
+  // would leave SMs idle (a mask-head call has 100 RoIs x 196 bins)
+  const long long want = d2b_cdiv(8LL * kNumSMs, (long long)K * slabs);
+  int nchunks = (int)std::max<long long>(d2b_cdiv(bins, kNhwcChunk), std::min<long long>(want, d2b_cdiv(bins, 8)));
+  const int chunk = d2b_cdiv(bins, nchunks);
+  nchunks = d2b_cdiv(bins, chunk);
+  const int chunk_pad = chunk | 1;
+  const int nwarps = (chunk % 7 == 0) ? 7 : 8;  // 7x7 / 14x14 outputs: bins split evenly over 7 warps
+  const size_t smem = sizeof(float) * 128 * (size_t)chunk_pad;
+  if (nchunks > 65535) return D2B_EUNSUPPORTED;
+  dim3 grid(K, slabs, nchunks);
+  roi_align_nhwc_kernel<<<grid, nwarps * 32, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+// NCHW -> NHWC of every pyramid level in one launch: 32 channels x 64 pixels per CTA through a padded tile.
+struct XposeLevels {
+  int num_levels;
+  const float* src[D2B_MAX_LEVELS];
+  float* dst[D2B_MAX_LEVELS];
+  int HW[D2B_MAX_LEVELS];
+  int tile_begin[D2B_MAX_LEVELS + 1];
+};
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const XposeLevels L, int C) {
+  __shared__ float tile[32][65];
+  int l = 0;
+  while (l + 1 < L.num_levels && (int)blockIdx.x >= L.tile_begin[l + 1]) ++l;
+  const int HW = L.HW[l];
+  const int hw0 = ((int)blockIdx.x - L.tile_begin[l]) * 64;
+  const int c0 = blockIdx.y * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ src = L.src[l] + (size_t)blockIdx.z * C * HW;
+  float* __restrict__ dst = L.dst[l] + (size_t)blockIdx.z * HW * C;
+#pragma unroll
+  for (int r = warp; r < 32; r += 8) {  // read: lanes along the pixels of one channel plane
+    const int c = c0 + r;
+    const int hwa = hw0 + lane, hwb = hw0 + 32 + lane;
+    const float* __restrict__ p = src + (size_t)min(c, C - 1) * HW;
+    tile[r][lane] = hwa < HW ? __ldg(p + hwa) : 0.f;
+    tile[r][lane + 32] = hwb < HW ? __ldg(p + hwb) : 0.f;
+  }
+  __syncthreads();
+  // write: 8 lanes x float4 = the 32 channels of one pixel (128 B), 4 pixels per warp instruction; tile pitch 65 and
+  // (quad, pixel) -> lane mapping make the 32 lanes hit 32 different banks
+  const int cq = tid & 7;
+  const int c = c0 + cq * 4;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int hwl = (tid >> 3) + half * 32;
+    const int hw = hw0 + hwl;
+    if (hw < HW && c < C) {
+      const float4 v = make_float4(tile[cq * 4 + 0][hwl], tile[cq * 4 + 1][hwl], tile[cq * 4 + 2][hwl], tile[cq * 4 + 3][hwl]);
+      *reinterpret_cast<float4*>(dst + (size_t)hw * C + c) = v;
+    }
+  }
+}
+
 }  // namespace
+
+D2B_API int d2b_roi_align_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                                       float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                       int aligned, float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  if (!input || !rois || !out || N <= 0 || H <= 0 || W <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0)
+    return D2B_EINVAL;
+  Pyr P = {};
+  P.num_levels = 1;
+  P.feat[0] = input;
+  P.H[0] = H;
+  P.W[0] = W;
+  P.scale[0] = spatial_scale;
+  return launch_fwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
+}
+
 
 D2B_API int d2b_roi_align_forward(const float* input, int N, int C, int H, int W, const float* rois, int K,
                                   float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
@@ -750,6 +1002,40 @@ D2B_API int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const f
   for (int l = 0; l < P.num_levels; ++l)
     if (!P.feat[l]) return D2B_EINVAL;
   return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
+}
+
+D2B_API int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                        int pooled_w, int sampling_ratio, int aligned, float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  Pyr P;
+  if (!make_pyr(pyr, P) || !rois || !out || N <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0) return D2B_EINVAL;
+  for (int l = 0; l < P.num_levels; ++l)
+    if (!P.feat[l]) return D2B_EINVAL;
+  return launch_fwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
+}
+
+D2B_API int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
+  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0) return D2B_EINVAL;
+  if (N == 0 || C == 0) return D2B_OK;
+  if (C % 4 != 0) return D2B_EUNSUPPORTED;
+  XposeLevels L = {};
+  L.num_levels = pyr->num_levels;
+  int tiles = 0;
+  for (int l = 0; l < pyr->num_levels; ++l) {
+    if (!pyr->feat[l] || !dst[l] || pyr->H[l] <= 0 || pyr->W[l] <= 0) return D2B_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(dst[l]) & 15) != 0) return D2B_EINVAL;
+    L.src[l] = pyr->feat[l];
+    L.dst[l] = dst[l];
+    L.HW[l] = pyr->H[l] * pyr->W[l];
+    L.tile_begin[l] = tiles;
+    tiles += d2b_cdiv(L.HW[l], 64);
+  }
+  L.tile_begin[pyr->num_levels] = tiles;
+  if (N > 65535 || d2b_cdiv(C, 32) > 65535) return D2B_EUNSUPPORTED;
+  dim3 grid(tiles, d2b_cdiv(C, 32), N);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
 }
 
 D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,

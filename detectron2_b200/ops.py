@@ -11,6 +11,7 @@ Two op namespaces are served:
 PyTorch is plumbing here: allocation, streams, autograd graph.  All arithmetic happens in the hand-written kernels.
 """
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -28,6 +29,45 @@ def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
 
 
 # =================================================================================== RoIAlign
+# Feature-map layout policy of the axis-aligned forward (D2B_POOLER_LAYOUT = auto | nchw | nhwc):
+#   * channels_last inputs are consumed in place by the NHWC kernel (torchvision would .contiguous() them first);
+#   * NCHW inputs go to the NCHW kernel, unless the call is large enough that "one layout-change launch + NHWC
+#     pooling" is cheaper (cost model below, fitted to the B200 measurements in profiles/r1_ops.md).
+POOLER_LAYOUT = os.environ.get("D2B_POOLER_LAYOUT", "auto")
+_NCHW_PS_PER_OUT = 18.0      # NCHW kernel: picoseconds per output element (adaptive sampling, FPN-sized RoIs)
+_NHWC_PS_PER_OUT = 6.0       # NHWC kernel
+_XPOSE_PS_PER_BYTE = 0.42    # layout change: read + write each byte once at ~4.8 TB/s
+
+
+def _is_channels_last(t: Tensor) -> bool:
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _nhwc_ok(feats, c: int) -> bool:
+    return c % 4 == 0 and all(t.shape[2] * t.shape[3] * (c // 4) < 2 ** 28 for t in feats)
+
+
+def _pick_layout(feats, n_out: int) -> str:
+    """'cl' = channels_last inputs used in place, 'xpose' = layout change + NHWC kernel, 'nchw' = NCHW kernel."""
+    c = feats[0].shape[1]
+    if POOLER_LAYOUT == "nchw" or not _nhwc_ok(feats, c):
+        return "nchw"
+    if all(_is_channels_last(t) and t.data_ptr() % 16 == 0 for t in feats):
+        return "cl"
+    if POOLER_LAYOUT == "nhwc":
+        return "xpose"
+    feat_bytes = 4 * sum(t.numel() for t in feats)
+    return "xpose" if (n_out * _NHWC_PS_PER_OUT + feat_bytes * _XPOSE_PS_PER_BYTE < n_out * _NCHW_PS_PER_OUT) else "nchw"
+
+
+def _to_nhwc(fs, P, n: int, c: int, device):
+    """One launch: every level of the NCHW pyramid `P` -> freshly allocated NHWC buffers; returns them."""
+    bufs = [torch.empty((t.shape[0], t.shape[2], t.shape[3], t.shape[1]), dtype=torch.float32, device=device) for t in fs]
+    dst = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+    check(_C.lib().d2b_pyramid_nchw_to_nhwc(C.byref(P), n, c, dst, stream_ptr(device)), "pyramid_nchw_to_nhwc")
+    return bufs
+
+
 def _roi_common(input: Tensor, rois: Tensor, cols: int):
     _C.require_cuda(input, rois)
     if input.dim() != 4:
@@ -40,15 +80,26 @@ def _roi_common(input: Tensor, rois: Tensor, cols: int):
 def roi_align_op(input: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
                  sampling_ratio: int, aligned: bool) -> Tensor:
     _roi_common(input, rois, 5)
-    x, r = _f32c(input), _f32c(rois)
-    n, c, h, w = x.shape
+    r = _f32c(rois)
+    n, c, h, w = input.shape
     k = r.shape[0]
-    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=x.device)
+    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=input.device)
     if out.numel():
+        x = input.to(dtype=torch.float32)
+        layout = _pick_layout([x], out.numel())
         with torch.cuda.device(x.device):
-            check(_C.lib().d2b_roi_align_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h, pooled_w,
-                                                 sampling_ratio, int(aligned), ptr(out), stream_ptr(x.device)),
-                  "roi_align_forward")
+            if layout == "nchw":
+                x = x.contiguous()
+                check(_C.lib().d2b_roi_align_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h, pooled_w,
+                                                     sampling_ratio, int(aligned), ptr(out), stream_ptr(x.device)),
+                      "roi_align_forward")
+            else:
+                if layout == "xpose":
+                    x = x.contiguous()
+                    x = _to_nhwc([x], _pyramid([x], None, [spatial_scale], 0, 0, 0, 1.0), n, c, x.device)[0]
+                check(_C.lib().d2b_roi_align_forward_nhwc(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h,
+                                                          pooled_w, sampling_ratio, int(aligned), ptr(out),
+                                                          stream_ptr(x.device)), "roi_align_forward_nhwc")
     return out.to(input.dtype)
 
 
@@ -112,16 +163,27 @@ def roi_pooler_op(feats: List[Tensor], rois: Tensor, scales: List[float], pooled
     _C.require_cuda(rois, *feats)
     if len(feats) < 1 or len(feats) > _C.MAX_LEVELS or len(feats) != len(scales):
         raise RuntimeError("roi_pooler: need 1..%d feature levels with one scale each" % _C.MAX_LEVELS)
-    fs = [_f32c(t) for t in feats]
+    fs = [t.to(dtype=torch.float32) for t in feats]
     r = _f32c(rois)
     n, c = fs[0].shape[:2]
     k = r.shape[0]
     out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=r.device)
     if out.numel():
-        P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size)
+        layout = _pick_layout(fs, out.numel())
+        args = (n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio, int(aligned), ptr(out), stream_ptr(r.device))
         with torch.cuda.device(r.device):
-            check(_C.lib().d2b_roi_pooler_forward(C.byref(P), n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio,
-                                                  int(aligned), ptr(out), stream_ptr(r.device)), "roi_pooler_forward")
+            if layout != "cl":
+                fs = [t.contiguous() for t in fs]
+            # channels_last tensors: same logical shape, NHWC storage -- _pyramid only takes pointers and H, W
+            P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size)
+            if layout == "nchw":
+                check(_C.lib().d2b_roi_pooler_forward(C.byref(P), *args), "roi_pooler_forward")
+            else:
+                if layout == "xpose":
+                    bufs = _to_nhwc(fs, P, n, c, r.device)
+                    for l, b in enumerate(bufs):
+                        P.feat[l] = b.data_ptr()
+                check(_C.lib().d2b_roi_pooler_forward_nhwc(C.byref(P), *args), "roi_pooler_forward_nhwc")
     return out.to(feats[0].dtype)
 
 

@@ -73,6 +73,20 @@ int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const float* ro
 int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
                             int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream);
 
+/* Channels-last variants.  torchvision::roi_align calls input.contiguous() (a hidden NCHW copy) when it is handed a
+ * torch.channels_last feature map; these entry points consume the NHWC storage directly: feat[l] / input is
+ * [N,H,W,C] fp32 (the storage of a channels_last [N,C,H,W] tensor), C % 4 == 0, H*W*C < 2^31 per image.
+ * Same results contract as d2b_roi_align_forward / d2b_roi_pooler_forward, out stays [K,C,PH,PW]. */
+int d2b_roi_align_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                               float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                               int aligned, float* out, void* stream);
+int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                int pooled_w, int sampling_ratio, int aligned, float* out, void* stream);
+/* Layout change of a whole pyramid in ONE launch: pyr->feat[l] [N,C,H,W] -> dst[l] [N,H,W,C] (dst: host array of
+ * pyr->num_levels device pointers, caller-owned).  Used by the host when a large pooler call on NCHW features is
+ * cheaper as transform + channels-last pooling (detectron2_b200/ops.py). */
+int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream);
+
 /* ---- RoIAlign, rotated ------------------------------------------------------------------
  * Replaces torch.ops.detectron2.roi_align_rotated_forward / _backward
  * (csrc/vision.cpp:118-119, csrc/ROIAlignRotated/ROIAlignRotated.h:50-113).

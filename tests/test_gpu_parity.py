@@ -430,6 +430,85 @@ def test_roi_pooler_fused_vs_reference_loop(out, ptype):
         assert ok, (l, err)
 
 
+# ------------------------------------------------------------------------------- channels-last (NHWC) RoIAlign path
+def _rand_rois(g, k, n, wmax, hmax, smin, smax):
+    cx, cy = torch.rand(k, generator=g) * wmax, torch.rand(k, generator=g) * hmax
+    w = smin + torch.rand(k, generator=g) * (smax - smin)
+    h = smin + torch.rand(k, generator=g) * (smax - smin)
+    b = torch.randint(0, n, (k,), generator=g).float()
+    return torch.stack([b, (cx - w / 2).clamp(0, wmax), (cy - h / 2).clamp(0, hmax), (cx + w / 2).clamp(0, wmax),
+                        (cy + h / 2).clamp(0, hmax)], 1)
+
+
+def test_pyramid_layout_change_is_exact():
+    import ctypes as C
+    from detectron2_b200 import _C, ops
+
+    g = torch.Generator().manual_seed(3)
+    feats = [torch.randn(2, 36, h, w, generator=g).to(DEV) for (h, w) in [(37, 51), (19, 26), (1, 7), (64, 2)]]
+    P = ops._pyramid(feats, None, [0.25, 0.125, 0.0625, 0.03125], 2, 5, 4, 224.0)
+    bufs = ops._to_nhwc(feats, P, 2, 36, feats[0].device)
+    for f, b in zip(feats, bufs):
+        assert torch.equal(b, f.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("c,ph,pw,sr,aligned", [(4, 7, 7, 0, True), (12, 7, 7, 2, False), (132, 7, 7, 0, True),
+                                                 (256, 14, 14, 0, True), (8, 17, 5, 0, True), (64, 3, 9, 3, False)])
+def test_roi_align_channels_last_vs_oracle(L, c, ph, pw, sr, aligned):
+    # channels_last input is consumed in place (no NCHW copy); (17, 5) exercises the taps-on-the-fly path (pooled > 16)
+    g = torch.Generator().manual_seed(c + ph)
+    x = torch.randn(2, c, 50, 76, generator=g)
+    rois = _rand_rois(g, 97, 2, 304.0, 200.0, 4.0, 180.0)
+    rois[0] = torch.tensor([0.0, 10, 10, 10, 10])          # empty box
+    rois[1] = torch.tensor([1.0, -50, -40, 400, 300])      # larger than the map: samples outside are skipped
+    rois[2] = torch.tensor([0.0, -100, 0, 900, 6.0])      # 36-pixel-wide bins inside the map: tap-list overflow -> on the fly
+    ref = orc.roi_align_forward(x, rois, 0.25, ph, pw, sr, aligned)
+    xcl = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    from detectron2_b200 import ops
+
+    assert ops._pick_layout([xcl.detach()], 1) == "cl"
+    y = L.ROIAlign((ph, pw), 0.25, sr, aligned)(xcl, rois.to(DEV))
+    ok, err = rel_close(y, ref, rtol=1e-4, atol=5e-5)
+    assert ok, err
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go.to(DEV))
+    gref = orc.roi_align_backward(go, rois, 0.25, ph, pw, 2, c, 50, 76, sr, aligned)
+    ok, err = rel_close(xcl.grad, gref, atol=2e-4)
+    assert ok, err
+
+
+@pytest.mark.parametrize("mode", ["cl", "xpose"])
+def test_roi_pooler_nhwc_paths_vs_reference_loop(mode, monkeypatch):
+    from detectron2_b200 import ops
+    from detectron2_b200.poolers import ROIPooler
+
+    g = torch.Generator().manual_seed(11)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    feats = [torch.randn(2, 40, 200 // 2 ** i, 336 // 2 ** i, generator=g) for i in range(4)]
+    per_img = []
+    for _ in range(2):
+        s = torch.exp(torch.rand(120, generator=g) * (math.log(700) - math.log(8)) + math.log(8))
+        ctr = torch.rand(120, 2, generator=g) * torch.tensor([1344.0, 800.0])
+        ar = torch.exp((torch.rand(120, generator=g) - 0.5) * 1.4)
+        wh = torch.stack([s * ar.sqrt(), s / ar.sqrt()], 1)
+        per_img.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+    rois = torch.cat([torch.cat([torch.full((120, 1), float(i)), b], 1) for i, b in enumerate(per_img)])
+    ref, _ = _oracle_pooler(feats, rois, scales, 7, 0, True)
+    if mode == "cl":
+        fd = [f.to(DEV).contiguous(memory_format=torch.channels_last) for f in feats]
+    else:
+        monkeypatch.setattr(ops, "POOLER_LAYOUT", "nhwc")  # force layout change + NHWC kernel on NCHW inputs
+        fd = [f.to(DEV) for f in feats]
+    assert ops._pick_layout(fd, 1) == mode
+    y = ROIPooler(7, scales, 0, "ROIAlignV2")(fd, [b.to(DEV) for b in per_img])
+    ok, err = rel_close(y, ref, rtol=1e-4, atol=5e-5)
+    assert ok, err
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", "nchw")
+    y2 = ROIPooler(7, scales, 0, "ROIAlignV2")([f.to(DEV) for f in feats], [b.to(DEV) for b in per_img])
+    ok, err = rel_close(y, y2, rtol=1e-5, atol=1e-5)  # the two layouts sum the same taps (same lists, same order)
+    assert ok, err
+
+
 # ------------------------------------------------------------------------------- deformable conv on tcgen05 / TMEM
 @pytest.mark.parametrize("cin,cout,h,w,grp,dg,mod,stride,prec", [
     (64, 64, 12, 20, 1, 1, False, 1, 1), (128, 128, 25, 42, 1, 1, False, 1, 1), (128, 192, 17, 23, 2, 1, True, 1, 1),
