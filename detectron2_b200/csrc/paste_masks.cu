@@ -23,11 +23,9 @@ __device__ __forceinline__ float sample_coord(float p, float b0, float b1, float
   return ((g + 1.f) * M - 1.f) / 2.f;
 }
 
-// exact value of one output pixel (reference expression order, see file header)
-__device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask, int M, float fM, int px, int py,
-                                                float x0, float y0, float x1, float y1, float threshold) {
-  const float ix = sample_coord((float)px, x0, x1, fM);
-  const float iy = sample_coord((float)py, y0, y1, fM);
+// exact value of one output pixel from its sample coordinates (reference expression order, see file header)
+__device__ __forceinline__ uint32_t paste_value(const float* __restrict__ smask, int M, float fM, float ix, float iy,
+                                                float threshold) {
   float v = 0.f;
   // in-range test written so that NaN / inf (degenerate boxes) fall through to 0
   if (ix > -1.f && ix < fM && iy > -1.f && iy < fM) {
@@ -43,11 +41,20 @@ __device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask,
   return threshold >= 0.f ? (v >= threshold ? 1u : 0u) : (uint32_t)(uint8_t)(v * 255.f);
 }
 
+__device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask, int M, float fM, int px, int py,
+                                                float x0, float y0, float x1, float y1, float threshold) {
+  return paste_value(smask, M, fM, sample_coord((float)px, x0, x1, fM), sample_coord((float)py, y0, y1, fM), threshold);
+}
+
 // grid (gx, N).  Two phases per mask:
 //   1. every 16-byte chunk of the output plane that cannot see the mask (conservative rectangle test) is written as
 //      one 128-bit store of the "outside" value -- this is ~90% of the bytes and runs at store bandwidth;
-//   2. the rows/columns of the conservative rectangle, widened to whole 16-byte chunks, are evaluated exactly with one
-//      pixel per lane, so a warp works on 32 neighbouring pixels (no divergence between inside / outside lanes).
+//   2. the rows/columns of the conservative rectangle, widened to whole 16-byte chunks, are evaluated exactly.  The sample
+//      coordinates are separable (ix depends on the column only, iy on the row only) and each costs two IEEE divisions,
+//      so TAB = true tabulates them once per CTA in shared memory (the same expressions: bit-identical values); a warp
+//      then owns a row of the rectangle, a lane 4 neighbouring pixels (one 32-bit store).  TAB = false (image too large
+//      for the tables) evaluates one pixel per lane from scratch.
+template <bool TAB>
 __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __restrict__ masks,
                                                                const float* __restrict__ boxes, int M, int H, int W,
                                                                float threshold, uint8_t* __restrict__ out,
@@ -114,9 +121,46 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
       }
     }
   }
-  // ---- phase 2a: the rectangle, row by row, widened to chunk boundaries (one pixel per lane).  32-bit index math; the
-  //      byte -> (py, px) mapping needs no division because a widened range spills at most 15 bytes into a neighbour row.
-  if (!empty) {
+  // ---- phase 2a (TAB): coordinate tables, then one warp per rectangle row, 4 pixels per lane
+  if (TAB && !empty) {
+    extern __shared__ float tabs[];
+    float* __restrict__ ixs = tabs;      // [W]            sample x of every column
+    float* __restrict__ iys = tabs + W;  // [nrows + 2]    sample y of rows ry0-1 .. ry1+1 (a widened range may wrap a row)
+    const int rbase = ry0 - 1;
+    const int nrows = ry1 - ry0 + 1;
+    for (int i = threadIdx.x; i < W; i += kThreads) ixs[i] = sample_coord((float)i, x0, x1, fM);
+    for (int i = threadIdx.x; i < nrows + 2; i += kThreads) iys[i] = sample_coord((float)(rbase + i), y0, y1, fM);
+    __syncthreads();
+    const int body_end = head + (int)((plane - head) / kPix) * kPix;  // bytes past it belong to phase 2b
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (kThreads / 32);
+    for (int dr = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); dr < nrows; dr += warps) {
+      const int r = ry0 + dr;
+      const int lo = r * W + cx0, hi = r * W + cx1;  // inclusive flat range of this row
+      const int A = lo < head ? head : ((lo - head) & ~(kPix - 1)) + head;
+      int B = hi < head ? head : (((hi - head) >> 4) + 1) * kPix + head;
+      if (B > body_end) B = body_end;
+      for (int b4 = A + 4 * lane; b4 < B; b4 += 128) {  // (obase + A) is 16-byte aligned, B - A a multiple of 16
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int py = r, px = b4 + q - r * W;
+          if (px < 0) {
+            px += W;
+            --py;
+          } else if (px >= W) {
+            px -= W;
+            ++py;
+          }
+          word |= paste_value(smask, M, fM, ixs[px], iys[py - rbase], threshold) << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(obase + b4) = word;
+      }
+    }
+  }
+  // ---- phase 2a (!TAB): the rectangle, row by row, widened to chunk boundaries (one pixel per lane).  32-bit index math;
+  //      the byte -> (py, px) mapping needs no division because a widened range spills at most 15 bytes into a neighbour row.
+  if (!TAB && !empty) {
     const int RL = (cx1 - cx0 + 1) + 2 * (kPix - 1) + 1;
     const int nrows = ry1 - ry0 + 1;
     const int iplane = (int)plane;  // H*W < 2^31 (checked on the host)
@@ -132,10 +176,11 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
       const int byte = A + t;
       if (byte >= B) continue;
       int py = r, px = byte - r * W;
-      if (px < 0) {
+      while (px < 0) {  // a widened range spills at most 15 bytes: one wrap unless the image is narrower than a chunk
         px += W;
         --py;
-      } else if (px >= W) {
+      }
+      while (px >= W) {
         px -= W;
         ++py;
       }
@@ -172,7 +217,11 @@ D2B_API int d2b_paste_masks(const float* masks, const float* boxes, int N, int M
   int want = d2b_cdiv(8LL * kNumSMs, N);
   if (gx > want) gx = want < 1 ? 1 : want;
   dim3 grid(gx, N);
-  paste_masks_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, chunks);
+  const size_t tab_bytes = sizeof(float) * ((size_t)W + (size_t)H + 2);
+  if (W >= kPix && tab_bytes <= 30 * 1024)  // 16 KB static mask + tables inside the default 48 KB; one-wrap rows
+    paste_masks_kernel<true><<<grid, kThreads, tab_bytes, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, chunks);
+  else
+    paste_masks_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, chunks);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

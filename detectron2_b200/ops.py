@@ -34,9 +34,9 @@ def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
 #   * NCHW inputs go to the NCHW kernel, unless the call is large enough that "one layout-change launch + NHWC
 #     pooling" is cheaper (cost model below, fitted to the B200 measurements in profiles/r1_ops.md).
 POOLER_LAYOUT = os.environ.get("D2B_POOLER_LAYOUT", "auto")
-_NCHW_PS_PER_OUT = 18.0      # NCHW kernel: picoseconds per output element (adaptive sampling, FPN-sized RoIs)
-_NHWC_PS_PER_OUT = 6.0       # NHWC kernel
-_XPOSE_PS_PER_BYTE = 0.42    # layout change: read + write each byte once at ~4.8 TB/s
+_NCHW_PS_PER_OUT = 13.0      # NCHW kernel: picoseconds per output element (12.4 mask head .. 17.8 box head)
+_NHWC_PS_PER_OUT = 7.5       # NHWC kernel (7.4 .. 7.6)
+_XPOSE_PS_PER_BYTE = 0.32    # layout change: 91.7 MB of fp32 features in 29 us (reads + writes each byte once)
 
 
 def _is_channels_last(t: Tensor) -> bool:
@@ -66,6 +66,32 @@ def _to_nhwc(fs, P, n: int, c: int, device):
     dst = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
     check(_C.lib().d2b_pyramid_nchw_to_nhwc(C.byref(P), n, c, dst, stream_ptr(device)), "pyramid_nchw_to_nhwc")
     return bufs
+
+
+def pyramid_to_channels_last(feats: List[Tensor]) -> List[Tensor]:
+    """All levels of an NCHW fp32 feature pyramid -> channels_last tensors (same logical [N,C,H,W] shape, NHWC storage)
+    with ONE kernel launch.  A caller that pools the same features more than once per image (box head + mask head,
+    roi_heads.py:798,856 in the reference) converts once and hands the result to every ROIPooler / ROIAlign call, which
+    then run the channels-last kernel in place.  Inputs that are already channels_last, need autograd, are not fp32 or
+    do not fit the NHWC kernel's limits are returned through torch's own (autograd-aware) conversion / unchanged."""
+    _C.require_cuda(*feats)
+    if len(feats) == 0 or len(feats) > _C.MAX_LEVELS:
+        raise RuntimeError("pyramid_to_channels_last: need 1..%d levels" % _C.MAX_LEVELS)
+    c = feats[0].shape[1]
+    if not _nhwc_ok(feats, c) or any(t.shape[:2] != feats[0].shape[:2] for t in feats):
+        return list(feats)
+    if any(t.dtype != torch.float32 for t in feats) or (torch.is_grad_enabled() and any(t.requires_grad for t in feats)):
+        return [t.contiguous(memory_format=torch.channels_last) for t in feats]
+    if all(_is_channels_last(t) for t in feats):
+        return list(feats)
+    fs = [t.contiguous() for t in feats]
+    n = fs[0].shape[0]
+    if n == 0 or c == 0:
+        return list(feats)
+    with torch.cuda.device(fs[0].device):
+        P = _pyramid(fs, None, [1.0] * len(fs), 0, len(fs) - 1, 0, 1.0)
+        bufs = _to_nhwc(fs, P, n, c, fs[0].device)
+    return [b.permute(0, 3, 1, 2) for b in bufs]
 
 
 def _roi_common(input: Tensor, rois: Tensor, cols: int):

@@ -14,7 +14,9 @@ from torch import nn
 from . import ops
 from .layers import ROIAlignRotated
 
-__all__ = ["ROIPooler", "assign_boxes_to_levels", "convert_boxes_to_pooler_format"]
+__all__ = ["ROIPooler", "assign_boxes_to_levels", "convert_boxes_to_pooler_format", "pyramid_to_channels_last"]
+
+pyramid_to_channels_last = ops.pyramid_to_channels_last
 
 
 def _tensor_of(b):

@@ -360,6 +360,20 @@ def test_paste_masks_golden(L, golden):
     assert L.paste_masks_in_image(torch.zeros(0, 28, 28, device=DEV), torch.zeros(0, 4, device=DEV), (h, w)).shape == (0, h, w)
 
 
+@pytest.mark.parametrize("h,w", [(5, 7), (3, 40), (2, 7700), (37, 129), (64, 64)])
+def test_paste_masks_odd_shapes_vs_oracle(L, h, w):
+    # narrow images (rows shorter than a 16-byte chunk), images too large for the coordinate tables, unaligned planes
+    g = torch.Generator().manual_seed(h * w)
+    n = 7
+    masks = torch.rand(n, 28, 28, generator=g)
+    ctr = torch.rand(n, 2, generator=g) * torch.tensor([float(w), float(h)])
+    wh = 1 + torch.rand(n, 2, generator=g) * torch.tensor([float(w), float(h)])
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    for thr in (0.5, -1):
+        out = L.paste_masks_in_image(masks.to(DEV), boxes.to(DEV), (h, w), thr)
+        assert torch.equal(out.cpu(), orc.paste_masks(masks, boxes, (h, w), thr)), thr
+
+
 def test_paste_masks_full_size_vs_oracle(L):
     # config 2: 100 masks, 800x1333 image; oracle on a 12-mask subset (seconds), all 100 via a checksum property
     g = torch.Generator().manual_seed(42)
@@ -450,6 +464,17 @@ def test_pyramid_layout_change_is_exact():
     bufs = ops._to_nhwc(feats, P, 2, 36, feats[0].device)
     for f, b in zip(feats, bufs):
         assert torch.equal(b, f.permute(0, 2, 3, 1))
+    # public form: ordinary channels_last tensors (same logical shape), consumed in place by the pooler
+    from detectron2_b200.poolers import pyramid_to_channels_last
+
+    cl = pyramid_to_channels_last(feats[:2])
+    for f, t in zip(feats, cl):
+        assert t.shape == f.shape and torch.equal(t, f) and t.is_contiguous(memory_format=torch.channels_last)
+    assert ops._pick_layout(cl, 1) == "cl"
+    again = pyramid_to_channels_last(cl)
+    assert all(a.data_ptr() == b.data_ptr() for a, b in zip(again, cl))  # already channels_last: no copy
+    xg = [f.clone().requires_grad_(True) for f in feats[:2]]
+    assert all(t.requires_grad for t in pyramid_to_channels_last(xg))    # autograd inputs: torch's own conversion
 
 
 @pytest.mark.parametrize("c,ph,pw,sr,aligned", [(4, 7, 7, 0, True), (12, 7, 7, 2, False), (132, 7, 7, 0, True),
