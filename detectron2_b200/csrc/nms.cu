@@ -331,36 +331,47 @@ constexpr int kScanThreads = 512;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kMaxColsPerWarp = 10;  // register-prefetched column words per warp (covers segments <= 64*16*10 = 10240)
 
-// segment table of the class-major order: seg_start[0..nseg], seg_start[nseg] = M.  Single CTA.
+// Exclusive prefix sum of one int per thread over a 1024-thread CTA (shuffle scan inside the warps, one barrier);
+// `total` receives the sum over the CTA.  warp_tot: 32 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* __restrict__ warp_tot, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  const int wt = warp_tot[lane];
+  int winc = wt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += t;
+  }
+  total = __shfl_sync(0xffffffffu, winc, 31);
+  const int wbase = __shfl_sync(0xffffffffu, winc, warp) - __shfl_sync(0xffffffffu, wt, warp);
+  return wbase + inc - v;
+}
+
+// segment table of the class-major order: seg_start[0..nseg], seg_start[nseg] = M.  Single CTA; every thread owns a
+// contiguous strip of positions (count, one block-wide scan, write), so the table comes out in ascending order.
 __global__ void __launch_bounds__(1024) nms_segments_kernel(const int* __restrict__ cls, int M, int* __restrict__ seg_start,
                                                             int* __restrict__ nseg) {
   __shared__ int warp_tot[32];
-  __shared__ int s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int p0 = 0; p0 < M; p0 += 1024) {
-    const int p = p0 + tid;
-    const int flag = (p < M) && (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1]));
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    const int in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < 32; ++w) {
-      const int t = warp_tot[w];
-      if (w < warp) before += t;
-      total += t;
-    }
-    const int base = s_base;
-    if (flag) seg_start[base + before + in_warp] = p;
-    __syncthreads();
-    if (tid == 0) s_base = base + total;
-    __syncthreads();
-  }
+  const int tid = threadIdx.x;
+  const int per = (M + 1023) / 1024;
+  const int p0 = min(M, tid * per), p1 = min(M, p0 + per);
+  int cnt = 0;
+  for (int p = p0; p < p1; ++p) cnt += (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1])) ? 1 : 0;
+  int total;
+  int idx = block_excl_scan_1024(cnt, warp_tot, total);
+  for (int p = p0; p < p1; ++p)
+    if (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1])) seg_start[idx++] = p;
   if (tid == 0) {
-    seg_start[s_base] = M;
-    *nseg = s_base;
+    seg_start[total] = M;
+    *nseg = total;
   }
 }
 
@@ -503,35 +514,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
   }
 }
 
-// keep[] = original indices of the flagged ranks, in rank (= score) order; single CTA.
+// keep[] = original indices of the flagged ranks, in rank (= score) order; single CTA, contiguous strip per thread.
 __global__ void __launch_bounds__(1024) nms_compact_kernel(const unsigned char* __restrict__ keepflag,
                                                            const int* __restrict__ order, int M,
                                                            long long* __restrict__ keep, long long* __restrict__ num_keep) {
   __shared__ int warp_tot[32];
-  __shared__ int s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int r0 = 0; r0 < M; r0 += 1024) {
-    const int r = r0 + tid;
-    const int flag = (r < M) && keepflag[r];
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    const int in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < 32; ++w) {
-      const int t = warp_tot[w];
-      if (w < warp) before += t;
-      total += t;
-    }
-    const int base = s_base;
-    if (flag) keep[base + before + in_warp] = (long long)order[r];
-    __syncthreads();
-    if (tid == 0) s_base = base + total;
-    __syncthreads();
-  }
-  if (tid == 0) *num_keep = (long long)s_base;
+  const int tid = threadIdx.x;
+  const int per = (M + 1023) / 1024;
+  const int r0 = min(M, tid * per), r1 = min(M, r0 + per);
+  int cnt = 0;
+  for (int r = r0; r < r1; ++r) cnt += keepflag[r] ? 1 : 0;
+  int total;
+  int idx = block_excl_scan_1024(cnt, warp_tot, total);
+  for (int r = r0; r < r1; ++r)
+    if (keepflag[r]) keep[idx++] = (long long)order[r];
+  if (tid == 0) *num_keep = (long long)total;
 }
 
 struct NmsWorkspace {

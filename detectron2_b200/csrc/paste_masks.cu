@@ -46,6 +46,84 @@ __device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask,
   return paste_value(smask, M, fM, sample_coord((float)px, x0, x1, fM), sample_coord((float)py, y0, y1, fM), threshold);
 }
 
+// Conservative support of the pasted mask: outside [cx0,cx1] x [ry0,ry1] every sample point lies >= 1.5 px beyond the
+// mask's (-1, M) support, far more than fp32 rounding can move it, so the value there is exactly that of v = 0.
+// Degenerate / non-finite boxes disable the shortcut (everything is evaluated exactly).
+struct PasteRect {
+  int cx0, cx1, ry0, ry1;
+};
+
+__device__ __forceinline__ PasteRect paste_rect(float x0, float y0, float x1, float y1, float fM, int H, int W) {
+  PasteRect r = {0, W - 1, 0, H - 1};
+  const float bw = x1 - x0, bh = y1 - y0;
+  if (W >= 2 * kPix && bw > 0.f && bh > 0.f && bw < 1e8f && bh < 1e8f && fabsf(x0) < 1e8f && fabsf(y0) < 1e8f) {
+    const float fx0 = floorf(x0 - bw / fM) - 2.f, fx1 = ceilf(x1 + bw / fM) + 2.f;
+    const float fy0 = floorf(y0 - bh / fM) - 2.f, fy1 = ceilf(y1 + bh / fM) + 2.f;
+    r.cx0 = (int)fmaxf(fx0, 0.f);
+    r.cx1 = (int)fminf(fx1, (float)(W - 1));
+    r.ry0 = (int)fmaxf(fy0, 0.f);
+    r.ry1 = (int)fminf(fy1, (float)(H - 1));
+  }
+  return r;
+}
+
+// CTAs of a balanced launch (1-D grid): every mask gets one CTA plus a share of the remaining ones proportional to its
+// estimated instruction count (zero-fill of the plane + exact evaluation of its rectangle) -- with a fixed number of CTAs
+// per mask the few large boxes of an image finish long after everything else.  Integer arithmetic: every CTA derives the
+// same boundaries.  Returns this CTA's mask, its index among the mask's CTAs and their count.
+__device__ __forceinline__ void paste_assign(const float* __restrict__ boxes, int N, int M, int H, int W, int& n,
+                                             int& local, int& count) {
+  __shared__ unsigned long long s_wsum[kThreads / 32];
+  __shared__ int s_asg[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (N + kThreads - 1) / kThreads;  // masks per thread (contiguous strip)
+  const int m0 = min(N, tid * per), m1 = min(N, m0 + per);
+  const unsigned long long fill = (unsigned long long)((long long)H * W / kPix) * 24ull;
+  unsigned long long mine = 0;
+  for (int m = m0; m < m1; ++m) {
+    const PasteRect r = paste_rect(boxes[4 * m], boxes[4 * m + 1], boxes[4 * m + 2], boxes[4 * m + 3], (float)M, H, W);
+    unsigned long long c = fill;
+    if (r.cx1 >= r.cx0 && r.ry1 >= r.ry0) c += (unsigned long long)(r.ry1 - r.ry0 + 1) * (unsigned long long)(r.cx1 - r.cx0 + 32) * 44ull;
+    mine += (c >> 8) + 1ull;
+  }
+  unsigned long long inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  unsigned long long wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const unsigned long long t = s_wsum[w];
+    if (w < warp) wbase += t;
+    total += t;
+  }
+  unsigned long long prefix = wbase + inc - mine;  // cost of all masks before this thread's strip
+  const unsigned long long spare = (unsigned long long)((int)gridDim.x - N);
+  const unsigned f = blockIdx.x;
+  for (int m = m0; m < m1; ++m) {
+    const PasteRect r = paste_rect(boxes[4 * m], boxes[4 * m + 1], boxes[4 * m + 2], boxes[4 * m + 3], (float)M, H, W);
+    unsigned long long c = fill;
+    if (r.cx1 >= r.cx0 && r.ry1 >= r.ry0) c += (unsigned long long)(r.ry1 - r.ry0 + 1) * (unsigned long long)(r.cx1 - r.cx0 + 32) * 44ull;
+    c = (c >> 8) + 1ull;
+    const unsigned b0 = (unsigned)m + (unsigned)(spare * prefix / total);
+    const unsigned b1 = (unsigned)(m + 1) + (unsigned)(spare * (prefix + c) / total);
+    if (f >= b0 && f < b1) {
+      s_asg[0] = m;
+      s_asg[1] = (int)(f - b0);
+      s_asg[2] = (int)(b1 - b0);
+    }
+    prefix += c;
+  }
+  __syncthreads();
+  n = s_asg[0];
+  local = s_asg[1];
+  count = s_asg[2];
+}
+
 // grid (gx, N).  Two phases per mask:
 //   1. every 16-byte chunk of the output plane that cannot see the mask (conservative rectangle test) is written as
 //      one 128-bit store of the "outside" value -- this is ~90% of the bytes and runs at store bandwidth;
@@ -57,30 +135,18 @@ __device__ __forceinline__ uint32_t paste_pixel(const float* __restrict__ smask,
 template <bool TAB>
 __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __restrict__ masks,
                                                                const float* __restrict__ boxes, int M, int H, int W,
-                                                               float threshold, uint8_t* __restrict__ out,
-                                                               int chunks_per_mask) {
+                                                               float threshold, uint8_t* __restrict__ out, int N,
+                                                               int balanced) {
   __shared__ float smask[kMaxM * kMaxM];
-  const int n = blockIdx.y;
+  int n = blockIdx.y, cta_local = blockIdx.x, cta_count = gridDim.x;  // uniform launch: grid (CTAs per mask, N)
+  if (balanced) paste_assign(boxes, N, M, H, W, n, cta_local, cta_count);
   const float* __restrict__ mk = masks + (size_t)n * M * M;
   for (int i = threadIdx.x; i < M * M; i += kThreads) smask[i] = mk[i];
   const float x0 = boxes[4 * n], y0 = boxes[4 * n + 1], x1 = boxes[4 * n + 2], y1 = boxes[4 * n + 3];
   __syncthreads();
   const float fM = (float)M;
-  // Conservative support of the pasted mask: outside [cx0,cx1] x [ry0,ry1] every sample point lies >= 1.5 px beyond the
-  // mask's (-1, M) support, far more than fp32 rounding can move it, so the value there is exactly that of v = 0.
-  // Degenerate / non-finite boxes disable the shortcut (everything is evaluated exactly).
-  int cx0 = 0, cx1 = W - 1, ry0 = 0, ry1 = H - 1;
-  {
-    const float bw = x1 - x0, bh = y1 - y0;
-    if (W >= 2 * kPix && bw > 0.f && bh > 0.f && bw < 1e8f && bh < 1e8f && fabsf(x0) < 1e8f && fabsf(y0) < 1e8f) {
-      const float fx0 = floorf(x0 - bw / fM) - 2.f, fx1 = ceilf(x1 + bw / fM) + 2.f;
-      const float fy0 = floorf(y0 - bh / fM) - 2.f, fy1 = ceilf(y1 + bh / fM) + 2.f;
-      cx0 = (int)fmaxf(fx0, 0.f);
-      cx1 = (int)fminf(fx1, (float)(W - 1));
-      ry0 = (int)fmaxf(fy0, 0.f);
-      ry1 = (int)fminf(fy1, (float)(H - 1));
-    }
-  }
+  const PasteRect rect = paste_rect(x0, y0, x1, y1, fM, H, W);
+  const int cx0 = rect.cx0, cx1 = rect.cx1, ry0 = rect.ry0, ry1 = rect.ry1;
   const bool empty = cx1 < cx0 || ry1 < ry0;  // rectangle entirely off the image
   const uint32_t zbyte = threshold >= 0.f ? ((0.f >= threshold) ? 1u : 0u) : 0u;
   const uint32_t zword = zbyte * 0x01010101u;
@@ -88,8 +154,8 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
   uint8_t* __restrict__ obase = out + (size_t)n * plane;
   // obase may be misaligned w.r.t. 16 B when H*W is not a multiple of 16: chunk c covers [head + 16c, head + 16c + 16)
   const int head = (int)((16 - ((uintptr_t)obase & 15)) & 15);
-  const long long stride = (long long)gridDim.x * kThreads;
-  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long stride = (long long)cta_count * kThreads;
+  const long long gtid = (long long)cta_local * kThreads + threadIdx.x;
 
   // ---- phase 1: chunks that cannot see the mask.  (py, px) of a thread's chunk advance incrementally: one 32-bit
   //      division per thread instead of one 64-bit division per chunk -- this loop is instruction-bound, not HBM-bound.
@@ -128,13 +194,19 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
     float* __restrict__ iys = tabs + W;  // [nrows + 2]    sample y of rows ry0-1 .. ry1+1 (a widened range may wrap a row)
     const int rbase = ry0 - 1;
     const int nrows = ry1 - ry0 + 1;
-    for (int i = threadIdx.x; i < W; i += kThreads) ixs[i] = sample_coord((float)i, x0, x1, fM);
+    // columns a widened row range can touch: the rectangle +- 15, plus the far edge when the range wraps into a neighbour row
+    const int c_lo = max(cx0 - (kPix - 1), 0), c_hi = min(cx1 + (kPix - 1), W - 1);
+    for (int i = c_lo + threadIdx.x; i <= c_hi; i += kThreads) ixs[i] = sample_coord((float)i, x0, x1, fM);
+    if (threadIdx.x < 2 * kPix) {
+      const int i = threadIdx.x < kPix ? threadIdx.x : W - 2 * kPix + threadIdx.x;  // [0,16) and [W-16,W)
+      ixs[i] = sample_coord((float)i, x0, x1, fM);
+    }
     for (int i = threadIdx.x; i < nrows + 2; i += kThreads) iys[i] = sample_coord((float)(rbase + i), y0, y1, fM);
     __syncthreads();
     const int body_end = head + (int)((plane - head) / kPix) * kPix;  // bytes past it belong to phase 2b
     const int lane = threadIdx.x & 31;
-    const int warps = gridDim.x * (kThreads / 32);
-    for (int dr = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); dr < nrows; dr += warps) {
+    const int warps = cta_count * (kThreads / 32);
+    for (int dr = cta_local * (kThreads / 32) + (threadIdx.x >> 5); dr < nrows; dr += warps) {
       const int r = ry0 + dr;
       const int lo = r * W + cx0, hi = r * W + cx1;  // inclusive flat range of this row
       const int A = lo < head ? head : ((lo - head) & ~(kPix - 1)) + head;
@@ -188,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
     }
   }
   // ---- phase 2b: unaligned head and ragged tail bytes (< 32 bytes per mask)
-  if (blockIdx.x == 0) {
+  if (cta_local == 0) {
     const long long tail0 = head + (long long)((plane - head) / kPix) * kPix;
     for (long long byte = threadIdx.x; byte < head && byte < plane; byte += kThreads) {
       const int py = (int)(byte / W), px = (int)(byte - (long long)py * W);
@@ -212,16 +284,20 @@ D2B_API int d2b_paste_masks(const float* masks, const float* boxes, int N, int M
   long long plane = (long long)H * W;
   if (plane >= (1LL << 30)) return D2B_EUNSUPPORTED;  // 32-bit pixel indices inside one mask plane
   int chunks = (int)((plane + kPix - 1) / kPix);  // upper bound; chunks past the plane are skipped in-kernel
-  int gx = d2b_cdiv(chunks + 1, kThreads);
-  // enough CTAs per mask to fill the machine even for a single mask, capped to keep the smem mask staging amortised
-  int want = d2b_cdiv(8LL * kNumSMs, N);
-  if (gx > want) gx = want < 1 ? 1 : want;
-  dim3 grid(gx, N);
   const size_t tab_bytes = sizeof(float) * ((size_t)W + (size_t)H + 2);
-  if (W >= kPix && tab_bytes <= 30 * 1024)  // 16 KB static mask + tables inside the default 48 KB; one-wrap rows
-    paste_masks_kernel<true><<<grid, kThreads, tab_bytes, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, chunks);
-  else
-    paste_masks_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, chunks);
+  const bool tab = W >= 2 * kPix && tab_bytes <= 30 * 1024;  // 16 KB static mask + tables inside the default 48 KB; one-wrap rows
+  const int total = 8 * kNumSMs;
+  if (2 * N <= total) {  // balanced: CTAs handed to the masks in proportion to their work (decided in-kernel from the boxes)
+    if (tab) paste_masks_kernel<true><<<total, kThreads, tab_bytes, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, N, 1);
+    else paste_masks_kernel<false><<<total, kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, N, 1);
+  } else {  // many masks: a fixed, small number of CTAs each
+    int gx = d2b_cdiv(chunks + 1, kThreads);
+    int want = d2b_cdiv(8LL * kNumSMs, N);
+    if (gx > want) gx = want < 1 ? 1 : want;
+    dim3 grid(gx, N);
+    if (tab) paste_masks_kernel<true><<<grid, kThreads, tab_bytes, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, N, 0);
+    else paste_masks_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, threshold, out, N, 0);
+  }
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

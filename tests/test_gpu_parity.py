@@ -374,6 +374,18 @@ def test_paste_masks_odd_shapes_vs_oracle(L, h, w):
         assert torch.equal(out.cpu(), orc.paste_masks(masks, boxes, (h, w), thr)), thr
 
 
+def test_paste_masks_many_masks_uniform_grid_vs_oracle(L):
+    # more masks than half the CTA budget: fixed CTAs-per-mask launch instead of the work-proportional assignment
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 700, 40, 72
+    masks = torch.rand(n, 28, 28, generator=g)
+    ctr = torch.rand(n, 2, generator=g) * torch.tensor([float(w), float(h)])
+    wh = 1 + torch.rand(n, 2, generator=g) * torch.tensor([float(w), float(h)])
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    out = L.paste_masks_in_image(masks.to(DEV), boxes.to(DEV), (h, w), 0.5)
+    assert torch.equal(out.cpu(), orc.paste_masks(masks, boxes, (h, w), 0.5))
+
+
 def test_paste_masks_full_size_vs_oracle(L):
     # config 2: 100 masks, 800x1333 image; oracle on a 12-mask subset (seconds), all 100 via a checksum property
     g = torch.Generator().manual_seed(42)
