@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
   __shared__ int rowoff[kRowoffCap];    // global offset (y*W + x) of every footprint pixel, row-major
   __shared__ int yn[kMaxP], xn[kMaxP], ylo[kMaxP], yhi[kMaxP];
   __shared__ int band_ph0[kMaxP + 1], band_yb[kMaxP], band_npx[kMaxP];
-  __shared__ int s_overflow, s_xmin, s_xmax, s_nbands, s_direct, s_nyu, s_nxu, s_ymin, s_ymax;
+  __shared__ int s_overflow, s_tapov, s_xmin, s_xmax, s_nbands, s_direct, s_nyu, s_nxu, s_ymin, s_ymax;
 
   const int k = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
   const int g_begin = blockIdx.y * groups_per_cta, g_end = min(ngroup, g_begin + groups_per_cta);
 
   if (tid == 0) {
-    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;
+    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;  // written here only; tap-list overflow goes to s_tapov (atomic)
+    s_tapov = 0;
     s_xmin = 1 << 30;
     s_xmax = -1;
   }
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
       yn[tid] = n;
       ylo[tid] = lo;
       yhi[tid] = hi;
-      if (ov) s_overflow = 1;
+      if (ov) atomicOr(&s_tapov, 1);
     } else if (tid >= 32 && tid < 32 + PW) {
       const int pw = tid - 32;
       CTap* list = xtab + pw;
@@ -358,13 +359,14 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
         atomicMax(&s_xmax, list[e * kMaxP].idx);
       }
       xn[pw] = n;
-      if (ov) s_overflow = 1;
+      if (ov) atomicOr(&s_tapov, 1);
     }
   }
   __syncthreads();
   const int xmin = s_xmin, fw = s_xmax - s_xmin + 1;
   if (tid == 0) {  // uniform list lengths, band schedule
-    int direct = s_overflow, nb = 0, nyu = 0, nxu = 0, ymin = 1 << 30, ymax = -1;
+    const int overflow = s_overflow | s_tapov;
+    int direct = overflow, nb = 0, nyu = 0, nxu = 0, ymin = 1 << 30, ymax = -1;
     if (!direct) {
       for (int ph = 0; ph < PH; ++ph) {
         nyu = max(nyu, yn[ph]);
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
     s_nbands = nb;
     // mode 0: staged footprint; 1: tap lists + loads straight from global (footprint too large for a warp's slice, or
     // sparsely sampled: fewer distinct taps than half the footprint pixels); 2: tap lists overflowed -> taps on the fly
-    int mode = s_overflow ? 2 : (direct ? 1 : 0);
+    int mode = overflow ? 2 : (direct ? 1 : 0);
     if (mode == 0 && fw > 0 && ymax >= ymin) {
       int sy = 0, sx = 0;
       for (int ph = 0; ph < PH; ++ph) sy += yn[ph];
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   __shared__ CTap ytab[kMaxE * kMaxP];            // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];            // [tap][pw]
   __shared__ int yn[kMaxP], xn[kMaxP];
-  __shared__ int s_overflow;
+  __shared__ int s_overflow, s_tapov;
   __shared__ RoiGeom sg;  // read from shared memory where needed: keeps the tap loop's register budget small
 
   const int k = blockIdx.x;
@@ -790,7 +792,8 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   const bool lane_live = lane * 4 < ncta;
   // a dead lane (ragged last slab) re-reads the slab's first quad and is never stored
   if (tid == 0) {
-    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;
+    s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;  // written here only; tap-list overflow goes to s_tapov (atomic)
+    s_tapov = 0;
     sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
   }
   __syncthreads();
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
       }
       for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= W * C4;  // row offset in float4 units
       yn[tid] = n;
-      if (ov) s_overflow = 1;
+      if (ov) atomicOr(&s_tapov, 1);
     } else if (tid >= 32 && tid < 32 + PW) {
       const int pw = tid - 32;
       const RoiGeom g = sg;
@@ -821,11 +824,11 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
       }
       for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4;
       xn[pw] = n;
-      if (ov) s_overflow = 1;
+      if (ov) atomicOr(&s_tapov, 1);
     }
   }
   __syncthreads();
-  const bool onfly = s_overflow != 0;
+  const bool onfly = (s_overflow | s_tapov) != 0;
 
   {
     const int bin0 = blockIdx.z * chunk;  // one output chunk per CTA

@@ -71,7 +71,7 @@ def _to_nhwc(fs, P, n: int, c: int, device):
 def pyramid_to_channels_last(feats: List[Tensor]) -> List[Tensor]:
     """All levels of an NCHW fp32 feature pyramid -> channels_last tensors (same logical [N,C,H,W] shape, NHWC storage)
     with ONE kernel launch.  A caller that pools the same features more than once per image (box head + mask head,
-    roi_heads.py:798,856 in the reference) converts once and hands the result to every ROIPooler / ROIAlign call, which
+    roi_heads.py:798,843 in the reference) converts once and hands the result to every ROIPooler / ROIAlign call, which
     then run the channels-last kernel in place.  Inputs that are already channels_last, need autograd, are not fp32 or
     do not fit the NHWC kernel's limits are returned through torch's own (autograd-aware) conversion / unchanged."""
     _C.require_cuda(*feats)

@@ -114,3 +114,28 @@ def test_fake_kernels_trace_shapes():
         assert ops.box_iou_rotated_op(torch.empty(5, 5, device="cuda"), torch.empty(9, 5, device="cuda")).shape == (5, 9)
         pm = ops.paste_masks_op(torch.empty(3, 28, 28, device="cuda"), torch.empty(3, 4, device="cuda"), 40, 50, 0.5)
         assert pm.shape == (3, 40, 50) and pm.dtype == torch.uint8
+
+
+def test_pooler_layout_policy_host_logic(monkeypatch):
+    """Which RoIAlign kernel a call gets (detectron2_b200/ops.py): pure host logic, checked on CPU tensors."""
+    from detectron2_b200 import ops
+
+    nchw = [torch.zeros(1, 256, 200 // 2 ** i, 336 // 2 ** i) for i in range(4)]
+    cl = [t.contiguous(memory_format=torch.channels_last) for t in nchw]
+    assert all(ops._is_channels_last(t) for t in cl) and not any(ops._is_channels_last(t) for t in nchw)
+    # C == 1 or H*W == 1: both layouts coincide, treated as plain NCHW
+    assert not ops._is_channels_last(torch.zeros(2, 1, 5, 5).contiguous(memory_format=torch.channels_last))
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", "auto")
+    assert ops._pick_layout(cl, 1) == "cl"                        # channels_last is consumed in place
+    assert ops._pick_layout(nchw, 1000 * 256 * 49) == "xpose"     # box head: layout change + NHWC kernel pays
+    assert ops._pick_layout(nchw, 100 * 256 * 196) == "nchw"      # mask head alone: NCHW kernel
+    assert ops._pick_layout(nchw, 10 * 256 * 49) == "nchw"
+    assert ops._pick_layout([nchw[0], cl[1]], 10) == "nchw"        # mixed pyramid: falls back to the NCHW kernel
+    odd = [torch.zeros(1, 6, 8, 8).contiguous(memory_format=torch.channels_last)]
+    assert ops._pick_layout(odd, 10 ** 9) == "nchw"                # C % 4 != 0: NHWC kernel not applicable
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", "nchw")
+    assert ops._pick_layout(cl, 1) == "nchw"
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", "nhwc")
+    assert ops._pick_layout(nchw, 1) == "xpose"
+    with pytest.raises(NotImplementedError):                       # no CPU fallback for the layout change either
+        ops.pyramid_to_channels_last(nchw)
