@@ -313,6 +313,78 @@ def gen_fast_rcnn_inference():
     save("fast_rcnn_inference", **out)
 
 
+def _import_reference_dense_detector():
+    """The real DenseDetector decode methods + Box2BoxTransform, imported with stubs for their unrelated dependencies."""
+    import types
+
+    _import_reference_fast_rcnn()  # fvcore / pycocotools / config / events / data stubs, detectron2.layers + structures
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    sys.modules["detectron2.data.detection_utils"].convert_image_to_rgb = None
+    mm = sys.modules["detectron2.modeling"]
+    mm.Backbone = object
+    spec = importlib.util.spec_from_file_location("detectron2.modeling.box_regression",
+                                                  "/root/reference/detectron2/modeling/box_regression.py")
+    br = importlib.util.module_from_spec(spec)
+    sys.modules["detectron2.modeling.box_regression"] = br
+    spec.loader.exec_module(br)
+    ma = stub("detectron2.modeling.meta_arch")
+    ma.__path__ = []
+    stub("detectron2.modeling.postprocessing", detector_postprocess=None)
+    spec = importlib.util.spec_from_file_location("detectron2.modeling.meta_arch.dense_detector",
+                                                  "/root/reference/detectron2/modeling/meta_arch/dense_detector.py")
+    dd = importlib.util.module_from_spec(spec)
+    sys.modules["detectron2.modeling.meta_arch.dense_detector"] = dd
+    spec.loader.exec_module(dd)
+    return dd, br
+
+
+def gen_retinanet_inference():
+    """RetinaNet.forward_inference (meta_arch/retinanet.py:256-308) on the real DenseDetector decode methods."""
+    import types
+
+    dd, br = _import_reference_dense_detector()  # also puts /root/reference on sys.path
+    from detectron2.layers import batched_nms
+    from detectron2.structures import Boxes
+
+    g = torch.Generator().manual_seed(2024)
+    n, k_cls = 2, 5
+    image_sizes = [(96, 128), (80, 120)]
+    per_level = [(12 * 16 * 3, 8.0), (6 * 8 * 3, 16.0), (3 * 4 * 3, 32.0)]  # (H*W*A anchors, stride)
+    score_thresh, topk_candidates, nms_thresh, max_det = 0.3, 60, 0.5, 20
+    anchors, logits, deltas = [], [], []
+    for r, stride in per_level:
+        ctr = torch.rand(r, 2, generator=g) * torch.tensor([128.0, 96.0])
+        wh = stride * (2 + 4 * torch.rand(r, 2, generator=g))
+        anchors.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+        logits.append(torch.randn(n, r, k_cls, generator=g) * 1.5 - 1.0)
+        deltas.append(torch.randn(n, r, 4, generator=g) * 0.3)
+    deltas[0][0, 5, 2] = 9.0      # exercises the scale clamp (box_regression.py:103)
+    logits[2][1] = -20.0          # a level without any candidate for image 1
+    me = types.SimpleNamespace(box2box_transform=br.Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0)))
+    me._decode_per_level_predictions = types.MethodType(dd.DenseDetector._decode_per_level_predictions, me)
+    out = {"cfg": np.asarray([score_thresh, topk_candidates, nms_thresh, max_det]), "image_sizes": np.asarray(image_sizes)}
+    for l in range(len(per_level)):
+        out[f"anchors{l}"], out[f"logits{l}"], out[f"deltas{l}"] = anchors[l], logits[l], deltas[l]
+    for img_idx, image_size in enumerate(image_sizes):
+        scores_per_image = [x[img_idx].clone().sigmoid_() for x in logits]      # retinanet.py:267
+        deltas_per_image = [x[img_idx] for x in deltas]
+        pred = dd.DenseDetector._decode_multi_level_predictions(
+            me, [Boxes(a) for a in anchors], scores_per_image, deltas_per_image, score_thresh, topk_candidates, image_size)
+        keep = batched_nms(pred.pred_boxes.tensor, pred.scores, pred.pred_classes, nms_thresh)  # retinanet.py:305-307
+        res = pred[keep[:max_det]]                                                              # :308
+        out[f"n_candidates{img_idx}"] = np.asarray(len(pred))
+        out[f"out_boxes{img_idx}"] = res.pred_boxes.tensor
+        out[f"out_scores{img_idx}"] = res.scores
+        out[f"out_classes{img_idx}"] = res.pred_classes
+    save("retinanet_inference", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     gen_roi_align()
@@ -323,3 +395,4 @@ if __name__ == "__main__":
     gen_paste_masks()
     gen_rpn_proposals()
     gen_fast_rcnn_inference()
+    gen_retinanet_inference()
