@@ -532,9 +532,9 @@ def main():
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                      "algorithmic_bytes": alg_bytes, "avg_launch_ms": box_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                     # (profiles/r1_ncu_full.txt: 82.49 MB read + 24.81 MB written; the rest of the 50 MB output is still
-                     # in L2 when the kernel ends)
-                     "traffic": 107296000,
+                     # (profiles/r1_ncu_full.txt, launch id 3: 81.50 MB read + 23.06 MB written; the rest of the 50 MB
+                     # output is still in L2 when the kernel ends)
+                     "traffic": 104559104,
                      # the NCHW pyramid the reference API hands over is re-laid out once per image by nchw_to_nhwc_kernel
                      # (stage "layout": 2 x 91.7 MB at HBM speed); box pooling including that launch:
                      "achieved_incl_layout_change": alg_bytes / ((box_ms + layout_ms) / 1e3) / 1e9},
