@@ -385,6 +385,46 @@ def gen_retinanet_inference():
     save("retinanet_inference", **out)
 
 
+def gen_postprocessing():
+    """detector_postprocess (modeling/postprocessing.py:9-74) and BitMasks.crop_and_resize (structures/masks.py:193-224),
+    both from the real reference modules (CPU: torchvision roi_align, python paste)."""
+    _import_reference_fast_rcnn()  # stubs + sys.path
+    from detectron2.structures import BitMasks, Boxes, Instances
+
+    spec = importlib.util.spec_from_file_location("ref_postprocessing", "/root/reference/detectron2/modeling/postprocessing.py")
+    pp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pp)
+    g = torch.Generator().manual_seed(808)
+    n, m, h, w, oh, ow = 11, 28, 60, 90, 97, 141
+    boxes = random_boxes(g, n, 60)
+    boxes[:, 0::2] *= 1.4
+    boxes[0] = torch.tensor([10.0, 10.0, 10.0, 30.0])       # empty after scaling (zero width)
+    boxes[1] = torch.tensor([85.0, 50.0, 120.0, 70.0])      # clipped by the image border
+    boxes[2] = torch.tensor([95.0, 5.0, 130.0, 20.0])       # entirely outside -> empty after clipping
+    scores, classes = torch.rand(n, generator=g), torch.randint(0, 7, (n,), generator=g)
+    masks = torch.rand(n, 1, m, m, generator=g)
+    inst = Instances((h, w), pred_boxes=Boxes(boxes.clone()), scores=scores.clone(), pred_classes=classes.clone(),
+                     pred_masks=masks.clone())
+    res = pp.detector_postprocess(inst, oh, ow, 0.5)
+    out = {"hw": np.asarray([h, w, oh, ow]), "boxes": boxes, "scores": scores, "classes": classes, "masks": masks,
+           "out_boxes": res.pred_boxes.tensor, "out_scores": res.scores, "out_classes": res.pred_classes,
+           "out_masks": res.pred_masks}
+    # crop_and_resize: ground-truth bitmasks (filled ellipses) cropped by jittered boxes
+    k, gh, gw, ms = 9, 72, 104, 28
+    yy, xx = torch.meshgrid(torch.arange(gh, dtype=torch.float32), torch.arange(gw, dtype=torch.float32), indexing="ij")
+    cb = random_boxes(g, k, 70)
+    cb[:, 0::2] *= 1.4
+    bit = torch.zeros(k, gh, gw, dtype=torch.bool)
+    for i in range(k):
+        cx, cy = (cb[i, 0] + cb[i, 2]) / 2, (cb[i, 1] + cb[i, 3]) / 2
+        rx, ry = (cb[i, 2] - cb[i, 0]) / 2 + 0.5, (cb[i, 3] - cb[i, 1]) / 2 + 0.5
+        bit[i] = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0
+    crop_boxes = cb + torch.randn(k, 4, generator=g) * 2
+    out.update({"bit_masks": bit, "crop_boxes": crop_boxes,
+                "crops": BitMasks(bit).crop_and_resize(crop_boxes, ms), "mask_size": np.asarray(ms)})
+    save("postprocessing", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     gen_roi_align()
@@ -396,3 +436,4 @@ if __name__ == "__main__":
     gen_rpn_proposals()
     gen_fast_rcnn_inference()
     gen_retinanet_inference()
+    gen_postprocessing()

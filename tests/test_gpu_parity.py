@@ -739,3 +739,20 @@ def test_retinanet_inference_coco_size_vs_oracle():
         assert len(gs) == len(kept) == 100, (i, len(gs))
         assert (gs != s[kept]).sum().item() <= 2, i
         assert (gs[:-1] >= gs[1:]).all()
+
+
+# ------------------------------------------------------------------------------- mask targets / detector post-processing (8f-4)
+def test_detector_postprocess_and_crop_and_resize_golden(golden):
+    """Against the REAL detector_postprocess / BitMasks.crop_and_resize of the reference (fixture from make_golden.py)."""
+    from detectron2_b200 import postprocessing as pp
+    from detectron2_b200.fast_rcnn_inference import Detections
+    from test_host_logic_cpu import _postprocess_fixture, check_crops
+
+    d, h, w, oh, ow = _postprocess_fixture(golden)
+    det = Detections((h, w), T(d["boxes"]).to(DEV), T(d["scores"]).to(DEV), T(d["classes"]).to(DEV))
+    res = pp.detector_postprocess(det, oh, ow, 0.5, pred_masks=T(d["masks"]).to(DEV))
+    assert res.image_size == (oh, ow)
+    assert torch.allclose(res.pred_boxes.cpu(), T(d["out_boxes"]), rtol=0, atol=1e-4)
+    assert torch.equal(res.scores.cpu(), T(d["out_scores"])) and torch.equal(res.pred_classes.cpu(), T(d["out_classes"]))
+    assert res.pred_masks.dtype == torch.bool and (res.pred_masks.cpu() != T(d["out_masks"])).sum().item() <= 3
+    check_crops(d, pp.crop_and_resize(T(d["bit_masks"]).to(DEV), T(d["crop_boxes"]).to(DEV), int(d["mask_size"])))

@@ -121,3 +121,54 @@ def test_retinanet_inference_host_logic(golden, cpu_nms):
     for i, r in enumerate(res):
         assert len(r) >= max_det and torch.equal(r.scores[:max_det], T(d[f"out_scores{i}"]))
         assert (r.scores[:-1] >= r.scores[1:]).all()
+
+
+# ------------------------------------------------------------------------------- 8f-4: mask targets, detector post-processing
+class _OracleROIAlign:
+    """Stand-in for layers.ROIAlign on CPU tensors (the product op has no CPU path)."""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio, aligned=True):
+        self.a = (output_size, spatial_scale, sampling_ratio, aligned)
+
+    def forward(self, x, rois):
+        (ph, pw), scale, sr, aligned = self.a
+        return orc.roi_align_forward(x, rois, scale, ph, pw, sr, aligned)
+
+
+def _postprocess_fixture(golden):
+    d = golden("postprocessing")
+    h, w, oh, ow = [int(v) for v in d["hw"]]
+    return d, h, w, oh, ow
+
+
+def check_postprocess(d, res, oh, ow):
+    assert res.image_size == (oh, ow)
+    assert torch.equal(res.pred_boxes.cpu(), T(d["out_boxes"]))
+    assert torch.equal(res.scores.cpu(), T(d["out_scores"])) and torch.equal(res.pred_classes.cpu(), T(d["out_classes"]))
+    ref = T(d["out_masks"])
+    assert res.pred_masks.shape == ref.shape and res.pred_masks.dtype == torch.bool
+    # the reference pastes through grid_sample; pixels whose soft value sits within rounding of the threshold may differ
+    assert (res.pred_masks.cpu() != ref).sum().item() <= 3
+
+
+def check_crops(d, crops):
+    ref = T(d["crops"])
+    assert crops.shape == ref.shape and crops.dtype == torch.bool
+    # RoIAlign of a 0/1 mask produces exact halves (2 of 4 samples inside); `>= 0.5` there depends on the summation order
+    assert (crops.cpu() != ref).float().mean().item() <= 0.003
+
+
+def test_detector_postprocess_and_crop_host_logic(golden, monkeypatch):
+    from detectron2_b200 import postprocessing as pp
+    from detectron2_b200.fast_rcnn_inference import Detections
+
+    monkeypatch.setattr(pp, "paste_masks_in_image", lambda m, b, hw, threshold=0.5: orc.paste_masks(m, b, hw, threshold))
+    monkeypatch.setattr(pp, "ROIAlign", _OracleROIAlign)
+    d, h, w, oh, ow = _postprocess_fixture(golden)
+    det = Detections((h, w), T(d["boxes"]), T(d["scores"]), T(d["classes"]))
+    res = pp.detector_postprocess(det, oh, ow, 0.5, pred_masks=T(d["masks"]))
+    check_postprocess(d, res, oh, ow)
+    assert torch.equal(det.pred_boxes, T(d["boxes"]))  # the input record is not modified
+    nomask = pp.detector_postprocess(det, oh, ow)
+    assert nomask.pred_masks is None and torch.equal(nomask.pred_boxes, T(d["out_boxes"]))
+    check_crops(d, pp.crop_and_resize(T(d["bit_masks"]), T(d["crop_boxes"]), int(d["mask_size"])))
