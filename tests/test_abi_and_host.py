@@ -139,3 +139,15 @@ def test_pooler_layout_policy_host_logic(monkeypatch):
     assert ops._pick_layout(nchw, 1) == "xpose"
     with pytest.raises(NotImplementedError):                       # no CPU fallback for the layout change either
         ops.pyramid_to_channels_last(nchw)
+
+
+def test_roi_pooler_no_images():  # /root/reference/tests/modeling/test_roi_pooler.py:107-115
+    from detectron2_b200.poolers import ROIPooler
+
+    feature = torch.rand(0, 32, 32, 32) - 0.5
+    pooler = ROIPooler(output_size=14, scales=(1.0,), sampling_ratio=0.0, pooler_type="ROIAlignV2")
+    assert pooler.forward([feature], []).shape == (0, 32, 14, 14)
+    with pytest.raises(ValueError):
+        ROIPooler(output_size=7, scales=(0.25,), sampling_ratio=0, pooler_type="ROIPool")
+    with pytest.raises(AssertionError):  # scales that do not form a pyramid (poolers.py:186-190)
+        ROIPooler(output_size=7, scales=(0.25, 0.0625), sampling_ratio=0, pooler_type="ROIAlignV2")

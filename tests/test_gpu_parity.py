@@ -756,3 +756,26 @@ def test_detector_postprocess_and_crop_and_resize_golden(golden):
     assert torch.equal(res.scores.cpu(), T(d["out_scores"])) and torch.equal(res.pred_classes.cpu(), T(d["out_classes"]))
     assert res.pred_masks.dtype == torch.bool and (res.pred_masks.cpu() != T(d["out_masks"])).sum().item() <= 3
     check_crops(d, pp.crop_and_resize(T(d["bit_masks"]).to(DEV), T(d["crop_boxes"]).to(DEV), int(d["mask_size"])))
+
+
+def test_roialignv2_roialignrotated_match():
+    # /root/reference/tests/modeling/test_roi_pooler.py:14-59: a ROIAlignV2 pooler and a ROIAlignRotated pooler agree on
+    # axis-aligned boxes (angle 0)
+    from detectron2_b200.poolers import ROIPooler
+
+    g = torch.Generator().manual_seed(0)
+    n, c, h, w, n_rois = 2, 4, 10, 8, 10
+    feature = ((torch.rand(n, c, h, w, generator=g) - 0.5) * 2 * 11).to(DEV)
+    rois, rois_rotated = [], []
+    for _ in range(n):
+        b = torch.rand(n_rois, 4, generator=g) * (w * 16 * 0.5)
+        b[:, 2:] += w * 16 * 0.5
+        r = torch.zeros(n_rois, 5)
+        r[:, 0], r[:, 1] = (b[:, 0] + b[:, 2]) / 2.0, (b[:, 1] + b[:, 3]) / 2.0
+        r[:, 2], r[:, 3] = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+        rois.append(b.to(DEV))
+        rois_rotated.append(r.to(DEV))
+    v2 = ROIPooler(output_size=14, scales=(1.0 / 16,), sampling_ratio=0, pooler_type="ROIAlignV2")([feature], rois)
+    rot = ROIPooler(output_size=14, scales=(1.0 / 16,), sampling_ratio=0, pooler_type="ROIAlignRotated")([feature], rois_rotated)
+    assert v2.shape == rot.shape == (n * n_rois, c, 14, 14)
+    assert torch.allclose(v2, rot, atol=1e-4)
