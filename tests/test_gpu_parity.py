@@ -737,7 +737,8 @@ def test_retinanet_inference_coco_size_vs_oracle():
         kept = orc.batched_nms(b, s, c, 0.5)[:100]
         gs = res[i].scores.cpu()
         assert len(gs) == len(kept) == 100, (i, len(gs))
-        assert (gs != s[kept]).sum().item() <= 2, i
+        missing = len(set(gs.tolist()) ^ set(s[kept].tolist()))  # a flipped decision shifts the list: compare as sets
+        assert missing <= 4, (i, missing)
         assert (gs[:-1] >= gs[1:]).all()
 
 
