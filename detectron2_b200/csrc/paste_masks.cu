@@ -1,10 +1,10 @@
 // paste_masks_in_image for sm_100a -- one fused kernel instead of the reference's
 // meshgrid + grid_sample + compare + copy chain (detectron2/layers/mask_ops.py:17-69,74-147).
 //
-// HBM-bound byte kernel: the output (N*H*W bytes) dominates; each thread produces 16 consecutive output
-// bytes and stores them with one 128-bit st.global.  The 28x28 soft mask of the current instance is staged in
-// shared memory once per CTA.  Pixels whose sample point falls outside the mask support are written as 0
-// without touching the mask (most of the image).
+// HBM-bound byte kernel: the output (N*H*W bytes) dominates.  Most of every plane cannot see its mask and is written
+// as the constant "outside" value with 128-bit stores; only the box's (conservative) rectangle is evaluated, from
+// per-column / per-row sample coordinates tabulated in shared memory next to the 28x28 soft mask.  CTAs are handed to
+// the masks in proportion to their work (paste_assign), because box areas differ by two orders of magnitude.
 //
 // Arithmetic mirrors the reference expression order (no FMA contraction: this file is compiled with -fmad=false):
 //   g  = ((p + 0.5 - b0) / (b1 - b0)) * 2 - 1          (mask_ops.py:53-54)
@@ -124,7 +124,7 @@ __device__ __forceinline__ void paste_assign(const float* __restrict__ boxes, in
   count = s_asg[2];
 }
 
-// grid (gx, N).  Two phases per mask:
+// grid: 1-D balanced launch (paste_assign) or (CTAs per mask, N).  Two phases per mask:
 //   1. every 16-byte chunk of the output plane that cannot see the mask (conservative rectangle test) is written as
 //      one 128-bit store of the "outside" value -- this is ~90% of the bytes and runs at store bandwidth;
 //   2. the rows/columns of the conservative rectangle, widened to whole 16-byte chunks, are evaluated exactly.  The sample
