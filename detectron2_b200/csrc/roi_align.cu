@@ -4,7 +4,10 @@
 // torchvision/ops/roi_align.py::_roi_align) and detectron2/layers/csrc/ROIAlignRotated/ROIAlignRotated_cuda.cu:143-323.
 //
 // Design (differs from the reference's one-thread-per-output grid-stride loop):
-//   * axis-aligned forward AND backward: roi_align_v3_kernel<BWD> below -- per-RoI separable tap lists built once per CTA,
+//   * axis-aligned forward on channels-last storage: roi_align_nhwc_kernel -- lane = 4 channels, a warp reads a tap pixel's
+//     128 channels as one 512-byte request with warp-uniform tap index / weight, 8 loads in flight; used in place for
+//     torch.channels_last inputs, or after nchw_to_nhwc_kernel (one launch for a whole pyramid) when that pays;
+//   * axis-aligned forward (NCHW) AND backward: roi_align_v3_kernel<BWD> -- per-RoI separable tap lists built once per CTA,
 //     every warp stages (forward) or accumulates (backward) the RoI's pixel footprint of 4 channel planes in its private
 //     shared-memory slice, lane == bin, no CTA barrier in the channel loop; the FPN level of a RoI is picked in-kernel so
 //     that a whole multi-level ROIPooler call is one launch;
