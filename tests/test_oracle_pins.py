@@ -283,3 +283,62 @@ def test_golden_rpn_proposals(golden):
     res = proposals_ref.find_top_rpn_proposals(props, logits, sizes, thr, pre, post, mbs, False)
     for i, (b, s) in enumerate(res):
         assert torch.equal(b, T(d[f"boxes_img{i}"])) and torch.equal(s, T(d[f"scores_img{i}"])), i
+
+
+# ---------------------------------------------------------------- 4. randomized sweeps (oracle vs torchvision / compiled reference)
+@pytest.mark.parametrize("seed", range(6))
+def test_sweep_roi_align_fwd_bwd_vs_torchvision(seed):
+    tv = pytest.importorskip("torchvision")
+    g = torch.Generator().manual_seed(1000 + seed)
+    n, c = int(torch.randint(1, 4, (1,), generator=g)), int(torch.randint(1, 9, (1,), generator=g))
+    h, w = int(torch.randint(5, 40, (1,), generator=g)), int(torch.randint(5, 40, (1,), generator=g))
+    ph, pw = int(torch.randint(1, 9, (1,), generator=g)), int(torch.randint(1, 9, (1,), generator=g))
+    sr, aligned = int(torch.randint(0, 4, (1,), generator=g)), bool(seed % 2)
+    scale = [1.0, 0.5, 0.25][seed % 3]
+    k = 23
+    ctr = torch.rand(k, 2, generator=g) * torch.tensor([w / scale, h / scale])
+    wh = torch.rand(k, 2, generator=g) * torch.tensor([w / scale, h / scale]) * 0.8
+    rois = torch.cat([torch.randint(0, n, (k, 1), generator=g).float(), ctr - wh / 2, ctr + wh / 2], 1)
+    rois[0, 1:] = torch.tensor([-30.0, -20.0, 2 * w / scale, 2 * h / scale])  # far larger than the map
+    x = torch.randn(n, c, h, w, generator=g).requires_grad_(True)
+    ref = tv.ops.roi_align(x, rois, (ph, pw), scale, sr, aligned)
+    got = orc.roi_align_forward(x.detach(), rois, scale, ph, pw, sr, aligned)
+    assert torch.allclose(got, ref.detach(), rtol=1e-4, atol=1e-5), (got - ref.detach()).abs().max()
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    gx = orc.roi_align_backward(go, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    assert torch.allclose(gx, x.grad, rtol=1e-4, atol=1e-4), (gx - x.grad).abs().max()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sweep_batched_nms_vs_torchvision(seed):
+    tv = pytest.importorskip("torchvision")
+    g = torch.Generator().manual_seed(2000 + seed)
+    m, ncls = [17, 300, 999, 64][seed], [1, 3, 20, 64][seed]
+    base = torch.rand(max(m // 6, 1), 4, generator=g) * 200
+    base[:, 2:] = base[:, :2] + 5 + torch.rand(base.shape[0], 2, generator=g) * 80
+    boxes = base[torch.randint(0, base.shape[0], (m,), generator=g)] + torch.randn(m, 4, generator=g) * 3
+    boxes[:, 2:] = torch.maximum(boxes[:, 2:], boxes[:, :2] + 1)
+    boxes.clamp_(min=0)  # detectron2 call sites clip first (batched NMS note)
+    scores = torch.rand(m, generator=g)
+    idxs = torch.randint(0, ncls, (m,), generator=g)
+    for thr in (0.3, 0.6):
+        assert torch.equal(orc.batched_nms(boxes, scores, idxs, thr), tv.ops.batched_nms(boxes, scores, idxs, thr))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_sweep_roi_align_rotated_vs_compiled_reference(seed):
+    if not orc.load_reference():
+        pytest.skip("oracle/_ref not available")
+    g = torch.Generator().manual_seed(3000 + seed)
+    n, c, h, w = 2, 3 + seed, 17 + 5 * seed, 23
+    ph, pw, sr = [(7, 7, 0), (3, 5, 2), (2, 2, 3)][seed]
+    k = 19
+    rois = torch.cat([torch.randint(0, n, (k, 1), generator=g).float(), torch.rand(k, 2, generator=g) * torch.tensor([w * 4.0, h * 4.0]),
+                      2 + torch.rand(k, 2, generator=g) * 50, (torch.rand(k, 1, generator=g) - 0.5) * 360], 1)
+    x = torch.randn(n, c, h, w, generator=g)
+    ref = torch.ops.detectron2.roi_align_rotated_forward(x, rois, 0.25, ph, pw, sr)
+    assert torch.allclose(orc.roi_align_rotated_forward(x, rois, 0.25, ph, pw, sr), ref, rtol=1e-4, atol=1e-5)
+    go = torch.randn(ref.shape, generator=g)
+    gref = torch.ops.detectron2.roi_align_rotated_backward(go, rois, 0.25, ph, pw, n, c, h, w, sr)
+    assert torch.allclose(orc.roi_align_rotated_backward(go, rois, 0.25, ph, pw, n, c, h, w, sr), gref, rtol=1e-4, atol=1e-4)
