@@ -23,6 +23,8 @@ class DcnParams(C.Structure):
 
 
 MAX_LEVELS = 8
+ABI_VERSION = 2  # include/d2b200.h D2B_ABI_VERSION
+DCN_X_NHWC = 1   # D2B_DCN_X_NHWC
 
 
 class Pyramid(C.Structure):
@@ -51,11 +53,12 @@ def _declare(lib):
         "d2b_nms_workspace_bytes": (sz, [i64, i]),
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64p, i64p, vp, sz, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
-        "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i]),
-        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, f32p, vp, sz, vp]),
-        "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams)]),
-        "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), f32p, f32p, f32p, f32p,
-                                         f32p, vp, sz, vp]),
+        "d2b_deform_conv_tc_shape_supported": (i, [C.POINTER(DcnParams), i]),
+        "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i]),
+        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, vp, sz, vp]),
+        "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i, i, i]),
+        "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, f32p, f32p,
+                                         f32p, f32p, vp, sz, vp]),
         "d2b_paste_masks": (i, [f32p, f32p, i, i, i, i, f, u8p, vp]),
     }
     for name, (res, args) in sig.items():
@@ -78,7 +81,7 @@ def lib():
                 "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for these ops." % LIB_PATH)
         l = C.CDLL(LIB_PATH)
         EXPORTED = _declare(l)
-        if l.d2b_abi_version() != 1:
+        if l.d2b_abi_version() != ABI_VERSION:
             raise RuntimeError("libd2b200.so ABI version mismatch")
         _lib = l
     return _lib

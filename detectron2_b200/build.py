@@ -38,7 +38,8 @@ def _stale(target, deps):
 def _compile(name, extra, force):
     src = os.path.join(CSRC, name)
     obj = os.path.join(OBJ, name.replace(".cu", ".o"))
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "d2b200.h"), __file__]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
+            os.path.join(HERE, "..", "include", "d2b200.h"), __file__]
     if force or _stale(obj, deps):
         cmd = [NVCC] + ARCH + COMMON + extra + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -15,8 +15,8 @@
 // pixel): they are computed once per CTA tile into shared memory and reused by every channel, where the reference
 // recomputes them per channel (deform_conv_cuda_kernel.cu:238-287).
 //
-// The tcgen05 (bf16 / bf16x3) forward lives in deform_conv_tc.cu; this file is the fp32 FFMA path used for parity
-// (<= 1e-4 rel) and for shapes the tensor-core kernel does not take.
+// The tcgen05 (bf16 / bf16x3) forward and backward live in deform_conv_tc.cu; this file is the fp32 FFMA path used for
+// parity (<= 1e-4 rel) and for shapes the tensor-core kernels do not take, plus the public entry points that pick one.
 #include "common.cuh"
 
 namespace {
@@ -372,22 +372,32 @@ __global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float* __restr
 
 }  // namespace
 
-int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                               const float* bias, const d2b_dcn_params* p, int precision, float* out, void* workspace,
-                               size_t workspace_bytes, void* stream);
 int d2b_deform_conv_tc_supported(const d2b_dcn_params* p);
-size_t d2b_deform_conv_tc_workspace_bytes(const d2b_dcn_params* p);
+int d2b_deform_conv_tc_bwd_supported(const d2b_dcn_params* p);
+size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc);
+int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
+                               const float* bias, const d2b_dcn_params* p, int precision, int x_nhwc, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int need_data, int need_weight);
+int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
+                                const float* grad_out, const d2b_dcn_params* p, int precision, int x_nhwc,
+                                float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
-// precision: 0 = fp32 FFMA, 1 = bf16x3 on tcgen05, 2 = bf16 on tcgen05, -1 = auto (1 when the tensor-core kernel takes
+// precision: 0 = fp32 FFMA, 1 = bf16x3 on tcgen05, 2 = bf16 on tcgen05, -1 = auto (1 when the tensor-core kernels take
 // the shape, else 0 -- both are fp32-class, so "auto" never lowers accuracy)
-D2B_API size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision) {
+D2B_API int d2b_deform_conv_tc_shape_supported(const d2b_dcn_params* p, int backward) {
+  return backward ? d2b_deform_conv_tc_bwd_supported(p) : d2b_deform_conv_tc_supported(p);
+}
+
+D2B_API size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags) {
   if (precision == 0) return 0;
   if (precision == -1 && !d2b_deform_conv_tc_supported(p)) return 0;
-  return d2b_deform_conv_tc_workspace_bytes(p);
+  return d2b_deform_conv_tc_fwd_workspace(p, (flags & D2B_DCN_X_NHWC) ? 1 : 0);
 }
 
 D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask, const float* weight,
-                                    const float* bias, const d2b_dcn_params* p, int precision, float* out,
+                                    const float* bias, const d2b_dcn_params* p, int precision, int flags, float* out,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
@@ -396,36 +406,51 @@ D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const f
   if (precision < -1 || precision > 2) return D2B_EINVAL;
   if (precision == -1) precision = d2b_deform_conv_tc_supported(p) ? 1 : 0;
   if (precision != 0)  // no silent precision / path change: an unsupported shape is reported, not rerouted
-    return d2b_deform_conv_forward_tc(x, offset, mask, weight, bias, p, precision, out, workspace, workspace_bytes, stream);
+    return d2b_deform_conv_forward_tc(x, offset, mask, weight, bias, p, precision, (flags & D2B_DCN_X_NHWC) ? 1 : 0, out,
+                                      workspace, workspace_bytes, stream);
+  if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;  // the FFMA parity path reads NCHW planes
   dim3 grid(d2b_cdiv(d.HoWo, BN), d2b_cdiv(d.opg, BM), d.N * d.G);
   dcn_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, offset, mask, weight, bias, d, out);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
 
-D2B_API size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p) {
-  (void)p;
-  return 0;  // grad_columns are never materialised
+D2B_API size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags, int need_data,
+                                                        int need_weight) {
+  if (precision == 0) return 0;  // the FFMA path never materialises grad_columns
+  if (precision == -1 && !d2b_deform_conv_tc_bwd_supported(p)) return 0;
+  return d2b_deform_conv_tc_bwd_workspace(p, (flags & D2B_DCN_X_NHWC) ? 1 : 0, need_data, need_weight);
 }
 
 D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const float* mask, const float* weight,
-                                     const float* grad_out, const d2b_dcn_params* p, float* grad_x,
-                                     float* grad_offset, float* grad_mask, float* grad_weight, float* grad_bias,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
-  (void)workspace;
-  (void)workspace_bytes;
+                                     const float* grad_out, const d2b_dcn_params* p, int precision, int flags,
+                                     float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
+                                     float* grad_bias, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
+  if (precision < -1 || precision > 2) return D2B_EINVAL;
+  if (precision == -1) precision = d2b_deform_conv_tc_bwd_supported(p) ? 1 : 0;
+  if (d.N > 0 && (!x || !offset || !weight || !grad_out)) return D2B_EINVAL;
+  if (grad_bias) {
+    if (d.N == 0) {
+      D2B_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d.Cout * 4, stream));
+    } else {
+      dcn_bias_grad_kernel<<<d.Cout, 256, 0, stream>>>(grad_out, d.N, d.Cout, d.HoWo, grad_bias);
+      D2B_CHECK_LAUNCH();
+    }
+  }
+  if (precision != 0)
+    return d2b_deform_conv_backward_tc(x, offset, mask, weight, grad_out, p, precision, (flags & D2B_DCN_X_NHWC) ? 1 : 0,
+                                       grad_x, grad_offset, grad_mask, grad_weight, workspace, workspace_bytes, stream_);
+  if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;
   const size_t nx = (size_t)d.N * d.Cin * d.H * d.W, noff = (size_t)d.N * d.DG * 2 * d.KK * d.HoWo;
   const size_t nm = (size_t)d.N * d.DG * d.KK * d.HoWo, nw = (size_t)d.Cout * d.cpg * d.KK;
   if (grad_x && nx) D2B_CUDA(cudaMemsetAsync(grad_x, 0, nx * 4, stream));
   if (grad_offset && noff) D2B_CUDA(cudaMemsetAsync(grad_offset, 0, noff * 4, stream));
   if (grad_mask && nm) D2B_CUDA(cudaMemsetAsync(grad_mask, 0, nm * 4, stream));
   if (grad_weight) D2B_CUDA(cudaMemsetAsync(grad_weight, 0, nw * 4, stream));
-  if (grad_bias) D2B_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d.Cout * 4, stream));
   if (d.N == 0) return D2B_OK;
-  if (!x || !offset || !weight || !grad_out) return D2B_EINVAL;
   if (grad_x || grad_offset || grad_mask) {
     // few pixel tiles (small maps) -> split the channel chunks over blockIdx.y so that the grid still fills 148 SMs;
     // grad_offset / grad_mask partial sums meet through the atomics the kernel already uses
@@ -452,10 +477,6 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
     dim3 grid(splits, n_mtile * n_ctile, d.G);
     dcn_bwd_weight_kernel<<<grid, kThreads, 0, stream>>>(x, offset, mask, grad_out, d, tiles_per_cta, n_ctile,
                                                          grad_weight);
-    D2B_CHECK_LAUNCH();
-  }
-  if (grad_bias) {
-    dcn_bias_grad_kernel<<<d.Cout, 256, 0, stream>>>(grad_out, d.N, d.Cout, d.HoWo, grad_bias);
     D2B_CHECK_LAUNCH();
   }
   return D2B_OK;

@@ -1,323 +1,63 @@
-// Deformable convolution forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Deformable convolution v1/v2 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a: forward, backward-data
+// and backward-weight.  Replaces detectron2/layers/csrc/deformable/deform_conv_cuda.cu:272-444 (forward),
+// :446-642 / :985-1221 (backward input + offset + mask) and :644-824 (backward filter).
 //
-// The reference materialises columns[Cin*kh*kw, Ho*Wo] with a gather kernel and then calls cuBLAS per group
-// (detectron2/layers/csrc/deformable/deform_conv_cuda.cu:382-431).  Here the gathered operand never exists in HBM:
+// The reference materialises columns[Cin*kh*kw, Ho*Wo] in HBM with a gather kernel and calls cuBLAS per group; its
+// backward materialises grad_columns, runs col2im / col2im_coord over them and re-runs im2col for the filter gradient.
+// Here no column buffer exists: every kernel is an implicit GEMM on tcgen05 whose gathered operand is produced (or whose
+// result is consumed) on the SM, with the operands that are plain matrices pre-tiled once into the UMMA shared-memory
+// image so that ONE linear TMA copy (cp.async.bulk) brings a whole operand tile.
 //
-//   D[pixel, oc] = sum_k' A[pixel, k'] * B[oc, k']        k' = kp * (Cin/G) + c   (kernel-point major: the bilinear taps of
-//                                                          a (pixel, kernel point) are computed once and reused by 64 channels)
+//   K1 forward      D[128 px, oc]   = col[128 px, k'] . W[oc, k']^T        A = gather (K-major), B = weight tiles (TMA)
+//   K2 bwd data     gcol[128 px,k'] = gout[128 px, oc] . W[oc, k']          A = gout tiles (TMA), B = W^T tiles (TMA);
+//                   epilogue: gcol -> red.global.add.v4 into grad_x (NHWC), grad_offset, grad_mask
+//   K3 bwd weight   gW[k', oc]      = col^T[k', px] . gout[px, oc]          A = gather (MN-major), B = gout tiles (TMA)
 //
-//   * MMA M = 128 output pixels (TMEM lanes), N = up to 128 output channels of the group (TMEM columns), K step 16 (bf16).
-//   * A tile [128 x 64] bf16, K-major, 128-byte swizzle: written by the four GATHER warps (one thread per pixel row)
-//     straight into the UMMA shared-memory layout -- bilinear gather -> registers -> st.shared.v4, then
-//     fence.proxy.async + mbarrier arrive.
-//   * B tile [N x 64] bf16, K-major, 128-byte swizzle: a loader warp copies it from a pre-converted bf16 weight copy.
-//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, fp32 accumulate in TMEM); tcgen05.commit releases the
-//     smem stage to the producers (3-stage mbarrier ring) and finally signals the epilogue.
-//   * epilogue: the gather warps read their 32 TMEM lanes with tcgen05.ld (32x32b.x16) and store NCHW output, one
-//     coalesced 128-byte warp store per output channel (+ bias).
+// Layout decisions
+//   * x is gathered from channels-last storage [N,H,W,C] fp32: the 64 channels of a tap are 256 contiguous bytes, a
+//     half-warp reads them as 16 x LDG.128, a warp keeps 8 such loads in flight per lane.  NCHW inputs are re-laid out once
+//     per call by nchw_to_nhwc_kernel (roi_align.cu); channels_last inputs are used in place.
+//   * k' is ordered (kernel point, 64-channel block): one "unit" = 64 k' = one 128-byte swizzle row of bf16, so the
+//     bilinear taps of a (pixel, kernel point) are computed once (tap table in shared memory) and reused by all channels.
+//   * grouped convolutions with fewer than 64 channels per group are packed into "super-groups" of 64 input channels
+//     with block-diagonal (zero-padded) weight tiles: the gather stays 256 bytes per tap and the wasted MMA flops are free.
+//   * precision 1 ("bf16x3"): operands are split x = hi + lo (two bf16) and hi*hi + hi*lo + lo*hi is accumulated in fp32 --
+//     fp32-class accuracy (<= 1e-4 rel) at a third of the bf16 tensor peak.  precision 2: plain bf16 operands.
 //
-// precision 1 ("bf16x3"): operands are split x = hi + lo (two bf16) and three MMAs hi*hi + hi*lo + lo*hi are accumulated,
-// which keeps ~16 mantissa bits per product -- fp32-class accuracy (<= 1e-4 rel) at 1/3 of the bf16 tensor peak.
-// precision 2: plain bf16 operands (autocast-style), one MMA.
-//
-// Shapes taken: (Cin/G) % 64 == 0, (Cin/DG) % 64 == 0, (Cout/G) % 16 == 0.  Anything else returns D2B_EUNSUPPORTED
-// (the fp32 FFMA kernel in deform_conv.cu covers it).
-#include <cuda_bf16.h>
+// Warp roles (576 threads, one CTA per SM): warps 0-15 gather / scatter / epilogue, warp 16 TMA producer (one lane),
+// warp 17 MMA issuer (one lane) and TMEM owner.
+#include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace d2b_tc;
 
 namespace {
 
-constexpr int BM = 128;      // pixels per tile  (UMMA M)
-constexpr int BNMAX = 128;   // output channels per tile (UMMA N), multiple of 16
-constexpr int BK = 64;       // k' per stage: 64 bf16 = one 128-byte swizzle row
-constexpr int kStages = 3;
-constexpr int kGatherThreads = 128;
-constexpr int kThreads = 192;  // warps 0-3 gather + epilogue, warp 4 weight loader, warp 5 MMA issuer / TMEM owner
-constexpr int kTileBytesA = BM * BK * 2;      // 16 KB
-constexpr int kTileBytesB = BNMAX * BK * 2;   // 16 KB
-constexpr int kStageBytes = 2 * kTileBytesA + 2 * kTileBytesB;  // hi + lo of A and B: 64 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kTmemCols = 128;
+constexpr int kWorkerWarps = 16;
+constexpr int kWorkers = kWorkerWarps * 32;  // 512
+constexpr int kThreads = kWorkers + 64;      // + producer warp + MMA warp
+constexpr int kTile = 16384;                 // [128 rows][128 B]
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kGcolPitch = 132;              // floats per pixel row of the drained gcol tile (128 + 4: conflict-free float4)
 
-struct TcDims {
-  int N, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, G, DG, Ho, Wo, cpg, opg, cpdg, KK, HoWo, K;
+struct TC {
+  int N, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, G, DG, Ho, Wo, cpg, opg, cpdg, KK, HoWo;
+  int pack, SG, cps, ops, cbs, U;  // super-groups: cps input / ops output channels each, cbs 64-channel blocks, U units
+  int tiles_img;                   // 128-pixel tiles per image
+  int stages_img;                  // 64-pixel stages per image (K3)
+  int MC;                          // macro-chunks (pairs of units) per super-group
+  int nks;                         // 64-wide K stages over the super-group's output channels (K2)
 };
 
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct K1P { int BN, noct, gspan, nkp, ksplit, S, tap_bytes, stage_bytes, red; };  // red: k-split partial sums meet through red.add
+struct K2P { int mper, msplit, tap_bytes; };
+struct K3P { int BN, noct, sper, nsplit, S, stage_bytes; };
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, 8-row atoms 1024 B apart (SBO), version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                              // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;         // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                              // descriptor version
-  d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
-  return d;
-}
-
-// D[tmem] (+)= A[smem] * B[smem];  issued by one thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// ------------------------------------------------------------------------------------------------ weight pre-pass
-// w fp32 [Cout][cpg][KK]  ->  bf16 hi / lo [Cout][KK][cpg]   (k' = kp * cpg + c)
-__global__ void dcn_weight_split_kernel(const float* __restrict__ w, int Cout, int cpg, int KK,
-                                        __nv_bfloat16* __restrict__ whi, __nv_bfloat16* __restrict__ wlo) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = Cout * cpg * KK;
-  if (i >= total) return;
-  const int c = i % cpg, kp = (i / cpg) % KK, oc = i / (cpg * KK);
-  const float v = w[((size_t)oc * cpg + c) * KK + kp];
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  whi[i] = h;
-  wlo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-
-// ------------------------------------------------------------------------------------------------ main kernel
-// grid (pixel tiles, oc tiles, N*G)
-__global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __restrict__ x,
-                                                                 const float* __restrict__ offset,
-                                                                 const float* __restrict__ mask,
-                                                                 const __nv_bfloat16* __restrict__ whi,
-                                                                 const __nv_bfloat16* __restrict__ wlo,
-                                                                 const float* __restrict__ bias, TcDims d, int split,
-                                                                 float* __restrict__ out) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full_bar = bars;                 // [kStages]  producers -> MMA
-  uint64_t* empty_bar = bars + kStages;      // [kStages]  MMA -> producers
-  uint64_t* accum_bar = bars + 2 * kStages;  // MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int p0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BNMAX;
-  const int b = blockIdx.z / d.G, g = blockIdx.z - b * d.G;
-  const int bn = min(BNMAX, d.opg - n0);  // multiple of 16
-  const int nchunk = d.K / BK;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], kGatherThreads + 32);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(accum_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 5) {  // TMEM allocation by one full warp; the same warp frees it at the end
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    // =============================================================== GATHER producers (one pixel row per thread)
-    const int row = tid;  // 0..127
-    const int p = p0 + row;
-    const bool pix_ok = p < d.HoWo;
-    const int ho = pix_ok ? p / d.Wo : 0, wo = pix_ok ? p - (p / d.Wo) * d.Wo : 0;
-    const size_t plane = (size_t)d.H * d.W;
-    int cur_kp = -1, cur_dg = -1;
-    int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-    const uint32_t sw = (uint32_t)(row & 7);
-    for (int j = 0; j < nchunk; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (uint32_t)((j / kStages) & 1);
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const int k0 = j * BK;
-      const int kp = k0 / d.cpg, cl0 = k0 - kp * d.cpg;
-      const int c_first = g * d.cpg + cl0;
-      const int dg = c_first / d.cpdg;
-      if (kp != cur_kp || dg != cur_dg) {  // taps of (pixel, kernel point): deform_conv_cuda_kernel.cu:263-282, :96-130
-        cur_kp = kp;
-        cur_dg = dg;
-        q0 = q1 = q2 = q3 = -1;
-        w0 = w1 = w2 = w3 = 0.f;
-        if (pix_ok) {
-          const int ki = kp / d.kw, kj = kp - ki * d.kw;
-          const size_t ob = ((size_t)(b * d.DG + dg) * 2 * d.KK) * d.HoWo;
-          const float oh = __ldg(offset + ob + (size_t)(2 * kp) * d.HoWo + p);
-          const float ow = __ldg(offset + ob + (size_t)(2 * kp + 1) * d.HoWo + p);
-          const float hf = (float)(ho * d.sh - d.ph + ki * d.dh) + oh;
-          const float wf = (float)(wo * d.sw - d.pw + kj * d.dw) + ow;
-          const float m = mask ? __ldg(mask + ((size_t)(b * d.DG + dg) * d.KK + kp) * d.HoWo + p) : 1.f;
-          if (hf > -1.f && wf > -1.f && hf < (float)d.H && wf < (float)d.W) {
-            const int hl = (int)floorf(hf), wl = (int)floorf(wf);
-            const float lh = hf - (float)hl, lw = wf - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
-            const bool t0 = hl >= 0, t1 = hl + 1 <= d.H - 1, l0 = wl >= 0, l1 = wl + 1 <= d.W - 1;
-            if (t0 && l0) { q0 = hl * d.W + wl; w0 = hh * hw * m; }
-            if (t0 && l1) { q1 = hl * d.W + wl + 1; w1 = hh * lw * m; }
-            if (t1 && l0) { q2 = (hl + 1) * d.W + wl; w2 = lh * hw * m; }
-            if (t1 && l1) { q3 = (hl + 1) * d.W + wl + 1; w3 = lh * lw * m; }
-          }
-        }
-      }
-      uint8_t* a_hi = smem + s * kStageBytes;
-      uint8_t* a_lo = a_hi + kTileBytesA;
-      const float* __restrict__ xp = x + ((size_t)b * d.Cin + c_first) * plane;
-#pragma unroll 2
-      for (int c8 = 0; c8 < 8; ++c8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float* __restrict__ pl = xp + (size_t)(c8 * 8 + i) * plane;
-          float acc = 0.f;
-          if (q0 >= 0) acc = fmaf(w0, __ldg(pl + q0), acc);
-          if (q1 >= 0) acc = fmaf(w1, __ldg(pl + q1), acc);
-          if (q2 >= 0) acc = fmaf(w2, __ldg(pl + q2), acc);
-          if (q3 >= 0) acc = fmaf(w3, __ldg(pl + q3), acc);
-          v[i] = acc;
-        }
-        uint4 hi, lo;
-        {
-          __nv_bfloat16 h[8];
-          float r[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            h[i] = __float2bfloat16_rn(v[i]);
-            r[i] = v[i] - __bfloat162float(h[i]);
-          }
-          hi.x = pack_bf16(__bfloat162float(h[0]), __bfloat162float(h[1]));
-          hi.y = pack_bf16(__bfloat162float(h[2]), __bfloat162float(h[3]));
-          hi.z = pack_bf16(__bfloat162float(h[4]), __bfloat162float(h[5]));
-          hi.w = pack_bf16(__bfloat162float(h[6]), __bfloat162float(h[7]));
-          lo.x = pack_bf16(r[0], r[1]);
-          lo.y = pack_bf16(r[2], r[3]);
-          lo.z = pack_bf16(r[4], r[5]);
-          lo.w = pack_bf16(r[6], r[7]);
-        }
-        const uint32_t off = (uint32_t)row * 128u + (((uint32_t)c8 ^ sw) << 4);  // 128-byte swizzle: chunk ^= row % 8
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
-      }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[s]);
-    }
-    // =============================================================== EPILOGUE (TMEM -> registers -> NCHW global)
-    mbar_wait(accum_bar, 0u);
-    tc_fence_after();
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int col0 = 0; col0 < bn; col0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr_row + (uint32_t)col0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (pix_ok) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int oc = g * d.opg + n0 + col0 + i;
-          out[((size_t)b * d.Cout + oc) * d.HoWo + p] = __uint_as_float(r[i]) + (bias ? __ldg(bias + oc) : 0.f);
-        }
-      }
-    }
-  } else if (warp == 4) {
-    // =============================================================== WEIGHT loader (B tiles)
-    for (int j = 0; j < nchunk; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (uint32_t)((j / kStages) & 1);
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      uint8_t* b_hi = smem + s * kStageBytes + 2 * kTileBytesA;
-      uint8_t* b_lo = b_hi + kTileBytesB;
-      const size_t src0 = ((size_t)(g * d.opg + n0)) * d.K + (size_t)j * BK;
-      const int c = lane & 7;
-      for (int r = lane >> 3; r < bn; r += 4) {
-        const size_t src = src0 + (size_t)r * d.K + c * 8;
-        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ (uint32_t)(r & 7)) << 4);
-        *reinterpret_cast<uint4*>(b_hi + off) = __ldg(reinterpret_cast<const uint4*>(whi + src));
-        if (split) *reinterpret_cast<uint4*>(b_lo + off) = __ldg(reinterpret_cast<const uint4*>(wlo + src));
-      }
-      fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
-    }
-  } else {
-    // =============================================================== MMA issuer (warp 5, one elected lane)
-    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = bn, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    for (int j = 0; j < nchunk; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (uint32_t)((j / kStages) & 1);
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_hi = smem_u32(smem + s * kStageBytes);
-        const uint32_t a_lo = a_hi + kTileBytesA;
-        const uint32_t b_hi = a_hi + 2 * kTileBytesA;
-        const uint32_t b_lo = b_hi + kTileBytesB;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 = 32 bytes along K inside the swizzled row
-          umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, (j > 0 || k > 0) ? 1u : 0u);
-          if (split) {
-            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
-            umma_bf16(tmem_base, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, 1u);
-          }
-        }
-        umma_commit(&empty_bar[s]);                    // frees the smem stage once these MMAs have read it
-        if (j == nchunk - 1) umma_commit(accum_bar);   // accumulator complete -> epilogue
-      }
-      __syncwarp();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-  }
-}
-
-bool make_tc_dims(const d2b_dcn_params* p, TcDims& d) {
+bool make_tc(const d2b_dcn_params* p, TC& d) {
   if (!p) return false;
   d.N = p->N; d.Cin = p->Cin; d.H = p->H; d.W = p->W; d.Cout = p->Cout; d.kh = p->kh; d.kw = p->kw;
   d.sh = p->stride_h; d.sw = p->stride_w; d.ph = p->pad_h; d.pw = p->pad_w; d.dh = p->dil_h; d.dw = p->dil_w;
@@ -330,46 +70,1045 @@ bool make_tc_dims(const d2b_dcn_params* p, TcDims& d) {
   d.Wo = (d.W + 2 * d.pw - (d.dw * (d.kw - 1) + 1)) / d.sw + 1;
   if (d.Ho <= 0 || d.Wo <= 0) return false;
   d.cpg = d.Cin / d.G; d.opg = d.Cout / d.G; d.cpdg = d.Cin / d.DG; d.KK = d.kh * d.kw; d.HoWo = d.Ho * d.Wo;
-  d.K = d.cpg * d.KK;
+  // ---- shapes the tensor-core kernels take
+  if (d.cpg >= 64) {
+    if (d.cpg % 64) return false;
+    d.pack = 1;
+  } else {
+    if (d.cpg != 16 && d.cpg != 32) return false;
+    d.pack = 64 / d.cpg;
+    if (d.G % d.pack) return false;
+  }
+  if (d.cpdg % 64) return false;  // a 64-channel block never straddles deformable groups
+  d.SG = d.G / d.pack; d.cps = d.cpg * d.pack; d.ops = d.opg * d.pack; d.cbs = d.cps / 64; d.U = d.KK * d.cbs;
+  if (d.ops % 16) return false;
+  if (d.KK > 49) return false;
+  if ((long long)d.H * d.W * d.Cin >= (1LL << 29)) return false;  // 32-bit byte offsets inside one image
+  if ((long long)d.HoWo * d.Cout >= (1LL << 31) || (long long)d.Cout * d.cpg * d.KK >= (1LL << 31)) return false;
+  d.tiles_img = d2b_cdiv(d.HoWo, 128);
+  d.stages_img = d2b_cdiv(d.HoWo, 64);
+  d.MC = (d.U + 1) / 2;
+  d.nks = d.ops / 64;
+  if ((long long)d.N * d.tiles_img > 0x7fffffffLL) return false;
   return true;
+}
+
+int largest_tile(int n) {  // largest of {256,...,16} dividing n
+  for (int t = 256; t >= 16; t >>= 1)
+    if (n % t == 0) return t;
+  return 0;
+}
+
+int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+bool plan_k1(const TC& d, K1P& k) {
+  if (d.ops <= 256) {
+    k.BN = d.ops; k.noct = 1;
+    k.gspan = std::max(1, std::min(d.SG, 256 / d.ops));
+    while (d.SG % k.gspan) --k.gspan;
+  } else {
+    k.BN = largest_tile(d.ops); k.noct = d.ops / k.BN; k.gspan = 1;
+  }
+  if (k.BN < 16) return false;
+  const int base = d.N * d.tiles_img * (d.SG / k.gspan) * k.noct;
+  k.ksplit = 1;
+  if (base < 100) k.ksplit = std::min(d.KK, d2b_cdiv(kNumSMs, base));
+  k.nkp = d2b_cdiv(d.KK, k.ksplit);
+  k.ksplit = d2b_cdiv(d.KK, k.nkp);
+  k.red = k.ksplit > 1;
+  const int ndg = d.DG == 1 ? 1 : std::min(d.DG, d2b_cdiv(k.gspan * d.cps, d.cpdg) + 1);
+  k.tap_bytes = ndg * k.nkp * 128 * 16;
+  k.stage_bytes = 2 * kTile + 2 * k.BN * 128;
+  k.S = 3;
+  while (k.S > 1 && k.S * k.stage_bytes + k.tap_bytes + 1024 + 256 > kMaxSmem) --k.S;
+  return k.S >= 2;
+}
+
+bool plan_k2(const TC& d, K2P& k) {
+  if (d.ops % 64) return false;
+  const int base = d.N * d.tiles_img * d.SG;
+  k.msplit = 1;
+  if (base < 100) k.msplit = std::min(d.MC, d2b_cdiv(kNumSMs, base));
+  k.mper = d2b_cdiv(d.MC, k.msplit);
+  k.msplit = d2b_cdiv(d.MC, k.mper);
+  const int nkp = std::min(d.KK, (2 * k.mper + d.cbs - 1) / d.cbs + 1);
+  const int ndg = d.DG == 1 ? 1 : std::min(d.DG, d2b_cdiv(d.cps, d.cpdg) + 1);
+  k.tap_bytes = ndg * nkp * 128 * 16;
+  return 2 * 4 * kTile + 128 * kGcolPitch * 4 + k.tap_bytes + 1024 + 256 <= kMaxSmem;
+}
+
+bool plan_k3(const TC& d, K3P& k) {
+  k.BN = largest_tile(d.ops);
+  if (k.BN < 16) return false;
+  k.noct = d.ops / k.BN;
+  const int units = d.MC * d.SG * k.noct;
+  const int total = d.N * d.stages_img;
+  k.nsplit = std::max(1, std::min(total, d2b_cdiv(kNumSMs, units)));
+  k.sper = d2b_cdiv(total, k.nsplit);
+  k.nsplit = d2b_cdiv(total, k.sper);
+  k.stage_bytes = 2 * kTile + 2 * k.BN * 128;
+  k.S = 3;
+  while (k.S > 1 && k.S * k.stage_bytes + 4096 + 1024 + 256 > kMaxSmem) --k.S;
+  return k.S >= 2;
+}
+
+// ------------------------------------------------------------------------------------------------ sampling taps
+// One 16-byte entry per (deformable group, kernel point, pixel): {code, lh, lw, mask} with
+// code = ((pos0 + W + 1) << 4) | valid-corner bits, pos0 = floor(h)*W + floor(w) (may be "virtual": row/col -1).
+// An entry of zeros means "sample outside (-1,H)x(-1,W)": contributes nothing (deform_conv_cuda_kernel.cu:273).
+__device__ __forceinline__ int4 make_tap(const TC& d, const float* __restrict__ offset, const float* __restrict__ mask,
+                                         int b, int dg, int kp, int p) {
+  int4 t = make_int4(0, 0, 0, 0);
+  if (p < d.HoWo) {
+    const int ho = p / d.Wo, wo = p - ho * d.Wo;
+    const int ki = kp / d.kw, kj = kp - ki * d.kw;
+    const size_t ob = ((size_t)(b * d.DG + dg) * 2 * d.KK) * d.HoWo;
+    const float oh = __ldg(offset + ob + (size_t)(2 * kp) * d.HoWo + p);       // deform_conv_cuda_kernel.cu:263-269
+    const float ow = __ldg(offset + ob + (size_t)(2 * kp + 1) * d.HoWo + p);
+    const float hf = (float)(ho * d.sh - d.ph + ki * d.dh) + oh;
+    const float wf = (float)(wo * d.sw - d.pw + kj * d.dw) + ow;
+    const float m = mask ? __ldg(mask + ((size_t)(b * d.DG + dg) * d.KK + kp) * d.HoWo + p) : 1.f;
+    if (hf > -1.f && wf > -1.f && hf < (float)d.H && wf < (float)d.W) {
+      const float hfl = floorf(hf), wfl = floorf(wf);
+      const int hl = (int)hfl, wl = (int)wfl;
+      const bool t0 = hl >= 0, t1 = hl + 1 <= d.H - 1, l0 = wl >= 0, l1 = wl + 1 <= d.W - 1;
+      const int flags = (t0 && l0 ? 1 : 0) | (t0 && l1 ? 2 : 0) | (t1 && l0 ? 4 : 0) | (t1 && l1 ? 8 : 0);
+      t.x = ((hl * d.W + wl + d.W + 1) << 4) | flags;
+      t.y = __float_as_int(hf - hfl);
+      t.z = __float_as_int(wf - wfl);
+      t.w = __float_as_int(m);
+    }
+  }
+  return t;
+}
+
+struct Taps4 {
+  float4 v0, v1, v2, v3;
+};
+
+// the four corner pixels (4 channels each) of one tap entry; corners outside the image read as 0
+__device__ __forceinline__ void load_corners(const float* __restrict__ xc, int Cin, int W, int code, Taps4& t) {
+  const int pos0 = (code >> 4) - W - 1;
+  const float* __restrict__ p = xc + (long long)pos0 * Cin;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  t.v0 = (code & 1) ? __ldg(reinterpret_cast<const float4*>(p)) : z;
+  t.v1 = (code & 2) ? __ldg(reinterpret_cast<const float4*>(p + Cin)) : z;
+  t.v2 = (code & 4) ? __ldg(reinterpret_cast<const float4*>(p + (size_t)W * Cin)) : z;
+  t.v3 = (code & 8) ? __ldg(reinterpret_cast<const float4*>(p + (size_t)(W + 1) * Cin)) : z;
+}
+
+__device__ __forceinline__ void interp4(const Taps4& t, float w0, float w1, float w2, float w3, float (&v)[4]) {
+  v[0] = fmaf(w3, t.v3.x, fmaf(w2, t.v2.x, fmaf(w1, t.v1.x, w0 * t.v0.x)));
+  v[1] = fmaf(w3, t.v3.y, fmaf(w2, t.v2.y, fmaf(w1, t.v1.y, w0 * t.v0.y)));
+  v[2] = fmaf(w3, t.v3.z, fmaf(w2, t.v2.z, fmaf(w1, t.v1.z, w0 * t.v0.z)));
+  v[3] = fmaf(w3, t.v3.w, fmaf(w2, t.v2.w, fmaf(w1, t.v1.w, w0 * t.v0.w)));
+}
+
+// gather 4 channels of one (pixel, unit) and store them as bf16 hi / lo into a swizzled 128-byte row
+__device__ __forceinline__ void gather_store(const Taps4& t, int4 tap, uint8_t* a_hi, uint8_t* a_lo, uint32_t off,
+                                             bool split) {
+  const float lh = __int_as_float(tap.y), lw = __int_as_float(tap.z), m = __int_as_float(tap.w);
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  float v[4];
+  interp4(t, hh * hw * m, hh * lw * m, lh * hw * m, lh * lw * m, v);
+  uint2 hi, lo;
+  split4(v, hi, lo);
+  *reinterpret_cast<uint2*>(a_hi + off) = hi;
+  if (split) *reinterpret_cast<uint2*>(a_lo + off) = lo;
+}
+
+// ================================================================================================ K1: forward
+// grid (N * tiles_img, spans * oc tiles, k splits)
+template <int kTmemCols>
+__global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __restrict__ xh,
+                                                                 const float* __restrict__ offset,
+                                                                 const float* __restrict__ mask,
+                                                                 const uint8_t* __restrict__ wt,
+                                                                 const float* __restrict__ bias, const TC d,
+                                                                 const K1P k, const int split, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  int4* taps = reinterpret_cast<int4*>(smem + k.S * k.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(taps) + k.tap_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + k.S;
+  uint64_t* accum_bar = bars + 2 * k.S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k.S + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / d.tiles_img, p0 = (blockIdx.x - b * d.tiles_img) * 128;
+  const int span = blockIdx.y / k.noct, oct = blockIdx.y - span * k.noct;
+  const int sg0 = span * k.gspan;
+  const int kp0 = blockIdx.z * k.nkp, nkp = min(d.KK, kp0 + k.nkp) - kp0;
+  const int nt = k.gspan * nkp * d.cbs;
+  const int dg0 = (sg0 * d.cps) / d.cpdg;
+
+  if (tid == 0) {
+    for (int s = 0; s < k.S; ++s) {
+      mbar_init(&full_bar[s], kWorkerWarps + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_init_fence();
+  }
+  if (warp == kWorkerWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (tid < kWorkers) {
+    const int ndg = ((sg0 + k.gspan) * d.cps - 1) / d.cpdg - dg0 + 1;
+    for (int i = tid; i < ndg * nkp * 128; i += kWorkers) {
+      const int row = i & 127, r = i >> 7;
+      const int dgl = r / nkp, kpl = r - dgl * nkp;
+      taps[i] = make_tap(d, offset, mask, b, dg0 + dgl, kp0 + kpl, p0 + row);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWorkerWarps) {
+    // =============================================================== GATHER: A tile [128 px][64 k'] K-major, hi + lo
+    const int half = lane >> 4, q = lane & 15;
+    const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin;
+    int sgl = 0, kpl = 0, cb = 0;
+    for (int t = 0; t < nt; ++t) {
+      const int s = t % k.S;
+      const uint32_t par = (uint32_t)((t / k.S) & 1);
+      const int cbase = (sg0 + sgl) * d.cps + cb * 64;
+      const int4* __restrict__ tp = taps + ((cbase / d.cpdg - dg0) * nkp + kpl) * 128;
+      const float* __restrict__ xc = ximg + cbase + q * 4;
+      uint8_t* a_hi = smem + s * k.stage_bytes;
+      uint8_t* a_lo = a_hi + kTile;
+      mbar_wait(&empty_bar[s], par ^ 1u);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int r0 = warp * 8 + it * 4 + half, r1 = r0 + 2;
+        const int4 tap0 = tp[r0], tap1 = tp[r1];
+        Taps4 c0, c1;
+        load_corners(xc, d.Cin, d.W, tap0.x, c0);
+        load_corners(xc, d.Cin, d.W, tap1.x, c1);
+        gather_store(c0, tap0, a_hi, a_lo, swz128((uint32_t)r0, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        gather_store(c1, tap1, a_hi, a_lo, swz128((uint32_t)r1, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (++cb == d.cbs) {
+        cb = 0;
+        if (++kpl == nkp) { kpl = 0; ++sgl; }
+      }
+    }
+    // =============================================================== EPILOGUE: TMEM -> registers -> NCHW global
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int quad = warp & 3, cgrp = warp >> 2;
+    const int row = quad * 32 + lane, p = p0 + row;
+    const bool pix_ok = p < d.HoWo;
+    const int ntot = k.gspan * k.BN;
+    const int oc0 = sg0 * d.ops + oct * k.BN;
+    const bool add_bias = bias != nullptr && blockIdx.z == 0;
+    for (int c16 = cgrp; c16 * 16 < ntot; c16 += 4) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
+      tmem_ld_wait();
+      if (pix_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int oc = oc0 + c16 * 16 + i;
+          float* dst = out + ((size_t)b * d.Cout + oc) * d.HoWo + p;
+          const float v = __uint_as_float(r[i]) + (add_bias ? __ldg(bias + oc) : 0.f);
+          if (k.red) red_add(dst, v);
+          else *dst = v;
+        }
+      }
+    }
+  } else if (warp == kWorkerWarps) {
+    // =============================================================== TMA producer: weight tile of every chunk
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(split ? 2 : 1) * (uint32_t)k.BN * 128u;
+      int sgl = 0, kpl = 0, cb = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int s = t % k.S;
+        const uint32_t par = (uint32_t)((t / k.S) & 1);
+        mbar_wait(&empty_bar[s], par ^ 1u);
+        const size_t tile = ((size_t)((sg0 + sgl) * k.noct + oct) * d.U + (size_t)(kp0 + kpl) * d.cbs + cb);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_g2s(smem + s * k.stage_bytes + 2 * kTile, wt + tile * (size_t)(2 * k.BN * 128), bytes, &full_bar[s]);
+        if (++cb == d.cbs) {
+          cb = 0;
+          if (++kpl == nkp) { kpl = 0; ++sgl; }
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    const uint32_t idesc = umma_idesc(k.BN, false, false);
+    const int per_sg = nkp * d.cbs;
+    for (int t = 0; t < nt; ++t) {
+      const int s = t % k.S;
+      const uint32_t par = (uint32_t)((t / k.S) & 1);
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      if (lane == 0) {
+        const int sgl = t / per_sg;
+        const bool first = (t - sgl * per_sg) == 0;
+        const uint32_t a_hi = smem_u32(smem + s * k.stage_bytes), a_lo = a_hi + kTile;
+        const uint32_t b_hi = a_hi + 2 * kTile, b_lo = b_hi + (uint32_t)k.BN * 128u;
+        const uint32_t dcol = tmem_base + (uint32_t)(sgl * k.BN);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = (uint32_t)kk * 32u;  // 16 bf16 along K inside the swizzled row
+          umma_bf16(dcol, umma_desc(a_hi + ko, 0, 1024), umma_desc(b_hi + ko, 0, 1024), idesc, (!first || kk > 0) ? 1u : 0u);
+          if (split) {
+            umma_bf16(dcol, umma_desc(a_hi + ko, 0, 1024), umma_desc(b_lo + ko, 0, 1024), idesc, 1u);
+            umma_bf16(dcol, umma_desc(a_lo + ko, 0, 1024), umma_desc(b_hi + ko, 0, 1024), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (t == nt - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkerWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ================================================================================================ K2: backward data
+// grid (N * tiles_img, SG, macro-chunk splits).  Per macro-chunk (2 units = 128 k'): gcol[128 px][128] = gout . W over the
+// super-group's output channels (TMEM, double buffered), drained to shared memory, then scattered:
+//   grad_x   += gcol * mask * bilinear weight      (deform_conv_cuda_kernel.cu:313-362, :923-975) red.global.add.v4 (NHWC)
+//   grad_off += gcol * mask * d(sample)/d(h,w)     (:390-451, :977-1064)                           red.global.add
+//   grad_msk += gcol * sample                      (:1053-1064)
+__global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const float* __restrict__ xh,
+                                                                      const float* __restrict__ offset,
+                                                                      const float* __restrict__ mask,
+                                                                      const uint8_t* __restrict__ gt,
+                                                                      const uint8_t* __restrict__ wt, const TC d,
+                                                                      const K2P k, const int split,
+                                                                      float* __restrict__ gxh, float* __restrict__ goff,
+                                                                      float* __restrict__ gmask) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kStage = 4 * kTile;  // A hi | A lo | B hi | B lo
+  float* gcol = reinterpret_cast<float*>(smem + 2 * kStage);
+  int4* taps = reinterpret_cast<int4*>(smem + 2 * kStage + 128 * kGcolPitch * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(taps) + k.tap_bytes);
+  uint64_t* full_bar = bars;         // [2]
+  uint64_t* empty_bar = bars + 2;    // [2]
+  uint64_t* acc_full = bars + 4;     // [2]
+  uint64_t* acc_empty = bars + 6;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / d.tiles_img, pt = blockIdx.x - b * d.tiles_img, p0 = pt * 128;
+  const int sg = blockIdx.y;
+  const int m0 = blockIdx.z * k.mper, m1 = min(d.MC, m0 + k.mper), nm = m1 - m0;
+  const int u_begin = 2 * m0, u_end = min(d.U, 2 * m1);
+  const int kp0 = u_begin / d.cbs, nkp = (u_end - 1) / d.cbs - kp0 + 1;
+  const int dg0 = (sg * d.cps) / d.cpdg;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kWorkerWarps);
+    }
+    mbar_init_fence();
+  }
+  if (warp == kWorkerWarps + 1) tmem_alloc<256>(tmem_slot);
+  if (tid < kWorkers) {
+    const int ndg = ((sg + 1) * d.cps - 1) / d.cpdg - dg0 + 1;
+    for (int i = tid; i < ndg * nkp * 128; i += kWorkers) {
+      const int row = i & 127, r = i >> 7;
+      const int dgl = r / nkp, kpl = r - dgl * nkp;
+      taps[i] = make_tap(d, offset, mask, b, dg0 + dgl, kp0 + kpl, p0 + row);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWorkerWarps) {
+    const int half = lane >> 4, q = lane & 15;
+    const int quad = warp & 3, cq = warp >> 2;
+    const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin;
+    float* __restrict__ gimg = gxh ? gxh + (size_t)b * d.H * d.W * d.Cin : nullptr;
+    float sh[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_kp = -1, cur_dg = -1;
+
+    auto flush = [&]() {
+      if (cur_kp < 0) return;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+          sh[j] += __shfl_xor_sync(0xffffffffu, sh[j], o);
+          sw[j] += __shfl_xor_sync(0xffffffffu, sw[j], o);
+          sm[j] += __shfl_xor_sync(0xffffffffu, sm[j], o);
+        }
+      }
+      if (q < 12) {
+        const int j = q / 3, which = q - j * 3;
+        float v = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (jj == j) v = which == 0 ? sh[jj] : (which == 1 ? sw[jj] : sm[jj]);
+        const int p = p0 + warp * 8 + j * 2 + half;
+        if (p < d.HoWo) {
+          if (which < 2) {
+            if (goff) red_add(goff + ((size_t)(b * d.DG + cur_dg) * 2 * d.KK + 2 * cur_kp + which) * d.HoWo + p, v);
+          } else if (gmask) {
+            red_add(gmask + ((size_t)(b * d.DG + cur_dg) * d.KK + cur_kp) * d.HoWo + p, v);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sh[j] = sw[j] = sm[j] = 0.f;
+    };
+
+    for (int ml = 0; ml < nm; ++ml) {
+      const int buf = ml & 1;
+      const int m = m0 + ml;
+      const int nu = (2 * m + 1 < d.U) ? 2 : 1;
+      mbar_wait(&acc_full[buf], (uint32_t)((ml >> 1) & 1));
+      tc_fence_after();
+      // ---- drain: this warp's 32 TMEM lanes (pixels) x 32 of the 128 columns -> gcol[px][col]
+      if (cq * 32 < nu * 64) {
+        float* dst = gcol + (quad * 32 + lane) * kGcolPitch + cq * 32;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cq * 32 + h2 * 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(dst + h2 * 16 + i * 4) =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                            __uint_as_float(r[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      named_bar_sync(1, kWorkers);
+      // ---- scatter
+      for (int ul = 0; ul < nu; ++ul) {
+        const int u = 2 * m + ul;
+        const int kp = u / d.cbs, cb = u - kp * d.cbs;
+        const int cbase = sg * d.cps + cb * 64;
+        const int dg = cbase / d.cpdg;
+        if (kp != cur_kp || dg != cur_dg) {
+          flush();
+          cur_kp = kp;
+          cur_dg = dg;
+        }
+        const int4* __restrict__ tp = taps + ((dg - dg0) * nkp + (kp - kp0)) * 128;
+        const float* __restrict__ xc = ximg + cbase + q * 4;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int ra = warp * 8 + it * 4 + half, rb = ra + 2;
+          const int4 tapa = tp[ra], tapb = tp[rb];
+          Taps4 ca, cbv;
+          load_corners(xc, d.Cin, d.W, tapa.x, ca);
+          load_corners(xc, d.Cin, d.W, tapb.x, cbv);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int4 tap = e ? tapb : tapa;
+            if ((tap.x & 15) == 0) continue;  // sample outside the image: no gradient anywhere
+            const Taps4& c = e ? cbv : ca;
+            const int row = e ? rb : ra;
+            const int j = it * 2 + e;
+            const float4 g4 = *reinterpret_cast<const float4*>(gcol + row * kGcolPitch + ul * 64 + q * 4);
+            const float lh = __int_as_float(tap.y), lw = __int_as_float(tap.z), mk = __int_as_float(tap.w);
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float a0[4] = {c.v0.x, c.v0.y, c.v0.z, c.v0.w}, a1[4] = {c.v1.x, c.v1.y, c.v1.z, c.v1.w};
+            const float a2[4] = {c.v2.x, c.v2.y, c.v2.z, c.v2.w}, a3[4] = {c.v3.x, c.v3.y, c.v3.z, c.v3.w};
+            float gm[4];
+            float ah = 0.f, aw = 0.f, am = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              gm[i] = g[i] * mk;
+              // d val / d h = (1-lw)(v2-v0) + lw (v3-v1);  d val / d w = (1-lh)(v1-v0) + lh (v3-v2)
+              ah = fmaf(gm[i], fmaf(lw, a3[i] - a1[i], hw * (a2[i] - a0[i])), ah);
+              aw = fmaf(gm[i], fmaf(lh, a3[i] - a2[i], hh * (a1[i] - a0[i])), aw);
+              am = fmaf(g[i], fmaf(w3, a3[i], fmaf(w2, a2[i], fmaf(w1, a1[i], w0 * a0[i]))), am);
+            }
+            sh[j] += ah;
+            sw[j] += aw;
+            sm[j] += am;
+            if (gimg) {
+              const int pos0 = (tap.x >> 4) - d.W - 1;
+              float* gp = gimg + (long long)pos0 * d.Cin + cbase + q * 4;
+              if (tap.x & 1) red_add_v4(gp, gm[0] * w0, gm[1] * w0, gm[2] * w0, gm[3] * w0);
+              if (tap.x & 2) red_add_v4(gp + d.Cin, gm[0] * w1, gm[1] * w1, gm[2] * w1, gm[3] * w1);
+              if (tap.x & 4) red_add_v4(gp + (size_t)d.W * d.Cin, gm[0] * w2, gm[1] * w2, gm[2] * w2, gm[3] * w2);
+              if (tap.x & 8) red_add_v4(gp + (size_t)(d.W + 1) * d.Cin, gm[0] * w3, gm[1] * w3, gm[2] * w3, gm[3] * w3);
+            }
+          }
+        }
+      }
+      named_bar_sync(1, kWorkers);  // everyone is done reading gcol before the next drain overwrites it
+    }
+    flush();
+  } else if (warp == kWorkerWarps) {
+    // =============================================================== TMA producer: gout tile + W^T tile per K stage
+    if (lane == 0) {
+      const uint32_t half_bytes = (uint32_t)(split ? 2 : 1) * (uint32_t)kTile;
+      int c = 0;
+      for (int ml = 0; ml < nm; ++ml) {
+        const int m = m0 + ml;
+        for (int ks = 0; ks < d.nks; ++ks, ++c) {
+          const int s = c & 1;
+          const uint32_t par = (uint32_t)((c >> 1) & 1);
+          mbar_wait(&empty_bar[s], par ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], 2 * half_bytes);
+          const size_t atile = (((size_t)b * d.tiles_img + pt) * d.SG + sg) * d.nks + ks;
+          const size_t btile = ((size_t)sg * d.MC + m) * d.nks + ks;
+          bulk_g2s(smem + s * kStage, gt + atile * (size_t)(2 * kTile), half_bytes, &full_bar[s]);
+          bulk_g2s(smem + s * kStage + 2 * kTile, wt + btile * (size_t)(2 * kTile), half_bytes, &full_bar[s]);
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    int c = 0;
+    for (int ml = 0; ml < nm; ++ml) {
+      const int buf = ml & 1;
+      const int m = m0 + ml;
+      const int ncols = (2 * m + 1 < d.U) ? 128 : 64;
+      const uint32_t idesc = umma_idesc(ncols, false, false);
+      mbar_wait(&acc_empty[buf], (uint32_t)(((ml >> 1) & 1) ^ 1));
+      tc_fence_after();
+      for (int ks = 0; ks < d.nks; ++ks, ++c) {
+        const int s = c & 1;
+        const uint32_t par = (uint32_t)((c >> 1) & 1);
+        mbar_wait(&full_bar[s], par);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(smem + s * kStage), a_lo = a_hi + kTile, b_hi = a_hi + 2 * kTile, b_lo = b_hi + kTile;
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t ko = (uint32_t)kk * 32u;
+            umma_bf16(dcol, umma_desc(a_hi + ko, 0, 1024), umma_desc(b_hi + ko, 0, 1024), idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+            if (split) {
+              umma_bf16(dcol, umma_desc(a_hi + ko, 0, 1024), umma_desc(b_lo + ko, 0, 1024), idesc, 1u);
+              umma_bf16(dcol, umma_desc(a_lo + ko, 0, 1024), umma_desc(b_hi + ko, 0, 1024), idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (ks == d.nks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkerWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ================================================================================================ K3: backward weight
+// grid (M blocks = pairs of units, pixel splits, SG * oc tiles).  D[128 k'][BN oc] += col^T[128 k'][64 px] . gout[64 px][BN oc]
+// per 64-pixel stage; the gathered tile is written [unit half][pixel][64 ch] = MN-major for the tensor core.
+template <int kTmemCols>
+__global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const float* __restrict__ xh,
+                                                                        const float* __restrict__ offset,
+                                                                        const float* __restrict__ mask,
+                                                                        const uint8_t* __restrict__ gt, const TC d,
+                                                                        const K3P k, const int split,
+                                                                        float* __restrict__ gw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  int4* tap_s = reinterpret_cast<int4*>(smem + k.S * k.stage_bytes);  // [16 warps][8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tap_s) + 4096);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + k.S;
+  uint64_t* accum_bar = bars + 2 * k.S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k.S + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.x;
+  const int sg = blockIdx.z / k.noct, oct = blockIdx.z - sg * k.noct;
+  const int total = d.N * d.stages_img;
+  const int gs0 = blockIdx.y * k.sper, gs1 = min(total, gs0 + k.sper), ns = gs1 - gs0;
+
+  if (tid == 0) {
+    for (int s = 0; s < k.S; ++s) {
+      mbar_init(&full_bar[s], kWorkerWarps + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_init_fence();
+  }
+  if (warp == kWorkerWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWorkerWarps) {
+    // =============================================================== GATHER: A tile [2 units][64 px][64 ch], hi + lo
+    const int half = lane >> 4, q = lane & 15;
+    const int u = 2 * mb + half;             // this half-warp's unit
+    const bool u_ok = u < d.U;
+    const int kp = u_ok ? u / d.cbs : 0, cb = u_ok ? u - kp * d.cbs : 0;
+    const int cbase = sg * d.cps + cb * 64;
+    const int dg = cbase / d.cpdg;
+    // lanes 0..7 build the taps of this warp's 4 pixels x 2 units for every stage
+    const int tl_half = (lane >> 2) & 1, tl_j = lane & 3;
+    const int tl_u = 2 * mb + tl_half;
+    const int tl_kp = tl_u < d.U ? tl_u / d.cbs : 0;
+    const int tl_dg = tl_u < d.U ? (sg * d.cps + (tl_u - tl_kp * d.cbs) * 64) / d.cpdg : 0;
+    int4* my_taps = tap_s + warp * 8;
+    for (int i = 0; i < ns; ++i) {
+      const int s = i % k.S;
+      const uint32_t par = (uint32_t)((i / k.S) & 1);
+      const int gs = gs0 + i;
+      const int b = gs / d.stages_img, pbase = (gs - b * d.stages_img) * 64;
+      const float* __restrict__ xc = xh + (size_t)b * d.H * d.W * d.Cin + cbase + q * 4;
+      uint8_t* a_hi = smem + s * k.stage_bytes + half * 8192;
+      uint8_t* a_lo = a_hi + kTile;
+      if (lane < 8)
+        my_taps[lane] = tl_u < d.U ? make_tap(d, offset, mask, b, tl_dg, tl_kp, pbase + warp * 4 + tl_j) : make_int4(0, 0, 0, 0);
+      __syncwarp();
+      mbar_wait(&empty_bar[s], par ^ 1u);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int j0 = it * 2, j1 = j0 + 1;
+        const int4 tap0 = my_taps[half * 4 + j0], tap1 = my_taps[half * 4 + j1];
+        Taps4 c0, c1;
+        load_corners(xc, d.Cin, d.W, tap0.x, c0);
+        load_corners(xc, d.Cin, d.W, tap1.x, c1);
+        const int r0 = warp * 4 + j0, r1 = r0 + 1;
+        gather_store(c0, tap0, a_hi, a_lo, swz128((uint32_t)r0, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        gather_store(c1, tap1, a_hi, a_lo, swz128((uint32_t)r1, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> red.add into gW
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int quad = warp & 3, cgrp = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int eu = 2 * mb + (row >> 6);
+    const bool row_ok = eu < d.U;
+    const int ekp = row_ok ? eu / d.cbs : 0;
+    const int ec = sg * d.cps + (row_ok ? eu - ekp * d.cbs : 0) * 64 + (row & 63);  // global input channel
+    const int egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
+    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += 4) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int oc = sg * d.ops + oct * k.BN + c16 * 16 + i;
+          if (oc / d.opg == egrp) red_add(gw + ((size_t)oc * d.cpg + ecin) * d.KK + ekp, __uint_as_float(r[i]));
+        }
+      }
+    }
+  } else if (warp == kWorkerWarps) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(split ? 2 : 1) * (uint32_t)k.BN * 128u;
+      for (int i = 0; i < ns; ++i) {
+        const int s = i % k.S;
+        const uint32_t par = (uint32_t)((i / k.S) & 1);
+        mbar_wait(&empty_bar[s], par ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        const size_t tile = ((size_t)(gs0 + i) * d.SG + sg) * k.noct + oct;
+        bulk_g2s(smem + s * k.stage_bytes + 2 * kTile, gt + tile * (size_t)(2 * k.BN * 128), bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    const uint32_t idesc = umma_idesc(k.BN, true, false);
+    for (int i = 0; i < ns; ++i) {
+      const int s = i % k.S;
+      const uint32_t par = (uint32_t)((i / k.S) & 1);
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * k.stage_bytes), a_lo = a_hi + kTile;
+        const uint32_t b_hi = a_hi + 2 * kTile, b_lo = b_hi + (uint32_t)k.BN * 128u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // A: 16 pixels (K) = two 8-row atoms 1024 B apart; the two 64-channel M blocks are 8192 B apart
+          const uint32_t ao = (uint32_t)kk * 2048u, bo = (uint32_t)kk * 32u;
+          umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          if (split) {
+            umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_lo + bo, 0, 1024), idesc, 1u);
+            umma_bf16(tmem_base, umma_desc(a_lo + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == ns - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkerWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ================================================================================================ operand pre-tiling
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  float h[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    r[i] = v[i] - h[i];
+  }
+  hi = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+  lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+}
+
+// weight element of (global output channel, global input channel, kernel point); 0 across original groups
+__device__ __forceinline__ float w_elem(const float* __restrict__ w, const TC& d, int oc, int c, int kp) {
+  const int g = c / d.cpg;
+  if (oc / d.opg != g) return 0.f;
+  return __ldg(w + ((size_t)oc * d.cpg + (c - g * d.cpg)) * d.KK + kp);
+}
+
+// K1 B tiles: [sg][oc tile][unit] -> [BN rows = oc][64 k' = channels of the unit], K-major swizzled, hi then lo
+__global__ void dcn_wtile_fwd_kernel(const float* __restrict__ w, const TC d, int BN, int noct, uint8_t* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)d.SG * noct * d.U * BN * 8;
+  if (idx >= total) return;
+  const int c16 = (int)(idx & 7);
+  const int r = (int)((idx >> 3) % BN);
+  const long long tile = idx / (8LL * BN);
+  const int u = (int)(tile % d.U);
+  const int oct = (int)((tile / d.U) % noct);
+  const int sg = (int)(tile / ((long long)d.U * noct));
+  const int kp = u / d.cbs, cb = u - kp * d.cbs;
+  const int oc = sg * d.ops + oct * BN + r;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = w_elem(w, d, oc, sg * d.cps + cb * 64 + c16 * 8 + e, kp);
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  uint8_t* base = dst + tile * (size_t)(2 * BN * 128);
+  *reinterpret_cast<uint4*>(base + swz128((uint32_t)r, (uint32_t)c16)) = hi;
+  *reinterpret_cast<uint4*>(base + BN * 128 + swz128((uint32_t)r, (uint32_t)c16)) = lo;
+}
+
+// K2 B tiles: [sg][macro-chunk][K stage] -> [128 rows = k' of the 2 units][64 oc of the stage], hi then lo
+__global__ void dcn_wtile_bwd_kernel(const float* __restrict__ w, const TC d, uint8_t* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)d.SG * d.MC * d.nks * 128 * 8;
+  if (idx >= total) return;
+  const int c16 = (int)(idx & 7);
+  const int r = (int)((idx >> 3) & 127);
+  const long long tile = idx >> 10;
+  const int ks = (int)(tile % d.nks);
+  const int m = (int)((tile / d.nks) % d.MC);
+  const int sg = (int)(tile / ((long long)d.nks * d.MC));
+  const int u = 2 * m + (r >> 6);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (u < d.U) {
+    const int kp = u / d.cbs, cb = u - kp * d.cbs;
+    const int c = sg * d.cps + cb * 64 + (r & 63);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w_elem(w, d, sg * d.ops + ks * 64 + c16 * 8 + e, c, kp);
+  }
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  uint8_t* base = dst + tile * (size_t)(2 * kTile);
+  *reinterpret_cast<uint4*>(base + swz128((uint32_t)r, (uint32_t)c16)) = hi;
+  *reinterpret_cast<uint4*>(base + kTile + swz128((uint32_t)r, (uint32_t)c16)) = lo;
+}
+
+// K2 A tiles: gout [N,Cout,HoWo] -> [b][pixel tile][sg][K stage] -> [128 rows = px][64 oc], hi then lo.  One CTA per tile.
+__global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __restrict__ gout, const TC d,
+                                                                uint8_t* __restrict__ dst) {
+  __shared__ float t[64][129];
+  const long long tile = blockIdx.x;
+  const int ks = (int)(tile % d.nks);
+  const int sg = (int)((tile / d.nks) % d.SG);
+  const int pt = (int)((tile / ((long long)d.nks * d.SG)) % d.tiles_img);
+  const int b = (int)(tile / ((long long)d.nks * d.SG * d.tiles_img));
+  const int p0 = pt * 128, oc0 = sg * d.ops + ks * 64;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * 128; e += 256) {
+    const int o = e >> 7, pp = e & 127;
+    const int p = p0 + pp;
+    t[o][pp] = p < d.HoWo ? __ldg(gout + ((size_t)b * d.Cout + oc0 + o) * d.HoWo + p) : 0.f;
+  }
+  __syncthreads();
+  uint8_t* base = dst + tile * (size_t)(2 * kTile);
+  for (int e = tid; e < 128 * 8; e += 256) {
+    const int r = e >> 3, c16 = e & 7;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[c16 * 8 + i][r];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(base + swz128((uint32_t)r, (uint32_t)c16)) = hi;
+    *reinterpret_cast<uint4*>(base + kTile + swz128((uint32_t)r, (uint32_t)c16)) = lo;
+  }
+}
+
+// K3 B tiles: gout -> [b][64-pixel stage][sg][oc tile] -> [BN rows = oc][64 px], K-major swizzled, hi then lo
+__global__ void dcn_gout_oc_tiles_kernel(const float* __restrict__ gout, const TC d, int BN, int noct,
+                                         uint8_t* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)d.N * d.stages_img * d.SG * noct * BN * 8;
+  if (idx >= total) return;
+  const int c16 = (int)(idx & 7);
+  const int r = (int)((idx >> 3) % BN);
+  const long long tile = idx / (8LL * BN);
+  const int oct = (int)(tile % noct);
+  const int sg = (int)((tile / noct) % d.SG);
+  const int ps = (int)((tile / ((long long)noct * d.SG)) % d.stages_img);
+  const int b = (int)(tile / ((long long)noct * d.SG * d.stages_img));
+  const int oc = sg * d.ops + oct * BN + r;
+  const float* __restrict__ src = gout + ((size_t)b * d.Cout + oc) * d.HoWo;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int p = ps * 64 + c16 * 8 + e;
+    v[e] = p < d.HoWo ? __ldg(src + p) : 0.f;
+  }
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  uint8_t* base = dst + tile * (size_t)(2 * BN * 128);
+  *reinterpret_cast<uint4*>(base + swz128((uint32_t)r, (uint32_t)c16)) = hi;
+  *reinterpret_cast<uint4*>(base + BN * 128 + swz128((uint32_t)r, (uint32_t)c16)) = lo;
+}
+
+// [N,HW,C] -> [N,C,HW]  (grad_x back to the reference's layout)
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ src, int C, int HW,
+                                                           float* __restrict__ dst) {
+  __shared__ float t[64][33];
+  const int hw0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const float* __restrict__ s = src + (size_t)blockIdx.z * HW * C;
+  float* __restrict__ o = dst + (size_t)blockIdx.z * C * HW;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * 32; e += 256) {
+    const int pp = e >> 5, cc = e & 31;
+    t[pp][cc] = (hw0 + pp < HW && c0 + cc < C) ? __ldg(s + (size_t)(hw0 + pp) * C + c0 + cc) : 0.f;
+  }
+  __syncthreads();
+  for (int e = tid; e < 64 * 32; e += 256) {
+    const int cc = e >> 6, pp = e & 63;
+    if (hw0 + pp < HW && c0 + cc < C) o[(size_t)(c0 + cc) * HW + hw0 + pp] = t[pp][cc];
+  }
+}
+
+template <typename F>
+int set_smem(F* kernel, int bytes) {
+  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int to_nhwc(const float* x, const TC& d, float* dst, cudaStream_t stream) {
+  d2b_pyramid P = {};
+  P.num_levels = 1;
+  P.feat[0] = x;
+  P.H[0] = d.H;
+  P.W[0] = d.W;
+  P.scale[0] = 1.f;
+  float* dsts[1] = {dst};
+  return d2b_pyramid_nchw_to_nhwc(&P, d.N, d.Cin, dsts, (void*)stream);
 }
 
 }  // namespace
 
-// shapes the tensor-core kernel takes
+// ------------------------------------------------------------------------------------------------ host entry points
+// (internal linkage across the library: declared again in deform_conv.cu)
 int d2b_deform_conv_tc_supported(const d2b_dcn_params* p) {
-  TcDims d;
-  if (!make_tc_dims(p, d)) return 0;
-  return (d.cpg % BK == 0) && (d.cpdg % BK == 0) && (d.opg % 16 == 0) && ((size_t)d.HoWo * d.Cout < (1ull << 31));
+  TC d;
+  K1P k1;
+  return make_tc(p, d) && plan_k1(d, k1);
 }
 
-size_t d2b_deform_conv_tc_workspace_bytes(const d2b_dcn_params* p) {
-  TcDims d;
-  if (!make_tc_dims(p, d)) return 0;
-  return 2 * ((sizeof(__nv_bfloat16) * (size_t)d.Cout * d.K + 255) & ~(size_t)255);
+int d2b_deform_conv_tc_bwd_supported(const d2b_dcn_params* p) {
+  TC d;
+  K2P k2;
+  K3P k3;
+  return make_tc(p, d) && plan_k2(d, k2) && plan_k3(d, k3);
+}
+
+size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc) {
+  TC d;
+  K1P k;
+  if (!make_tc(p, d) || !plan_k1(d, k)) return 0;
+  size_t b = align256((size_t)d.SG * k.noct * d.U * 2 * k.BN * 128);
+  if (!x_nhwc) b += align256(sizeof(float) * (size_t)d.N * d.H * d.W * d.Cin);
+  return b;
 }
 
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                               const float* bias, const d2b_dcn_params* p, int precision, float* out, void* workspace,
-                               size_t workspace_bytes, void* stream_) {
+                               const float* bias, const d2b_dcn_params* p, int precision, int x_nhwc, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  TcDims d;
-  if (!make_tc_dims(p, d)) return D2B_EINVAL;
-  if (!d2b_deform_conv_tc_supported(p)) return D2B_EUNSUPPORTED;
+  TC d;
+  K1P k;
+  if (!make_tc(p, d) || !plan_k1(d, k)) return D2B_EUNSUPPORTED;  // argument validity was checked by the caller
   if (d.N == 0) return D2B_OK;
-  if (!workspace || workspace_bytes < d2b_deform_conv_tc_workspace_bytes(p)) return D2B_EWORKSPACE;
-  __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>((char*)workspace + d2b_deform_conv_tc_workspace_bytes(p) / 2);
-  const int total = d.Cout * d.K;
-  dcn_weight_split_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(weight, d.Cout, d.cpg, d.KK, whi, wlo);
-  D2B_CHECK_LAUNCH();
-  static bool attr_set = false;
-  if (!attr_set) {
-    D2B_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  if (!workspace || workspace_bytes < d2b_deform_conv_tc_fwd_workspace(p, x_nhwc)) return D2B_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15))) return D2B_EINVAL;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  uint8_t* wt = ws;
+  ws += align256((size_t)d.SG * k.noct * d.U * 2 * k.BN * 128);
+  const float* xh = x;
+  if (!x_nhwc) {
+    float* xn = reinterpret_cast<float*>(ws);
+    int rc = to_nhwc(x, d, xn, stream);
+    if (rc) return rc;
+    xh = xn;
   }
-  dim3 grid(d2b_cdiv(d.HoWo, BM), d2b_cdiv(d.opg, BNMAX), d.N * d.G);
-  dcn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(x, offset, mask, whi, wlo, bias, d, precision == 1 ? 1 : 0, out);
+  {
+    const long long total = (long long)d.SG * k.noct * d.U * k.BN * 8;
+    dcn_wtile_fwd_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(weight, d, k.BN, k.noct, wt);
+    D2B_CHECK_LAUNCH();
+  }
+  if (k.red) D2B_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)d.N * d.Cout * d.HoWo, stream));
+  const int smem_bytes = k.S * k.stage_bytes + k.tap_bytes + 1024 + 256;
+  const int cols = pow2_cols(k.gspan * k.BN);
+  const int split = precision == 1 ? 1 : 0;
+  dim3 grid(d.N * d.tiles_img, (d.SG / k.gspan) * k.noct, k.ksplit);
+#define D2B_LAUNCH_K1(COLS)                                                                                            \
+  {                                                                                                                    \
+    int rc = set_smem(dcn_fwd_tc_kernel<COLS>, smem_bytes);                                                            \
+    if (rc) return rc;                                                                                                 \
+    dcn_fwd_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, wt, bias, d, k, split, out);     \
+  }
+  if (cols <= 32) D2B_LAUNCH_K1(32)
+  else if (cols == 64) D2B_LAUNCH_K1(64)
+  else if (cols == 128) D2B_LAUNCH_K1(128)
+  else D2B_LAUNCH_K1(256)
+#undef D2B_LAUNCH_K1
   D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int need_data, int need_weight) {
+  TC d;
+  K2P k2;
+  K3P k3;
+  if (!make_tc(p, d) || !plan_k2(d, k2) || !plan_k3(d, k3)) return 0;
+  size_t b = 0;
+  const size_t xbytes = align256(sizeof(float) * (size_t)d.N * d.H * d.W * d.Cin);
+  if (!x_nhwc) b += xbytes;                     // x in NHWC
+  if (need_data && !x_nhwc) b += xbytes;        // grad_x accumulated in NHWC
+  if (need_data) {
+    b += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);  // gout, pixel-row tiles
+    b += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);               // W^T tiles
+  }
+  if (need_weight) b += align256((size_t)d.N * d.stages_img * d.SG * k3.noct * 2 * k3.BN * 128);  // gout, oc-row tiles
+  return b;
+}
+
+// grad_x: NCHW (or NHWC when x_nhwc) fully written; grad_offset / grad_mask / grad_weight fully written.
+int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
+                                const float* grad_out, const d2b_dcn_params* p, int precision, int x_nhwc,
+                                float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TC d;
+  K2P k2;
+  K3P k3;
+  if (!make_tc(p, d) || !plan_k2(d, k2) || !plan_k3(d, k3)) return D2B_EUNSUPPORTED;
+  const int need_data = (grad_x || grad_offset || grad_mask) ? 1 : 0, need_weight = grad_weight ? 1 : 0;
+  const size_t nx = (size_t)d.N * d.H * d.W * d.Cin, noff = (size_t)d.N * d.DG * 2 * d.KK * d.HoWo;
+  const size_t nm = (size_t)d.N * d.DG * d.KK * d.HoWo, nw = (size_t)d.Cout * d.cpg * d.KK;
+  if (grad_offset && noff) D2B_CUDA(cudaMemsetAsync(grad_offset, 0, noff * 4, stream));
+  if (grad_mask && nm) D2B_CUDA(cudaMemsetAsync(grad_mask, 0, nm * 4, stream));
+  if (grad_weight) D2B_CUDA(cudaMemsetAsync(grad_weight, 0, nw * 4, stream));
+  if (d.N == 0) return D2B_OK;
+  if (!need_data && !need_weight) return D2B_OK;
+  if (!workspace || workspace_bytes < d2b_deform_conv_tc_bwd_workspace(p, x_nhwc, need_data, need_weight)) return D2B_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15)) ||
+      (x_nhwc && grad_x && (reinterpret_cast<uintptr_t>(grad_x) & 15)))
+    return D2B_EINVAL;
+  const int split = precision == 1 ? 1 : 0;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const size_t xbytes = align256(sizeof(float) * nx);
+  const float* xh = x;
+  if (!x_nhwc) {
+    float* xn = reinterpret_cast<float*>(ws);
+    ws += xbytes;
+    int rc = to_nhwc(x, d, xn, stream);
+    if (rc) return rc;
+    xh = xn;
+  }
+  if (need_data) {
+    float* gxh = nullptr;
+    if (grad_x) {
+      if (x_nhwc) gxh = grad_x;
+      else gxh = reinterpret_cast<float*>(ws);
+      D2B_CUDA(cudaMemsetAsync(gxh, 0, nx * 4, stream));
+    }
+    if (!x_nhwc) ws += xbytes;
+    uint8_t* gt = ws;
+    ws += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);
+    uint8_t* wt = ws;
+    ws += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);
+    dcn_gout_px_tiles_kernel<<<(unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 256, 0, stream>>>(grad_out, d, gt);
+    D2B_CHECK_LAUNCH();
+    {
+      const long long total = (long long)d.SG * d.MC * d.nks * 128 * 8;
+      dcn_wtile_bwd_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(weight, d, wt);
+      D2B_CHECK_LAUNCH();
+    }
+    const int smem_bytes = 2 * 4 * kTile + 128 * kGcolPitch * 4 + k2.tap_bytes + 1024 + 256;
+    int rc = set_smem(dcn_bwd_data_tc_kernel, smem_bytes);
+    if (rc) return rc;
+    dim3 grid(d.N * d.tiles_img, d.SG, k2.msplit);
+    dcn_bwd_data_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, wt, d, k2, split, gxh, grad_offset,
+                                                                  mask ? grad_mask : nullptr);
+    D2B_CHECK_LAUNCH();
+    if (grad_x && !x_nhwc) {
+      dim3 g2(d2b_cdiv(d.H * d.W, 64), d2b_cdiv(d.Cin, 32), d.N);
+      nhwc_to_nchw_kernel<<<g2, 256, 0, stream>>>(gxh, d.Cin, d.H * d.W, grad_x);
+      D2B_CHECK_LAUNCH();
+    }
+  }
+  if (need_weight) {
+    uint8_t* gt = ws;
+    {
+      const long long total = (long long)d.N * d.stages_img * d.SG * k3.noct * k3.BN * 8;
+      dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, d, k3.BN, k3.noct, gt);
+      D2B_CHECK_LAUNCH();
+    }
+    const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;
+    const int cols = pow2_cols(k3.BN);
+    dim3 grid(d.MC, k3.nsplit, d.SG * k3.noct);
+#define D2B_LAUNCH_K3(COLS)                                                                                              \
+  {                                                                                                                      \
+    int rc = set_smem(dcn_bwd_weight_tc_kernel<COLS>, smem_bytes);                                                       \
+    if (rc) return rc;                                                                                                   \
+    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, d, k3, split, grad_weight); \
+  }
+    if (cols <= 32) D2B_LAUNCH_K3(32)
+    else if (cols == 64) D2B_LAUNCH_K3(64)
+    else if (cols == 128) D2B_LAUNCH_K3(128)
+    else D2B_LAUNCH_K3(256)
+#undef D2B_LAUNCH_K3
+    D2B_CHECK_LAUNCH();
+  }
   return D2B_OK;
 }

@@ -687,12 +687,10 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
 static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int PW, int sr, int aligned, float* out,
                       cudaStream_t stream, const float* gout = nullptr) {
   const size_t smem = sizeof(float) * (size_t)kV3Warps * kChW * kCapPx;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(roi_align_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {  // per launch: the attribute is per device, and the library keeps no state (a few hundred ns of host time)
+    cudaError_t e = gout ? cudaFuncSetAttribute(roi_align_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(roi_align_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int ngroup = d2b_cdiv(C, kChW);
   int groups_per_cta = ngroup;  // split the channel groups until the grid is several waves deep

@@ -406,19 +406,35 @@ def _dcn_check(x, offset, mask, weight, stride, padding, dilation, groups, dg):
                            (tuple(mask.shape), (n, dg * kh * kw, ho, wo)))
 
 
+def _dcn_x(x: Tensor, p, precision: int, backward: bool):
+    """(fp32 tensor to hand to the kernel, flags).  channels_last inputs are consumed in place by the tensor-core
+    kernels (D2B_DCN_X_NHWC); everything else is made NCHW-contiguous."""
+    xf = x.to(dtype=torch.float32)
+    if (precision != 0 and _is_channels_last(xf) and xf.data_ptr() % 16 == 0
+            and _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(p), int(backward))):
+        return xf, _C.DCN_X_NHWC
+    return xf.contiguous(), 0
+
+
+def _ws(nbytes: int, device):
+    # torch's caching allocator hands out 512-byte aligned blocks: satisfies the ABI's 256-byte requirement
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device) if nbytes else None
+
+
 @torch.library.custom_op("d2b200::deform_conv", mutates_args=(), device_types="cuda")
 def deform_conv_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
                    stride: List[int], padding: List[int], dilation: List[int], groups: int, deformable_groups: int,
                    precision: int) -> Tensor:
     _C.require_cuda(x, offset, mask, weight, bias)
     _dcn_check(x, offset, mask, weight, stride, padding, dilation, groups, deformable_groups)
-    xf, of, mf, wf, bf = _f32c(x), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(bias)
-    p = _dcn_params(xf, wf, stride, padding, dilation, groups, deformable_groups)
+    of, mf, wf, bf = _f32c(offset), _f32c(mask), _f32c(weight), _f32c(bias)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    xf, flags = _dcn_x(x, p, precision, False)
     out = torch.empty(dcn_output_shape(xf, wf, stride, padding, dilation), dtype=torch.float32, device=x.device)
-    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), precision)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
+    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), precision, flags)
+    ws = _ws(ws_bytes, x.device)
     with torch.cuda.device(x.device):
-        check(_C.lib().d2b_deform_conv_forward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision,
+        check(_C.lib().d2b_deform_conv_forward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision, flags,
                                                ptr(out), ptr(ws), ws_bytes, stream_ptr(x.device)),
               "deform_conv_forward")
     return out.to(x.dtype)
@@ -433,28 +449,32 @@ def _(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformab
 def deform_conv_backward_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, grad_out: Tensor,
                             stride: List[int], padding: List[int], dilation: List[int], groups: int,
                             deformable_groups: int, with_bias: bool, need_data: bool,
-                            need_weight: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                            need_weight: bool, precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     _C.require_cuda(x, offset, mask, weight, grad_out)
-    xf, of, mf, wf, gf = _f32c(x), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(grad_out)
-    p = _dcn_params(xf, wf, stride, padding, dilation, groups, deformable_groups)
+    of, mf, wf, gf = _f32c(offset), _f32c(mask), _f32c(weight), _f32c(grad_out)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    xf, flags = _dcn_x(x, p, precision, True)
     dev = x.device
     e = lambda: torch.empty((0,), dtype=torch.float32, device=dev)  # noqa: E731
-    gx = torch.empty_like(xf) if need_data else e()
+    gx = torch.empty_like(xf) if need_data else e()  # preserves channels_last strides when flags say NHWC
     go = torch.empty_like(of) if need_data else e()
     gm = torch.empty_like(mf) if (need_data and mf is not None) else e()
     gw = torch.empty_like(wf) if need_weight else e()
     gb = torch.empty((wf.shape[0],), dtype=torch.float32, device=dev) if (with_bias and need_weight) else e()
     P = lambda t: ptr(t) if t.numel() else None  # noqa: E731
+    ws_bytes = _C.lib().d2b_deform_conv_backward_workspace_bytes(C.byref(p), precision, flags, int(need_data),
+                                                                 int(need_weight))
+    ws = _ws(ws_bytes, dev)
     with torch.cuda.device(dev):
-        check(_C.lib().d2b_deform_conv_backward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(gf), C.byref(p), P(gx), P(go),
-                                                P(gm), P(gw), P(gb), None, 0, stream_ptr(dev)),
+        check(_C.lib().d2b_deform_conv_backward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(gf), C.byref(p), precision, flags,
+                                                P(gx), P(go), P(gm), P(gw), P(gb), ptr(ws), ws_bytes, stream_ptr(dev)),
               "deform_conv_backward")
     return gx, go, gm, gw, gb
 
 
 @deform_conv_backward_op.register_fake
 def _(x, offset, mask, weight, grad_out, stride, padding, dilation, groups, deformable_groups, with_bias, need_data,
-      need_weight):
+      need_weight, precision):
     e = lambda: x.new_empty((0,))  # noqa: E731
     return (torch.empty_like(x) if need_data else e(), torch.empty_like(offset) if need_data else e(),
             torch.empty_like(mask) if (need_data and mask is not None) else e(),
@@ -465,17 +485,17 @@ def _(x, offset, mask, weight, grad_out, stride, padding, dilation, groups, defo
 def _dcn_setup(ctx, inputs, output):
     x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, precision = inputs
     ctx.save_for_backward(x, offset, mask, weight)
-    ctx.args = (stride, padding, dilation, groups, dg, bias is not None)
+    ctx.args = (stride, padding, dilation, groups, dg, bias is not None, precision)
     ctx.has_mask = mask is not None
 
 
 def _dcn_bwd(ctx, grad):
     x, offset, mask, weight = ctx.saved_tensors
-    stride, padding, dilation, groups, dg, with_bias = ctx.args
+    stride, padding, dilation, groups, dg, with_bias, precision = ctx.args
     need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ctx.has_mask and ctx.needs_input_grad[2])
     need_weight = ctx.needs_input_grad[3] or (with_bias and ctx.needs_input_grad[4])
     gx, go, gm, gw, gb = deform_conv_backward_op(x, offset, mask, weight, grad, stride, padding, dilation, groups, dg,
-                                                 with_bias, need_data, need_weight)
+                                                 with_bias, need_data, need_weight, precision)
     return (gx.to(x.dtype) if need_data else None, go.to(offset.dtype) if need_data else None,
             gm.to(mask.dtype) if (need_data and ctx.has_mask) else None,
             gw.to(weight.dtype) if need_weight else None, gb if (with_bias and need_weight) else None,
@@ -539,19 +559,28 @@ _d2_lib = None
 
 
 def register_detectron2_namespace():
-    """Expose our CUDA kernels under torch.ops.detectron2.* (idempotent)."""
+    """Expose our CUDA kernels under torch.ops.detectron2.* (idempotent).
+
+    Coexistence with the reference's own extension: if `detectron2._C` (or the oracle's build of its csrc) was loaded
+    first, its TORCH_LIBRARY(detectron2) block already defined the schemas -- we then only add a CUDA kernel, and only where
+    none is registered (a CUDA build of the reference keeps its own kernels: registering a second one would raise).
+    Loading the reference extension AFTER this module is not supported by the dispatcher (its `def` would collide with
+    the schemas defined here): import detectron2 first, or set D2B_NO_D2_NAMESPACE=1 and call the d2b200::* ops."""
     global _d2_lib
-    if _d2_lib is not None:
+    if _d2_lib is not None or os.environ.get("D2B_NO_D2_NAMESPACE", "0") == "1":
         return
     _d2_lib = torch.library.Library("detectron2", "FRAGMENT")
     for name, (schema, fn) in _D2_SCHEMAS.items():
+        qual = "detectron2::" + name
         exists = True
         try:
-            torch._C._dispatch_find_schema_or_throw("detectron2::" + name, "")
+            torch._C._dispatch_find_schema_or_throw(qual, "")
         except RuntimeError:
             exists = False
         if not exists:
             _d2_lib.define(name + schema)
+        elif torch._C._dispatch_has_kernel_for_dispatch_key(qual, "CUDA"):
+            continue  # the reference's own CUDA kernel is present: leave it
         _d2_lib.impl(name, fn, "CUDA")
 
 

@@ -31,7 +31,7 @@ extern "C" {
 #define D2B_EWORKSPACE (-2)  /* workspace too small */
 #define D2B_EUNSUPPORTED (-3)
 
-#define D2B_ABI_VERSION 1
+#define D2B_ABI_VERSION 2
 int d2b_abi_version(void);
 /* compile-time facts, replaces detectron2._C.get_cuda_version / has_cuda (csrc/vision.cpp:23-49,86-88) */
 int d2b_cuda_version(void);
@@ -133,28 +133,34 @@ int d2b_box_iou_rotated(const float* boxes1, int64_t N, const float* boxes2, int
  * mask == NULL -> DCNv1, bias == NULL -> no bias.
  *   x [N,Cin,H,W], offset [N,2*DG*kh*kw,Ho,Wo] (channel 2k = dy, 2k+1 = dx of kernel point k),
  *   mask [N,DG*kh*kw,Ho,Wo], weight [Cout,Cin/G,kh,kw], bias [Cout], out [N,Cout,Ho,Wo]; all fp32.
- * precision: 0 = fp32 FFMA (parity path, <=1e-4 rel), 1 = bf16x3 split on tcgen05 (fp32-class
- * accuracy), 2 = plain bf16 tcgen05 (autocast path). */
+ */
 typedef struct {
   int N, Cin, H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups,
       deformable_groups;
 } d2b_dcn_params;
 
-/* precision: 0 = fp32 FFMA, 1 = bf16x3 split on tcgen05 (fp32-class accuracy), 2 = plain bf16 on tcgen05,
- * -1 = auto (1 when the tensor-core kernel takes the shape, else 0).  The tensor-core path needs a workspace for the
- * bf16 weight copy: d2b_deform_conv_forward_workspace_bytes(p, precision) bytes (0 for the FFMA path). */
-size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision);
+/* precision: 0 = fp32 FFMA (parity path), 1 = bf16x3 split on tcgen05 (fp32-class accuracy, <= 1e-4 rel), 2 = plain bf16
+ * operands on tcgen05 (autocast path), -1 = auto (1 when the tensor-core kernels take the shape, else 0).
+ * flags: D2B_DCN_X_NHWC -- x (and grad_x) are channels-last storage [N,H,W,Cin] (the storage of a torch.channels_last
+ *        tensor), 16-byte aligned; tensor-core precisions only.  Without it the tensor-core path re-lays x out once per call.
+ * The tensor-core path needs scratch (NHWC copy of x, pre-tiled bf16 operands): query the size first; 256-byte aligned.
+ * d2b_deform_conv_tc_shape_supported: 1 when precision 1/2 is available for the shape (backward: both gradient kernels). */
+#define D2B_DCN_X_NHWC 1
+int d2b_deform_conv_tc_shape_supported(const d2b_dcn_params* p, int backward);
+size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags);
 int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask,
                             const float* weight, const float* bias, const d2b_dcn_params* p,
-                            int precision, float* out, void* workspace, size_t workspace_bytes,
+                            int precision, int flags, float* out, void* workspace, size_t workspace_bytes,
                             void* stream);
-/* Backward.  grad_columns scratch: workspace of d2b_deform_conv_backward_workspace_bytes(p) bytes.
- * Any of the grad outputs may be NULL to skip it.  Outputs are fully written (zero-filled inside). */
-size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p);
+/* Backward.  Any of the grad outputs may be NULL to skip it.  Outputs are fully written (zero-filled inside, then
+ * accumulated); need_data = any of grad_x / grad_offset / grad_mask, need_weight = grad_weight. */
+size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags, int need_data,
+                                                int need_weight);
 int d2b_deform_conv_backward(const float* x, const float* offset, const float* mask,
                              const float* weight, const float* grad_out, const d2b_dcn_params* p,
-                             float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
-                             float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+                             int precision, int flags, float* grad_x, float* grad_offset, float* grad_mask,
+                             float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* ---- paste_masks_in_image ---------------------------------------------------------------
  * Replaces detectron2/layers/mask_ops.py:74-147 (GPU branch: every pixel of the image for every mask).
