@@ -48,6 +48,9 @@ def _declare(lib):
         "d2b_roi_align_forward_nhwc": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, i, f32p, vp]),
         "d2b_roi_pooler_forward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, i, i, i, i, i, f32p, vp]),
         "d2b_pyramid_nchw_to_nhwc": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), vp]),
+        "d2b_pyramid_nhwc_to_nchw": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), vp]),
+        "d2b_roi_align_backward_nhwc": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, i, f32p, vp]),
+        "d2b_roi_pooler_backward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
         "d2b_roi_align_rotated_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
         "d2b_nms_workspace_bytes": (sz, [i64, i]),

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/d2b200.h"
 
 #define D2B_API extern "C" __attribute__((visibility("default")))
@@ -22,3 +24,20 @@
 __host__ __device__ static inline int d2b_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;  // B200
+
+// Kernels that need more than 48 KB of dynamic shared memory must opt in once PER DEVICE.  The opt-in is remembered per
+// call site and device ordinal (lock-free bit mask), raised to the device maximum so that it covers every launch
+// configuration, and therefore never runs inside a CUDA-graph capture after the first eager call on that device.
+#define D2B_ALLOW_BIG_SMEM(kernel)                                                                              \
+  do {                                                                                                          \
+    static std::atomic<unsigned long long> done__{0ull};                                                        \
+    int dev__ = 0;                                                                                              \
+    cudaError_t e__ = cudaGetDevice(&dev__);                                                                    \
+    if (e__ != cudaSuccess) return (int)e__;                                                                    \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                      \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                                    \
+      e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
+      if (e__ != cudaSuccess) return (int)e__;                                                                  \
+      done__.fetch_or(bit__, std::memory_order_release);                                                        \
+    }                                                                                                           \
+  } while (0)

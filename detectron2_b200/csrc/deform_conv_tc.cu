@@ -918,11 +918,6 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
   }
 }
 
-template <typename F>
-int set_smem(F* kernel, int bytes) {
-  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-
 int to_nhwc(const float* x, const TC& d, float* dst, cudaStream_t stream) {
   d2b_pyramid P = {};
   P.num_levels = 1;
@@ -992,8 +987,7 @@ int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float*
   dim3 grid(d.N * d.tiles_img, (d.SG / k.gspan) * k.noct, k.ksplit);
 #define D2B_LAUNCH_K1(COLS)                                                                                            \
   {                                                                                                                    \
-    int rc = set_smem(dcn_fwd_tc_kernel<COLS>, smem_bytes);                                                            \
-    if (rc) return rc;                                                                                                 \
+    D2B_ALLOW_BIG_SMEM(dcn_fwd_tc_kernel<COLS>);                                                                       \
     dcn_fwd_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, wt, bias, d, k, split, out);     \
   }
   if (cols <= 32) D2B_LAUNCH_K1(32)
@@ -1075,8 +1069,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
       D2B_CHECK_LAUNCH();
     }
     const int smem_bytes = 2 * 4 * kTile + 128 * kGcolPitch * 4 + k2.tap_bytes + 1024 + 256;
-    int rc = set_smem(dcn_bwd_data_tc_kernel, smem_bytes);
-    if (rc) return rc;
+    D2B_ALLOW_BIG_SMEM(dcn_bwd_data_tc_kernel);
     dim3 grid(d.N * d.tiles_img, d.SG, k2.msplit);
     dcn_bwd_data_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, wt, d, k2, split, gxh, grad_offset,
                                                                   mask ? grad_mask : nullptr);
@@ -1099,8 +1092,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     dim3 grid(d.MC, k3.nsplit, d.SG * k3.noct);
 #define D2B_LAUNCH_K3(COLS)                                                                                              \
   {                                                                                                                      \
-    int rc = set_smem(dcn_bwd_weight_tc_kernel<COLS>, smem_bytes);                                                       \
-    if (rc) return rc;                                                                                                   \
+    D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_tc_kernel<COLS>);                                                                  \
     dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, d, k3, split, grad_weight); \
   }
     if (cols <= 32) D2B_LAUNCH_K3(32)

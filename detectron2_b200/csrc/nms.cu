@@ -642,8 +642,7 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   else nms_mask_kernel<false, 4><<<grid, 256, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 5. per-segment greedy scans in parallel, then compaction in global score order
-  if (smem > 40 * 1024)
-    D2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  D2B_ALLOW_BIG_SMEM(nms_scan_kernel);
   const int scan_grid = idxs ? (m < 2 * kNumSMs ? m : 2 * kNumSMs) : 1;
   nms_scan_kernel<<<scan_grid, kScanThreads, smem, stream>>>(w.maskT, pos2, w.seg_start, w.nseg, m, w.keepflag);
   D2B_CHECK_LAUNCH();

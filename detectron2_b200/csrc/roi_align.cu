@@ -687,11 +687,8 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
 static int launch_fwd(const Pyr& P, const float* rois, int K, int C, int PH, int PW, int sr, int aligned, float* out,
                       cudaStream_t stream, const float* gout = nullptr) {
   const size_t smem = sizeof(float) * (size_t)kV3Warps * kChW * kCapPx;
-  {  // per launch: the attribute is per device, and the library keeps no state (a few hundred ns of host time)
-    cudaError_t e = gout ? cudaFuncSetAttribute(roi_align_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(roi_align_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
+  if (gout) D2B_ALLOW_BIG_SMEM(roi_align_v3_kernel<true>);
+  else D2B_ALLOW_BIG_SMEM(roi_align_v3_kernel<false>);
   const int ngroup = d2b_cdiv(C, kChW);
   int groups_per_cta = ngroup;  // split the channel groups until the grid is several waves deep
   while (groups_per_cta > kV3Warps && (long long)K * d2b_cdiv(ngroup, groups_per_cta) < 24LL * kNumSMs)
@@ -904,6 +901,200 @@ static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   return D2B_OK;
 }
 
+// ------------------------------------------------------------------ channels-last (NHWC) backward
+// The transpose of the forward, formulated per FOOTPRINT PIXEL instead of per sample: the g_h x g_w sample grid of a bin
+// is a product grid, so the weight of bin (ph, pw) on pixel (y, x) is Wy[ph][y] * Wx[pw][x] with 1-D tables that are built
+// once per RoI (a pixel row is touched by 1-2 bin rows, rarely more).  A warp owns one footprint pixel at a time
+// (lane = 4 channels): it sums the <= few contributing bins from the RoI's gradient tile in shared memory and issues ONE
+// red.global.add.v4.f32 per pixel -- against 4*g*g scalar atomics per output element in the reference
+// (ROIAlignRotated_cuda.cu:311-318 / torchvision roi_align_backward) and one scalar red per pixel and channel in the NCHW
+// kernel above.  Measured ceiling of red.v4 on 256-byte runs: 5.9 TB/s (profiles/r2_microbench.txt).
+constexpr int kBwdBand = 64;     // footprint rows per pass
+constexpr int kBwdMaxFw = 320;   // footprint columns with a table; wider RoIs take the per-sample path below
+constexpr int kBwdThreads = 256;
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Per-sample scatter (taps on the fly, one red.v4 per tap): pooled sizes > 16 and footprints wider than the column table.
+__device__ void bwd_nhwc_per_sample(const RoiGeom& g, const float* __restrict__ go, float* __restrict__ gimg, int H, int W,
+                                    int C, int PH, int PW, bool lane_live) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int bins = PH * PW;
+  for (int bin = warp; bin < bins; bin += nwarps) {
+    const int ph = bin / PW, pw = bin - ph * PW;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_live) {
+      const float* q = go + (size_t)(lane * 4) * bins + bin;
+      gv = make_float4(q[0] * g.inv_count, q[bins] * g.inv_count, q[2 * bins] * g.inv_count, q[3 * bins] * g.inv_count);
+    }
+    for (int iy = 0; iy < g.gh; ++iy) {
+      const Tap1 ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+      for (int ix = 0; ix < g.gw; ++ix) {
+        const Tap1 tx = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+        if (!lane_live) continue;
+        const float w1 = ty.wl * tx.wl, w2 = ty.wl * tx.wh, w3 = ty.wh * tx.wl, w4 = ty.wh * tx.wh;
+        if (w1 != 0.f) red_add_v4(gimg + ((size_t)ty.lo * W + tx.lo) * C, make_float4(gv.x * w1, gv.y * w1, gv.z * w1, gv.w * w1));
+        if (w2 != 0.f) red_add_v4(gimg + ((size_t)ty.lo * W + tx.hi) * C, make_float4(gv.x * w2, gv.y * w2, gv.z * w2, gv.w * w2));
+        if (w3 != 0.f) red_add_v4(gimg + ((size_t)ty.hi * W + tx.lo) * C, make_float4(gv.x * w3, gv.y * w3, gv.z * w3, gv.w * w3));
+        if (w4 != 0.f) red_add_v4(gimg + ((size_t)ty.hi * W + tx.hi) * C, make_float4(gv.x * w4, gv.y * w4, gv.z * w4, gv.w * w4));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C,
+                                                                       int PH, int PW, int sr, int aligned,
+                                                                       const float* __restrict__ gout) {
+  extern __shared__ __align__(16) float gs[];  // [bin][128 ch], float4 slots XOR-swizzled with the bin index
+  __shared__ float WyT[kBwdBand * kMaxP];      // [row of the band][ph]
+  __shared__ float WxT[kBwdMaxFw * kMaxP];     // [column of the footprint][pw]
+  __shared__ unsigned char ylo[kBwdBand], yhi[kBwdBand], xlo[kBwdMaxFw], xhi[kBwdMaxFw];  // non-zero bin range per row / column
+  __shared__ RoiGeom sg;
+  __shared__ int s_xmin, s_xmax, s_ymin, s_ymax;
+
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * kNhwcCh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kBwdThreads / 32;
+  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const int H = P.H[lvl], W = P.W[lvl];
+  const int bins = PH * PW;
+  const int ncta = min(kNhwcCh, C - c0);
+  const bool lane_live = lane * 4 < ncta;
+  if (tid == 0) {
+    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+    s_xmin = s_ymin = 1 << 30;
+    s_xmax = s_ymax = -1;
+  }
+  __syncthreads();
+  const RoiGeom g = sg;
+  float* __restrict__ gimg = P.grad[lvl] + (size_t)g.b * H * W * C + c0 + lane * 4;
+  const float* __restrict__ go = gout + ((size_t)k * C + c0) * bins;
+
+  if (PH > kMaxP || PW > kMaxP) {  // pooled size beyond the tables: per-sample path
+    bwd_nhwc_per_sample(g, go, gimg, H, W, C, PH, PW, lane_live);
+    return;
+  }
+  // ---- footprint bounds (rows / columns that receive a non-zero weight)
+  if (tid < PH) {
+    int lo = 1 << 30, hi = -1;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      const Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+      if (t.wl != 0.f) { lo = min(lo, t.lo); hi = max(hi, t.lo); }
+      if (t.wh != 0.f) { lo = min(lo, t.hi); hi = max(hi, t.hi); }
+    }
+    if (hi >= 0) {
+      atomicMin(&s_ymin, lo);
+      atomicMax(&s_ymax, hi);
+    }
+  } else if (tid >= 32 && tid < 32 + PW) {
+    const int pw = tid - 32;
+    int lo = 1 << 30, hi = -1;
+    for (int ix = 0; ix < g.gw; ++ix) {
+      const Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+      if (t.wl != 0.f) { lo = min(lo, t.lo); hi = max(hi, t.lo); }
+      if (t.wh != 0.f) { lo = min(lo, t.hi); hi = max(hi, t.hi); }
+    }
+    if (hi >= 0) {
+      atomicMin(&s_xmin, lo);
+      atomicMax(&s_xmax, hi);
+    }
+  }
+  __syncthreads();
+  const int xmin = s_xmin, fw = s_xmax - s_xmin + 1, ymin = s_ymin, ymax = s_ymax;
+  if (s_xmax < 0 || ymax < 0) return;  // no sample inside the map: zero gradient
+  if (fw > kBwdMaxFw) {  // very wide footprint (block-uniform)
+    bwd_nhwc_per_sample(g, go, gimg, H, W, C, PH, PW, lane_live);
+    return;
+  }
+  // ---- column table + gradient tile
+  for (int i = tid; i < fw * kMaxP; i += kBwdThreads) WxT[i] = 0.f;
+  __syncthreads();
+  if (tid >= 32 && tid < 32 + PW) {
+    const int pw = tid - 32;
+    for (int ix = 0; ix < g.gw; ++ix) {
+      const Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+      if (t.wl != 0.f) WxT[(t.lo - xmin) * kMaxP + pw] += t.wl;
+      if (t.wh != 0.f) WxT[(t.hi - xmin) * kMaxP + pw] += t.wh;
+    }
+  }
+  for (int e = tid; e < ncta * bins; e += kBwdThreads) {  // coalesced read of [ch][bin], transposed + swizzled store
+    const int c = e / bins, bin = e - c * bins;
+    gs[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] = __ldg(go + e) * g.inv_count;
+  }
+  __syncthreads();
+  for (int x = tid; x < fw; x += kBwdThreads) {
+    int lo = 255, hi = 0;
+    for (int pw = 0; pw < PW; ++pw)
+      if (WxT[x * kMaxP + pw] != 0.f) { lo = min(lo, pw); hi = max(hi, pw + 1); }
+    xlo[x] = (unsigned char)lo;
+    xhi[x] = (unsigned char)hi;
+  }
+  // ---- bands of footprint rows
+  for (int yb = ymin; yb <= ymax; yb += kBwdBand) {
+    const int nrow = min(kBwdBand, ymax - yb + 1);
+    __syncthreads();  // previous band consumed
+    for (int i = tid; i < nrow * kMaxP; i += kBwdThreads) WyT[i] = 0.f;
+    __syncthreads();
+    if (tid < PH) {
+      for (int iy = 0; iy < g.gh; ++iy) {
+        const Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+        if (t.wl != 0.f && t.lo >= yb && t.lo < yb + nrow) WyT[(t.lo - yb) * kMaxP + tid] += t.wl;
+        if (t.wh != 0.f && t.hi >= yb && t.hi < yb + nrow) WyT[(t.hi - yb) * kMaxP + tid] += t.wh;
+      }
+    }
+    __syncthreads();
+    for (int y = tid; y < nrow; y += kBwdThreads) {
+      int lo = 255, hi = 0;
+      for (int ph = 0; ph < PH; ++ph)
+        if (WyT[y * kMaxP + ph] != 0.f) { lo = min(lo, ph); hi = max(hi, ph + 1); }
+      ylo[y] = (unsigned char)lo;
+      yhi[y] = (unsigned char)hi;
+    }
+    __syncthreads();
+    for (int yr = 0; yr < nrow; ++yr) {
+      const int pa = ylo[yr], pb = yhi[yr];
+      if (pa >= pb) continue;
+      float* __restrict__ grow = gimg + (size_t)(yb + yr) * W * C;
+      for (int xr = warp; xr < fw; xr += kWarps) {
+        const int qa = xlo[xr], qb = xhi[xr];
+        if (qa >= qb) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ph = pa; ph < pb; ++ph) {
+          const float wy = WyT[yr * kMaxP + ph];
+          for (int pw = qa; pw < qb; ++pw) {
+            const float w = wy * WxT[xr * kMaxP + pw];
+            const int bin = ph * PW + pw;
+            const float4 gv = *reinterpret_cast<const float4*>(gs + bin * kNhwcCh + (((lane ^ bin) & 31) << 2));
+            acc.x = fmaf(w, gv.x, acc.x);
+            acc.y = fmaf(w, gv.y, acc.y);
+            acc.z = fmaf(w, gv.z, acc.z);
+            acc.w = fmaf(w, gv.w, acc.w);
+          }
+        }
+        if (lane_live) red_add_v4(grow + (size_t)(xmin + xr) * C, acc);
+      }
+    }
+  }
+}
+
+static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C, int PH, int PW, int sr, int aligned,
+                           const float* gout, cudaStream_t stream) {
+  if (C % 4 != 0) return D2B_EUNSUPPORTED;
+  for (int l = 0; l < P.num_levels; ++l)
+    if ((reinterpret_cast<uintptr_t>(P.grad[l]) & 15) != 0) return D2B_EINVAL;
+  (void)N;
+  const size_t smem = sizeof(float) * kNhwcCh * (size_t)PH * PW;
+  if (smem > 160 * 1024) return D2B_EUNSUPPORTED;
+  D2B_ALLOW_BIG_SMEM(roi_align_bwd_nhwc_kernel);
+  dim3 grid(K, d2b_cdiv(C, kNhwcCh));
+  roi_align_bwd_nhwc_kernel<<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, gout);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
 // NCHW -> NHWC of every pyramid level in one launch: 32 channels x 64 pixels per CTA through a padded tile.
 struct XposeLevels {
   int num_levels;
@@ -947,7 +1138,45 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const XposeLevels L, 
   }
 }
 
+// the inverse (gradients accumulated channels-last go back to the reference's NCHW): same tiling, roles swapped
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const XposeLevels L, int C) {
+  __shared__ float tile[32][65];
+  int l = 0;
+  while (l + 1 < L.num_levels && (int)blockIdx.x >= L.tile_begin[l + 1]) ++l;
+  const int HW = L.HW[l];
+  const int hw0 = ((int)blockIdx.x - L.tile_begin[l]) * 64;
+  const int c0 = blockIdx.y * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ src = L.src[l] + (size_t)blockIdx.z * HW * C;
+  float* __restrict__ dst = L.dst[l] + (size_t)blockIdx.z * C * HW;
+  const int cq = tid & 7;
+  const int c = c0 + cq * 4;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // read: 8 lanes x float4 = 32 channels of one pixel
+    const int hwl = (tid >> 3) + half * 32;
+    const int hw = hw0 + hwl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hw < HW && c < C) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)hw * C + c));
+    tile[cq * 4 + 0][hwl] = v.x;
+    tile[cq * 4 + 1][hwl] = v.y;
+    tile[cq * 4 + 2][hwl] = v.z;
+    tile[cq * 4 + 3][hwl] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = warp; r < 32; r += 8) {  // write: lanes along the pixels of one channel plane
+    const int cc = c0 + r;
+    if (cc >= C) continue;
+    float* __restrict__ p = dst + (size_t)cc * HW;
+    const int hwa = hw0 + lane, hwb = hw0 + 32 + lane;
+    if (hwa < HW) p[hwa] = tile[r][lane];
+    if (hwb < HW) p[hwb] = tile[r][lane + 32];
+  }
+}
+
 }  // namespace
+
+static bool make_pyr(const d2b_pyramid* pyr, Pyr& P);
 
 D2B_API int d2b_roi_align_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois, int K,
                                        float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
@@ -1042,6 +1271,61 @@ D2B_API int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float
   nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
+}
+
+D2B_API int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
+  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0) return D2B_EINVAL;
+  if (N == 0 || C == 0) return D2B_OK;
+  if (C % 4 != 0) return D2B_EUNSUPPORTED;
+  XposeLevels L = {};
+  L.num_levels = pyr->num_levels;
+  int tiles = 0;
+  for (int l = 0; l < pyr->num_levels; ++l) {
+    if (!pyr->feat[l] || !dst[l] || pyr->H[l] <= 0 || pyr->W[l] <= 0) return D2B_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(pyr->feat[l]) & 15) != 0) return D2B_EINVAL;
+    L.src[l] = pyr->feat[l];
+    L.dst[l] = dst[l];
+    L.HW[l] = pyr->H[l] * pyr->W[l];
+    L.tile_begin[l] = tiles;
+    tiles += d2b_cdiv(L.HW[l], 64);
+  }
+  L.tile_begin[pyr->num_levels] = tiles;
+  if (N > 65535 || d2b_cdiv(C, 32) > 65535) return D2B_EUNSUPPORTED;
+  dim3 grid(tiles, d2b_cdiv(C, 32), N);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
+                                         int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
+  Pyr P;
+  if (!make_pyr(pyr, P) || N < 0 || C < 0) return D2B_EINVAL;
+  for (int l = 0; l < P.num_levels; ++l) {
+    if (!P.grad[l]) return D2B_EINVAL;
+    size_t bytes = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
+    if (bytes) D2B_CUDA(cudaMemsetAsync(P.grad[l], 0, bytes, (cudaStream_t)stream));
+  }
+  if (K == 0 || C == 0 || N == 0) return D2B_OK;
+  if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  return launch_bwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, grad_out, (cudaStream_t)stream);
+}
+
+D2B_API int d2b_roi_align_backward_nhwc(const float* grad_out, const float* rois, int K, float spatial_scale,
+                                        int pooled_h, int pooled_w, int N, int C, int H, int W, int sampling_ratio,
+                                        int aligned, float* grad_in, void* stream) {
+  if (!grad_in || N < 0 || C < 0 || H < 0 || W < 0) return D2B_EINVAL;
+  size_t bytes = sizeof(float) * (size_t)N * C * H * W;
+  if (bytes) D2B_CUDA(cudaMemsetAsync(grad_in, 0, bytes, (cudaStream_t)stream));
+  if (K == 0 || bytes == 0) return D2B_OK;
+  if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  Pyr P = {};
+  P.num_levels = 1;
+  P.grad[0] = grad_in;
+  P.H[0] = H;
+  P.W[0] = W;
+  P.scale[0] = spatial_scale;
+  return launch_bwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, grad_out, (cudaStream_t)stream);
 }
 
 D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,

@@ -134,34 +134,76 @@ def _(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned):
     return input.new_empty((rois.shape[0], input.shape[1], pooled_h, pooled_w))
 
 
+_NCHW_BWD_PS_PER_OUT = 40.0  # NCHW backward kernel: picoseconds per grad_out element (33 .. 44 measured)
+_NHWC_BWD_PS_PER_OUT = 8.0   # channels-last backward (one red.v4 per footprint pixel)
+
+
+def _bwd_layout(shapes_nchw, n_out: int, channels_last: bool) -> str:
+    """'cl': gradients produced channels-last in place; 'xpose': channels-last kernel into scratch + one layout-change
+    launch back to NCHW; 'nchw': the NCHW kernel.  shapes_nchw: [(n, c, h, w)] per level."""
+    c = shapes_nchw[0][1]
+    ok = c % 4 == 0 and POOLER_LAYOUT != "nchw" and all(h * w * (c // 4) < 2 ** 28 for (_, _, h, w) in shapes_nchw)
+    if not ok:
+        return "nchw"
+    if channels_last:
+        return "cl"
+    if POOLER_LAYOUT == "nhwc":
+        return "xpose"
+    feat_bytes = 4 * sum(n * c * h * w for (n, c, h, w) in shapes_nchw)
+    return "xpose" if n_out * _NHWC_BWD_PS_PER_OUT + feat_bytes * _XPOSE_PS_PER_BYTE < n_out * _NCHW_BWD_PS_PER_OUT else "nchw"
+
+
+def _from_nhwc(bufs, n: int, c: int, device):
+    """One launch: NHWC buffers -> freshly allocated NCHW tensors."""
+    outs = [torch.empty((b.shape[0], b.shape[3], b.shape[1], b.shape[2]), dtype=torch.float32, device=device) for b in bufs]
+    P = _C.Pyramid()
+    P.num_levels = len(bufs)
+    for l, b in enumerate(bufs):
+        P.feat[l] = b.data_ptr()
+        P.H[l], P.W[l] = b.shape[1], b.shape[2]
+    dst = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    check(_C.lib().d2b_pyramid_nhwc_to_nchw(C.byref(P), n, c, dst, stream_ptr(device)), "pyramid_nhwc_to_nchw")
+    return outs
+
+
 @torch.library.custom_op("d2b200::roi_align_backward", mutates_args=(), device_types="cuda")
 def roi_align_backward_op(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int, n: int,
-                          c: int, h: int, w: int, sampling_ratio: int, aligned: bool) -> Tensor:
+                          c: int, h: int, w: int, sampling_ratio: int, aligned: bool,
+                          channels_last: bool = False) -> Tensor:
     _C.require_cuda(grad, rois)
     g, r = _f32c(grad), _f32c(rois)
-    gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+    layout = _bwd_layout([(n, c, h, w)], g.numel(), channels_last) if n * c * h * w else "nchw"
     with torch.cuda.device(g.device):
-        check(_C.lib().d2b_roi_align_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w, n, c, h,
-                                              w, sampling_ratio, int(aligned), ptr(gin), stream_ptr(g.device)),
-              "roi_align_backward")
+        if layout == "nchw":
+            gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+            check(_C.lib().d2b_roi_align_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w, n, c, h,
+                                                  w, sampling_ratio, int(aligned), ptr(gin), stream_ptr(g.device)),
+                  "roi_align_backward")
+        else:
+            buf = torch.empty((n, h, w, c), dtype=torch.float32, device=g.device)
+            check(_C.lib().d2b_roi_align_backward_nhwc(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w, n, c,
+                                                       h, w, sampling_ratio, int(aligned), ptr(buf),
+                                                       stream_ptr(g.device)), "roi_align_backward_nhwc")
+            gin = buf.permute(0, 3, 1, 2) if layout == "cl" else _from_nhwc([buf], n, c, g.device)[0]
     return gin.to(grad.dtype)
 
 
 @roi_align_backward_op.register_fake
-def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio, aligned):
-    return grad.new_empty((n, c, h, w))
+def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio, aligned, channels_last=False):
+    out = grad.new_empty((n, c, h, w))
+    return out.contiguous(memory_format=torch.channels_last) if channels_last else out
 
 
 def _roi_align_setup(ctx, inputs, output):
     input, rois, spatial_scale, ph, pw, sr, aligned = inputs
     ctx.save_for_backward(rois)
-    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr, aligned)
+    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr, aligned, _is_channels_last(input))
 
 
 def _roi_align_bwd(ctx, grad):
     (rois,) = ctx.saved_tensors
-    scale, ph, pw, (n, c, h, w), sr, aligned = ctx.args
-    gin = roi_align_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    scale, ph, pw, (n, c, h, w), sr, aligned, cl = ctx.args
+    gin = roi_align_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr, aligned, cl)
     return gin, None, None, None, None, None, None
 
 
@@ -222,26 +264,35 @@ def _(feats, rois, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_leve
 @torch.library.custom_op("d2b200::roi_pooler_backward", mutates_args=(), device_types="cuda")
 def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales: List[float], pooled_h: int,
                            pooled_w: int, sampling_ratio: int, aligned: bool, min_level: int, max_level: int,
-                           canonical_level: int, canonical_box_size: float) -> List[Tensor]:
+                           canonical_level: int, canonical_box_size: float,
+                           channels_last: bool = False) -> List[Tensor]:
     _C.require_cuda(grad, rois)
     g, r = _f32c(grad), _f32c(rois)
     nl = len(scales)
     n, c = shapes[0], shapes[1]
-    grads = [torch.empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=torch.float32, device=g.device)
-             for l in range(nl)]
-    P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size)
+    hw = [(shapes[2 + 2 * l], shapes[3 + 2 * l]) for l in range(nl)]
+    layout = _bwd_layout([(n, c, h, w) for (h, w) in hw], g.numel(), channels_last) if n * c else "nchw"
+    pargs = (n, c, ptr(g), ptr(r), r.shape[0], pooled_h, pooled_w, sampling_ratio, int(aligned), stream_ptr(g.device))
     with torch.cuda.device(g.device):
-        check(_C.lib().d2b_roi_pooler_backward(C.byref(P), n, c, ptr(g), ptr(r), r.shape[0], pooled_h, pooled_w,
-                                               sampling_ratio, int(aligned), stream_ptr(g.device)),
-              "roi_pooler_backward")
+        if layout == "nchw":
+            grads = [torch.empty((n, c, h, w), dtype=torch.float32, device=g.device) for (h, w) in hw]
+            P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size)
+            check(_C.lib().d2b_roi_pooler_backward(C.byref(P), *pargs), "roi_pooler_backward")
+        else:
+            bufs = [torch.empty((n, h, w, c), dtype=torch.float32, device=g.device) for (h, w) in hw]
+            views = [b.permute(0, 3, 1, 2) for b in bufs]  # logical NCHW shape: _pyramid reads H, W from dims 2, 3
+            P = _pyramid(views, views, scales, min_level, max_level, canonical_level, canonical_box_size)
+            check(_C.lib().d2b_roi_pooler_backward_nhwc(C.byref(P), *pargs), "roi_pooler_backward_nhwc")
+            grads = views if layout == "cl" else _from_nhwc(bufs, n, c, g.device)
     return grads
 
 
 @roi_pooler_backward_op.register_fake
 def _(grad, rois, shapes, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_level, max_level, canonical_level,
-      canonical_box_size):
+      canonical_box_size, channels_last=False):
     n, c = shapes[0], shapes[1]
-    return [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
+    outs = [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
+    return [o.contiguous(memory_format=torch.channels_last) for o in outs] if channels_last else outs
 
 
 def _pooler_setup(ctx, inputs, output):
@@ -250,13 +301,14 @@ def _pooler_setup(ctx, inputs, output):
     shapes = [feats[0].shape[0], feats[0].shape[1]]
     for t in feats:
         shapes += [t.shape[2], t.shape[3]]
-    ctx.args = (shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, [t.dtype for t in feats])
+    ctx.args = (shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, [t.dtype for t in feats],
+                all(_is_channels_last(t) for t in feats))
 
 
 def _pooler_bwd(ctx, grad):
     (rois,) = ctx.saved_tensors
-    shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, dts = ctx.args
-    grads = roi_pooler_backward_op(grad, rois, shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs)
+    shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, dts, chl = ctx.args
+    grads = roi_pooler_backward_op(grad, rois, shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, chl)
     return [g.to(dt) for g, dt in zip(grads, dts)], None, None, None, None, None, None, None, None, None, None
 
 

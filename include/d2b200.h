@@ -86,6 +86,16 @@ int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const floa
  * pyr->num_levels device pointers, caller-owned).  Used by the host when a large pooler call on NCHW features is
  * cheaper as transform + channels-last pooling (detectron2_b200/ops.py). */
 int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream);
+/* The inverse: pyr->feat[l] [N,H,W,C] -> dst[l] [N,C,H,W], one launch. */
+int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream);
+/* Channels-last backward (autograd of the two forwards above): grad_in / pyr->grad[l] are [N,H,W,C] fp32, 16-byte aligned,
+ * fully written (zero-filled inside, then accumulated with one 128-bit vector reduction per footprint pixel and 4 channels).
+ * grad_out stays [K,C,PH,PW].  Same results contract as d2b_roi_align_backward / d2b_roi_pooler_backward. */
+int d2b_roi_align_backward_nhwc(const float* grad_out, const float* rois, int K, float spatial_scale,
+                                int pooled_h, int pooled_w, int N, int C, int H, int W,
+                                int sampling_ratio, int aligned, float* grad_in, void* stream);
+int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
+                                 int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream);
 
 /* ---- RoIAlign, rotated ------------------------------------------------------------------
  * Replaces torch.ops.detectron2.roi_align_rotated_forward / _backward

@@ -546,6 +546,67 @@ def test_roi_pooler_nhwc_paths_vs_reference_loop(mode, monkeypatch):
     assert ok, err
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc", "cl"])
+def test_roi_pooler_backward_layouts_vs_oracle(layout, monkeypatch):
+    # the three backward routes: NCHW kernel, channels-last kernel into scratch + layout change, channels-last in place
+    from detectron2_b200 import ops
+    from detectron2_b200.poolers import ROIPooler
+
+    g = torch.Generator().manual_seed(23)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    c = 136  # two channel slabs, the second one ragged
+    feats = [torch.randn(2, c, 200 // 2 ** i, 336 // 2 ** i, generator=g) for i in range(4)]
+    per_img = []
+    for _ in range(2):
+        s = torch.exp(torch.rand(90, generator=g) * (math.log(900) - math.log(4)) + math.log(4))
+        ctr = torch.rand(90, 2, generator=g) * torch.tensor([1344.0, 800.0])
+        ar = torch.exp((torch.rand(90, generator=g) - 0.5) * 2.0)
+        wh = torch.stack([s * ar.sqrt(), s / ar.sqrt()], 1)
+        per_img.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+    per_img[0][0] = torch.tensor([50.0, 60.0, 50.0, 60.0])        # empty box: no samples
+    per_img[1][0] = torch.tensor([-300.0, -200.0, 1700.0, 1000.0])  # larger than the image
+    per_img[1][1] = torch.tensor([200.0, 300.0, 203.0, 302.0])      # bins much smaller than a pixel
+    rois = torch.cat([torch.cat([torch.full((90, 1), float(i)), b], 1) for i, b in enumerate(per_img)])
+    for out in (7, 14):
+        _, lv = _oracle_pooler([f[:, :1] for f in feats], rois, scales, out, 0, True)
+        if layout == "cl":
+            fg = [f.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+        else:
+            monkeypatch.setattr(ops, "POOLER_LAYOUT", layout)
+            fg = [f.to(DEV).requires_grad_(True) for f in feats]
+        y = ROIPooler(out, scales, 0, "ROIAlignV2")(fg, [b.to(DEV) for b in per_img])
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go.to(DEV))
+        for l, sc in enumerate(scales):
+            inds = torch.nonzero(lv == l, as_tuple=True)[0]
+            gref = orc.roi_align_backward(go[inds], rois[inds], sc, out, out, 2, c, feats[l].shape[2], feats[l].shape[3], 0, True)
+            assert fg[l].grad.shape == gref.shape
+            if layout == "cl":
+                assert fg[l].grad.is_contiguous(memory_format=torch.channels_last)
+            ok, err = rel_close(fg[l].grad, gref, atol=3e-4)
+            assert ok, (layout, out, l, err)
+
+
+@pytest.mark.parametrize("sr", [0, 2])
+def test_roi_align_backward_wide_footprint(L, sr, monkeypatch):
+    # footprint wider than the column table of the channels-last backward: per-sample path of the same kernel
+    from detectron2_b200 import ops
+
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", "nhwc")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 8, 6, 400, generator=g)
+    rois = torch.tensor([[0.0, 2.0, 1.0, 1596.0, 22.0], [0.0, 100.0, 0.0, 1500.0, 8.0], [0.0, 40.0, 4.0, 90.0, 20.0]])
+    xg = x.to(DEV).requires_grad_(True)
+    y = L.ROIAlign((7, 7), 0.25, sr, True)(xg, rois.to(DEV))
+    ok, err = rel_close(y, orc.roi_align_forward(x, rois, 0.25, 7, 7, sr, True), atol=5e-5)
+    assert ok, err
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go.to(DEV))
+    gref = orc.roi_align_backward(go, rois, 0.25, 7, 7, 1, 8, 6, 400, sr, True)
+    ok, err = rel_close(xg.grad, gref, atol=2e-4)
+    assert ok, err
+
+
 # ------------------------------------------------------------------------------- deformable conv on tcgen05 / TMEM
 @pytest.mark.parametrize("cin,cout,h,w,grp,dg,mod,stride,prec", [
     (64, 64, 12, 20, 1, 1, False, 1, 1), (128, 128, 25, 42, 1, 1, False, 1, 1), (128, 192, 17, 23, 2, 1, True, 1, 1),
@@ -573,7 +634,45 @@ def test_deform_conv_tensor_core_vs_oracle(cin, cout, h, w, grp, dg, mod, stride
     assert (y0.cpu() - ref).abs().max().item() <= 1e-4 * scale
     if prec == 1:
         ya = ops.deform_conv_op(dev(x), dev(off), dev(mask), dev(wt), dev(bias), [stride, stride], [p, p], [1, 1], grp, dg, -1)
-        assert torch.equal(ya, y)
+        # same kernel; small maps split the reduction over kernel points (partial sums meet through red.add): not bitwise
+        assert torch.allclose(ya, y, rtol=1e-5, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("cin,cout,h,w,grp,dg,mod,stride,prec", [
+    (64, 64, 12, 20, 1, 1, False, 1, 1), (128, 128, 25, 42, 1, 1, True, 1, 1), (256, 256, 21, 19, 1, 2, True, 2, 1),
+    (128, 128, 13, 17, 8, 1, True, 1, 1), (256, 256, 9, 11, 8, 1, False, 1, 1), (128, 128, 25, 42, 1, 1, False, 1, 2),
+    (256, 256, 50, 84, 1, 1, True, 1, 1)])
+def test_deform_conv_tensor_core_backward_vs_oracle(cin, cout, h, w, grp, dg, mod, stride, prec):
+    # tcgen05 backward (data: grad_x / grad_offset / grad_mask, weight) against the oracle (torchvision CPU autograd);
+    # grp=8 with 16 / 32 channels per group exercises the super-group packing, the last row is a cfg-5 layer (R50 res4)
+    from detectron2_b200 import _C, ops
+    import ctypes as C
+
+    g = torch.Generator().manual_seed(cin * 3 + cout + h)
+    n, k, p = 2, 3, 1
+    ho, wo = (h + 2 * p - k) // stride + 1, (w + 2 * p - k) // stride + 1
+    x = torch.randn(n, cin, h, w, generator=g)
+    off = torch.randn(n, 2 * dg * k * k, ho, wo, generator=g) * 2
+    mask = torch.sigmoid(torch.randn(n, dg * k * k, ho, wo, generator=g)) if mod else None
+    wt = torch.randn(cout, cin // grp, k, k, generator=g) * (1.0 / math.sqrt(cin // grp * 9))
+    go = torch.randn(n, cout, ho, wo, generator=g)
+    gref = orc.deform_conv_backward(x, off, mask, wt, go, stride, p, 1, grp, dg, mod)
+    dev = lambda t: None if t is None else t.to(DEV)  # noqa: E731
+    prm = _C.DcnParams(n, cin, h, w, cout, k, k, stride, stride, p, p, 1, 1, grp, dg)
+    assert _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(prm), 1) == 1
+    for cl in (False, True):
+        xd = dev(x).contiguous(memory_format=torch.channels_last) if cl else dev(x)
+        gs = ops.deform_conv_backward_op(xd, dev(off), dev(mask), dev(wt), dev(go), [stride, stride], [p, p], [1, 1], grp,
+                                         dg, mod, True, True, prec)
+        tol = 1e-4 if prec == 1 else 2e-2
+        for name, a, r in zip(["gx", "goff", "gmask", "gw", "gb"], gs, gref):
+            if r is None or a.numel() == 0:
+                continue
+            scale = r.abs().max().item() + 1e-6
+            err = (a.cpu() - r).abs().max().item()
+            assert err <= tol * scale + 1e-5, (name, cl, err, scale)
+        if cl:
+            assert gs[0].is_contiguous(memory_format=torch.channels_last)
 
 
 def test_deform_conv_tensor_core_unsupported_shape_is_loud():

@@ -37,9 +37,20 @@ def timeit(fn, rep=20, warm=3):
     return a.elapsed_time(b) / rep * 1e3  # us
 
 
+def ref_pooler_grad(fg, b, out, scales, tv):
+    sizes = torch.sqrt((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))
+    lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).to(torch.int64) - 2
+    r5 = torch.cat([torch.zeros(len(b), 1, device=DEV), b], 1)
+    res = torch.zeros(len(b), fg[0].shape[1], out, out, device=DEV)
+    for l, s in enumerate(scales):
+        inds = torch.nonzero(lv == l, as_tuple=True)[0]
+        res = res.index_put((inds,), tv.roi_align(fg[l], r5[inds], (out, out), s, 0, True))
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_ops.md"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_ops.md"))
     args = ap.parse_args()
     try:
         import torchvision
@@ -49,6 +60,14 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     rows = []
+    # the reference's own CUDA kernels (rotated ops, deform conv, paste): timed in a separate process (tools/bench_ref_gpu.py)
+    import subprocess
+    refgpu = {}
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_ref_gpu.py")], timeout=600, capture_output=True)
+        refgpu = json.load(open(os.path.join(ROOT, "gpurun_out", "ref_gpu.json")))
+    except Exception as e:
+        print("reference GPU kernels not timed:", e)
 
     def add(name, ours_us, ref_us, note=""):
         rows.append((name, ours_us, ref_us, note))
@@ -101,7 +120,11 @@ def main():
         y = pooler(fg, [b])
         go = torch.randn_like(y)
         t = timeit(lambda: torch.autograd.grad(y, fg, go, retain_graph=True))
-        add("ROIPooler bwd %dx%d K=%d" % (out, out, kk), t, None)
+        trb = None
+        if tv:
+            yr_ = ref_pooler_grad(fg, b, out, scales, tv)
+            trb = timeit(lambda: torch.autograd.grad(yr_, fg, go, retain_graph=True, allow_unused=True))
+        add("ROIPooler bwd %dx%d K=%d" % (out, out, kk), t, trb, "ref = autograd of the per-level tv.roi_align loop")
     # ---- NMS
     for m, ncls, thr, tag in ((4819, 5, 0.7, "RPN test"), (8819, 5, 0.7, "RPN train"), (5000, 80, 0.5, "RetinaNet/FastRCNN"),
                               (25000, 80, 0.5, "stress")):
@@ -154,20 +177,25 @@ def main():
     rb = torch.cat([torch.rand(1000, 2, generator=gb) * 300, 1 + torch.rand(1000, 2, generator=gb) * 120,
                     (torch.rand(1000, 1, generator=gb) - 0.5) * 360], 1).to(DEV)
     t = timeit(lambda: L.pairwise_iou_rotated(rb, rb))
-    add("box_iou_rotated 1000x1000", t, None, "%.1f Mpairs/s" % (1e6 / t))
+    add("box_iou_rotated 1000x1000", t, refgpu.get("box_iou_rotated 1000x1000"), "%.1f Mpairs/s; ref = reference csrc CUDA" % (1e6 / t))
     sc = torch.rand(1000, generator=gb).to(DEV)
     t = timeit(lambda: L.nms_rotated(rb, sc, 0.5))
-    add("nms_rotated M=1000", t, None)
+    add("nms_rotated M=1000", t, refgpu.get("nms_rotated M=1000"), "ref = reference csrc CUDA (mask on GPU, scan on host)")
     xr = torch.rand(2, 256, 50, 84, generator=gb).to(DEV)
     rr = torch.cat([torch.randint(0, 2, (512, 1), generator=gb).float(), torch.rand(512, 2, generator=gb) * 800,
                     16 + torch.rand(512, 2, generator=gb) * 300, (torch.rand(512, 1, generator=gb) - 0.5) * 360], 1).to(DEV)
     opr = L.ROIAlignRotated((7, 7), 1 / 16, 0)
     t = timeit(lambda: opr(xr, rr))
-    add("roi_align_rotated fwd 512 boxes, 2x256x50x84", t, None)
+    add("roi_align_rotated fwd 512 boxes, 2x256x50x84", t, refgpu.get("roi_align_rotated fwd 512 boxes, 2x256x50x84"), "ref = reference csrc CUDA")
+    xrg = xr.clone().requires_grad_(True)
+    yr = opr(xrg, rr)
+    gor = torch.randn_like(yr)
+    t = timeit(lambda: torch.autograd.grad(yr, xrg, gor, retain_graph=True))
+    add("roi_align_rotated bwd 512 boxes, 2x256x50x84", t, refgpu.get("roi_align_rotated bwd 512 boxes, 2x256x50x84"), "ref = reference csrc CUDA")
     # ---- paste
     masks, det = d["masks"].to(DEV), d["det_boxes"][:100].to(DEV)
     t = timeit(lambda: L.paste_masks_in_image(masks, det, (800, 1333), 0.5))
-    add("paste_masks 100 x 28x28 -> 800x1333", t, None, "alg 106.96 MB -> %.0f GB/s (%.2f of HBM peak)" % (106.96e6 / t / 1e3, 106.96e6 / t / 1e3 / hbm))
+    add("paste_masks 100 x 28x28 -> 800x1333", t, refgpu.get("paste_masks 100 x 28x28 -> 800x1333"), "ref = GPU branch of the reference function (grid_sample); alg 106.96 MB -> %.0f GB/s (%.2f of HBM peak)" % (106.96e6 / t / 1e3, 106.96e6 / t / 1e3 / hbm))
     # ---- deformable conv layer sweep, N=2, k=3, pad=1
     for cin, hh, ww, grp in ((128, 100, 168, 1), (256, 50, 84, 1), (512, 25, 42, 1), (512, 100, 168, 32), (1024, 50, 84, 32),
                              (2048, 25, 42, 32)):
@@ -183,7 +211,9 @@ def main():
                 t = timeit(lambda: _ops.deform_conv_op(xx, off, None, wt, None, [1, 1], [1, 1], [1, 1], grp, 1, prec), rep=10, warm=2)
             except RuntimeError:
                 continue
-            add("deform_conv fwd C=%d %dx%d g=%d (%s)" % (cin, hh, ww, grp, tag), t, tr, "%.2f TFLOP/s" % (flops / t / 1e6))
+            rc = refgpu.get("deform_conv fwd C=%d %dx%d g=%d" % (cin, hh, ww, grp))
+            add("deform_conv fwd C=%d %dx%d g=%d (%s)" % (cin, hh, ww, grp, tag), t, tr,
+                "%.2f TFLOP/s; reference csrc CUDA: %s us" % (flops / t / 1e6, ("%.1f" % rc) if rc else "n/a"))
         xg, og, wg = xx.clone().requires_grad_(True), off.clone().requires_grad_(True), wt.clone().requires_grad_(True)
         y = L.deform_conv(xg, og, wg, 1, 1, 1, grp, 1)
         go = torch.randn_like(y)
@@ -191,7 +221,9 @@ def main():
         if tv:
             y2 = tv.deform_conv2d(xg, og, wg, None, 1, 1, 1)
             tr = timeit(lambda: torch.autograd.grad(y2, (xg, og, wg), go, retain_graph=True), rep=3, warm=1)
-        add("deform_conv bwd C=%d %dx%d g=%d (fp32)" % (cin, hh, ww, grp), t, tr if tv else None, "%.2f TFLOP/s" % (2 * flops / t / 1e6))
+        rc = refgpu.get("deform_conv bwd C=%d %dx%d g=%d" % (cin, hh, ww, grp))
+        add("deform_conv bwd C=%d %dx%d g=%d (auto: bf16x3 tcgen05)" % (cin, hh, ww, grp), t, tr if tv else None,
+            "%.2f TFLOP/s; reference csrc CUDA: %s us" % (2 * flops / t / 1e6, ("%.1f" % rc) if rc else "n/a"))
 
     with open(args.out, "w") as f:
         f.write("# Per-op timings on B200 (tools/bench_ops.py) — ours vs the reference's GPU kernels (torchvision %s CUDA ops)\n\n" %
