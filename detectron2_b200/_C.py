@@ -53,8 +53,8 @@ def _declare(lib):
         "d2b_roi_pooler_backward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
         "d2b_roi_align_rotated_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
-        "d2b_nms_workspace_bytes": (sz, [i64, i]),
-        "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64p, i64p, vp, sz, vp]),
+        "d2b_nms_workspace_bytes": (sz, [i64, i, i64]),
+        "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64, i64p, i64p, vp, sz, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
         "d2b_deform_conv_tc_shape_supported": (i, [C.POINTER(DcnParams), i]),
         "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i]),

@@ -36,7 +36,11 @@ constexpr int kNumSMs = 148;  // B200
     if (e__ != cudaSuccess) return (int)e__;                                                                    \
     const unsigned long long bit__ = 1ull << (dev__ & 63);                                                      \
     if (!(done__.load(std::memory_order_acquire) & bit__)) {                                                    \
-      e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);              \
+      cudaFuncAttributes fa__;                                                                                  \
+      e__ = cudaFuncGetAttributes(&fa__, kernel);                                                               \
+      if (e__ != cudaSuccess) return (int)e__;                                                                  \
+      e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                           \
+                                 227 * 1024 - (int)fa__.sharedSizeBytes); /* static + dynamic <= 227 KB */      \
       if (e__ != cudaSuccess) return (int)e__;                                                                  \
       done__.fetch_or(bit__, std::memory_order_release);                                                        \
     }                                                                                                           \

@@ -6,19 +6,16 @@
 // (x86-64, no FMA), which is the bit-exact parity target (see DESIGN.md "bit-exactness").
 //
 // Pipeline of d2b_nms (all on the caller's stream, no host round trip -- the reference copies the N x N/64 bitmask
-// to the host and scans it there, nms_rotated_cuda.cu:114-137):
-//   1. stable descending radix sort of the scores (CUB)                              -> order[rank]
-//   2. batched NMS: stable radix sort of the ranks by category (CUB) -> class-major order with descending scores
-//      inside each class; a single-CTA kernel derives the segment table
-//   3. gather boxes in that order, applying the batched-NMS coordinate offsets in fp32 on the fly
-//   4. IoU bitmask, 64x64 tiles, upper triangle and same-class tiles only, stored COLUMN-WORD-MAJOR maskT[w][i] so that
-//      both the tile writes and the scan's reads are coalesced
-//   5. greedy scan, one CTA per class segment in parallel: per 64-box block one thread resolves the intra-block chain
-//      (branch-free) from the diagonal word, then 16 warps OR the kept rows into the `removed` words (rows prefetched
-//      one block ahead in ping-pong registers); kept boxes are flagged at their global score rank
-//   6. single-CTA compaction of the flags in score order -> kept original indices + device-side count.
-#include <cub/device/device_radix_sort.cuh>
-
+// to the host and scans it there, nms_rotated_cuda.cu:114-137).  One memset + THREE launches, no library sort:
+//   1. nms_rank_kernel: the position of every box in the stable descending score order AND in the category-major order
+//      (descending scores inside a category) by counting -- what two stable radix sorts would give -- together with the
+//      segment bounds, the boxes gathered into that order and the coordinate range of the batched-NMS offset trick;
+//   2. nms_mask_kernel: IoU bitmask, 64x64 tiles inside the categories only, stored in word planes maskT[w][row] so that
+//      both the tile writes and the scan's reads are coalesced; memory = planes(max category size) x M words;
+//   3. nms_scan_kernel: greedy scan, one CTA per category segment in parallel: per 64-box block one thread resolves the
+//      intra-block chain (branch-free) from the diagonal word, then 16 warps OR the kept rows into the `removed` words
+//      (rows prefetched one block ahead in ping-pong registers); kept boxes are flagged at their global score rank and
+//      the last CTA to finish compacts the flags into kept original indices (0-padded) + the device-side count.
 #include "common.cuh"
 
 namespace {
@@ -184,157 +181,229 @@ __global__ void __launch_bounds__(128) box_iou_rotated_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // NMS
 // ------------------------------------------------------------------------------------------------
-// v[i] = i (value array of the radix sorts) and keepflag[i] = 0 (output of the scans), one launch
-__global__ void iota_kernel(int* __restrict__ v, unsigned char* __restrict__ keepflag, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    v[i] = i;
-    keepflag[i] = 0;
-  }
+// Control block at the start of the workspace; zeroed together with keepflag[] by ONE memset per call.
+struct NmsCtrl {
+  int nseg;          // number of category segments found
+  unsigned ticket;   // CTAs of the scan kernel that have finished
+  unsigned mx;       // ordered-uint encoding of the largest coordinate (batched-NMS offset trick)
+  unsigned mn_neg;   // ... of the negated smallest coordinate (rotated variant)
+  int error;         // a category held more boxes than the caller's bound
+  int pad[3];
+};
+
+// monotone float <-> uint map (atomicMax on floats of either sign); 0 encodes "smaller than everything"
+__device__ __forceinline__ unsigned enc_f(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// coordinate range for the batched-NMS offset trick.  mm[0] = max, mm[1] = min.
-//   axis-aligned: max over all 4 coordinates (torchvision _batched_nms_coordinate_trick: boxes.max())
-//   rotated:      max(max(cx,cy) + max(w,h)/2), min(min(cx,cy) - max(w,h)/2)   (detectron2/layers/nms.py:137-143)
+// ---- kernel 1: order by counting.  One warp per TWO boxes; the scores / categories of all boxes stream through shared
+// memory once per CTA.  For box i:
+//   grank = #{j : s_j > s_i or (s_j == s_i and j < i)}                 position in the stable descending score order
+//   pos   = #{j : c_j < c_i} + #{j : c_j == c_i and j before i}        position in the category-major order
+// which is what two stable radix sorts would produce -- but in one launch, with the segment bounds of every position and
+// the segment list as by-products.  O(M^2 / 32) warp steps: 3 us at M = 8819, ~3 ms at M = 100 000.
+constexpr int kRankTile = 2048;
+constexpr int kRankWarps = 8;
+
 template <bool ROT>
-__global__ void __launch_bounds__(1024) coord_range_kernel(const float* __restrict__ boxes, int M,
-                                                           float* __restrict__ mm) {
-  __shared__ float smax[32], smin[32];
-  float mx = -INFINITY, mn = INFINITY;
-  for (int i = threadIdx.x; i < M; i += 1024) {
-    if (ROT) {
-      const float* b = boxes + (size_t)i * 5;
-      float half = fmaxf(b[2], b[3]) / 2;
-      mx = fmaxf(mx, fmaxf(b[0], b[1]) + half);
-      mn = fminf(mn, fminf(b[0], b[1]) - half);
-    } else {
-      const float* b = boxes + (size_t)i * 4;
-      mx = fmaxf(mx, fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])));
-    }
-  }
-  for (int o = 16; o; o >>= 1) {
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    smax[threadIdx.x >> 5] = mx;
-    smin[threadIdx.x >> 5] = mn;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    mx = smax[threadIdx.x];
-    mn = smin[threadIdx.x];
-    for (int o = 16; o; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if (threadIdx.x == 0) {
-      mm[0] = mx;
-      mm[1] = mn;
-    }
-  }
-}
-
-// class id (as int32) of the box at score rank r
-__global__ void class_of_rank_kernel(const int64_t* __restrict__ idxs, const int* __restrict__ order, int M,
-                                     int* __restrict__ cls) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < M) cls[r] = (int)idxs[order[r]];
-}
-
-// sorted[p] = boxes[order[pos2 ? pos2[p] : p]]  (+ the batched-NMS coordinate offset of its class)
-template <bool ROT>
-__global__ void gather_boxes_kernel(const float* __restrict__ boxes, const int* __restrict__ order,
-                                    const int* __restrict__ pos2, const int64_t* __restrict__ idxs,
-                                    const float* __restrict__ mm, int M, float* __restrict__ sorted) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= M) return;
-  const int src = order[pos2 ? pos2[r] : r];
+__global__ void __launch_bounds__(kRankWarps * 32) nms_rank_kernel(const float* __restrict__ boxes,
+                                                                   const float* __restrict__ scores,
+                                                                   const int64_t* __restrict__ idxs, int M, int max_segment,
+                                                                   int use_range, NmsCtrl* __restrict__ ctrl,
+                                                                   int* __restrict__ grank_of_pos, int* __restrict__ orig_of_grank,
+                                                                   int* __restrict__ seg_hi_of_pos, float* __restrict__ clsf_of_pos,
+                                                                   float* __restrict__ sorted_boxes, int* __restrict__ seg_start,
+                                                                   int* __restrict__ seg_end, unsigned char* __restrict__ keepflag) {
+  __shared__ float s_score[kRankTile];
+  __shared__ long long s_cls[kRankTile];
+  __shared__ float s_mx[kRankWarps], s_mn[kRankWarps];
   constexpr int D = ROT ? 5 : 4;
-  float b[D];
-#pragma unroll
-  for (int c = 0; c < D; ++c) b[c] = boxes[(size_t)src * D + c];
-  if (idxs) {
-    if (ROT) {
-      float off = (float)idxs[src] * (mm[0] - mm[1] + 1.0f);
-      b[0] += off;
-      b[1] += off;
-    } else {
-      float off = (float)idxs[src] * (mm[0] + 1.0f);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] += off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = (blockIdx.x * kRankWarps + warp) * 2, i1 = i0 + 1;
+  const bool ok0 = i0 < M, ok1 = i1 < M;
+  const float sa = ok0 ? scores[i0] : 0.f, sb = ok1 ? scores[i1] : 0.f;
+  const long long ca = (ok0 && idxs) ? idxs[i0] : 0, cb = (ok1 && idxs) ? idxs[i1] : 0;
+  int ga = 0, gb = 0, sma = 0, smb = 0, bea = 0, beb = 0, na = 0, nb = 0;  // grank, smaller-class, before-in-class, class size
+  for (int t0 = 0; t0 < M; t0 += kRankTile) {
+    const int tn = min(kRankTile, M - t0);
+    __syncthreads();
+    for (int j = tid; j < tn; j += kRankWarps * 32) {
+      s_score[j] = scores[t0 + j];
+      s_cls[j] = idxs ? idxs[t0 + j] : 0;
+    }
+    __syncthreads();
+    for (int jl = lane; jl < tn; jl += 32) {
+      const float s = s_score[jl];
+      const long long c = s_cls[jl];
+      const int j = t0 + jl;
+      const bool fa = s > sa || (s == sa && j < i0), fb = s > sb || (s == sb && j < i1);
+      ga += fa;
+      gb += fb;
+      sma += c < ca;
+      smb += c < cb;
+      na += c == ca;
+      nb += c == cb;
+      bea += (c == ca) && fa;
+      beb += (c == cb) && fb;
     }
   }
 #pragma unroll
-  for (int c = 0; c < D; ++c) sorted[(size_t)r * D + c] = b[c];
+  for (int o = 16; o; o >>= 1) {
+    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+    sma += __shfl_xor_sync(0xffffffffu, sma, o);
+    smb += __shfl_xor_sync(0xffffffffu, smb, o);
+    na += __shfl_xor_sync(0xffffffffu, na, o);
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    bea += __shfl_xor_sync(0xffffffffu, bea, o);
+    beb += __shfl_xor_sync(0xffffffffu, beb, o);
+  }
+  float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = e ? i1 : i0;
+    if (!(e ? ok1 : ok0)) continue;
+    const int g = e ? gb : ga, sm = e ? smb : sma, be = e ? beb : bea, n = e ? nb : na;
+    const long long c = e ? cb : ca;
+    const int pos = sm + be;
+    float b[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) b[q] = boxes[(size_t)i * D + q];
+    const bool ignored = c < 0;  // negative category: the box takes part in nothing and is never kept
+    if (!ignored) {
+      if (ROT) {  // detectron2/layers/nms.py:137-143
+        const float half = fmaxf(b[2], b[3]) / 2;
+        mx = fmaxf(mx, fmaxf(b[0], b[1]) + half);
+        mn = fminf(mn, fminf(b[0], b[1]) - half);
+      } else {  // torchvision _batched_nms_coordinate_trick: boxes.max()
+        mx = fmaxf(mx, fmaxf(fmaxf(b[0], b[1]), fmaxf(b[2], b[3])));
+      }
+    }
+    if (lane == 0) {
+      grank_of_pos[pos] = g;
+      orig_of_grank[g] = i;
+      seg_hi_of_pos[pos] = (ignored || n == 1) ? pos : sm + n;  // empty column range: the mask kernel skips the row
+      clsf_of_pos[pos] = (float)c;
+#pragma unroll
+      for (int q = 0; q < D; ++q) sorted_boxes[(size_t)pos * D + q] = b[q];
+      if (ignored) {
+      } else if (n == 1) {  // alone in its category: kept, nothing to scan
+        keepflag[g] = 1;
+      } else if (be == 0) {  // first box of its category: publish the segment
+        const int slot = atomicAdd(&ctrl->nseg, 1);
+        seg_start[slot] = sm;
+        seg_end[slot] = sm + n;
+        if (n > max_segment) ctrl->error = 1;
+      }
+    }
+  }
+  if (use_range) {  // one atomic per CTA
+    if (lane == 0) {
+      s_mx[warp] = mx;
+      s_mn[warp] = mn;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 1; q < kRankWarps; ++q) {
+        mx = fmaxf(mx, s_mx[q]);
+        mn = fminf(mn, s_mn[q]);
+      }
+      if (mx > -INFINITY) atomicMax(&ctrl->mx, enc_f(mx));
+      if (ROT && mn < INFINITY) atomicMax(&ctrl->mn_neg, enc_f(-mn));
+    }
+  }
 }
 
-// 64x64 IoU tile -> one 64-bit word per row.  grid (col_block, row_block); only col_block >= row_block does work.
-// maskT[(size_t)col_block * M + row]  (column-word-major).
-// cls (optional): class of every position of the class-major order; only same-class pairs can suppress each other, and a
-// tile whose row block and column block share no class is skipped altogether (never read by the scan).
+// ---- kernel 2: IoU bitmask, one CTA per block of 64 rows (positions of the category-major order).  A row only meets the
+// later boxes of its own category: columns (row, seg_hi[row]).  Word w of row r (64 columns starting at block (r/64)+w) lives
+// at maskT[w * M + r] (word-plane-major: the CTA's writes and the scan's reads are both coalesced); `wcap` planes, sized
+// from the caller's bound on the category size -- not from M.
 // Thread layout: kSub threads per row, each testing 64/kSub columns, partial words OR-ed with warp shuffles.  The rotated
 // IoU is ~50x the work of the axis-aligned one, so it gets 8 threads per row (512-thread CTAs), the cheap one gets 4.
 template <bool ROT, int kSub>
-__global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ cls,
-                                                             int M, double thr, unsigned long long* __restrict__ maskT) {
-  const int cb = blockIdx.x, rb = blockIdx.y;
-  if (cb < rb) return;
-  if (cls && cb > rb && cls[min(rb * 64 + 63, M - 1)] != cls[cb * 64]) return;  // classes ascend with position
+__global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ seg_hi_of_pos,
+                                                             const float* __restrict__ clsf_of_pos,
+                                                             const NmsCtrl* __restrict__ ctrl, int apply_offsets, int M,
+                                                             double thr, unsigned long long* __restrict__ maskT) {
   constexpr int D = ROT ? 5 : 4;
   constexpr int kCols = 64 / kSub;
   __shared__ float cbox[64 * D];
-  __shared__ int ccls[64];
-  const int c0 = cb * 64, r0 = rb * 64;
-  const int nc = min(64, M - c0);
-  for (int t = threadIdx.x; t < nc * D; t += 64 * kSub) cbox[t] = sb[(size_t)c0 * D + t];
-  if (cls && (int)threadIdx.x < nc) ccls[threadIdx.x] = cls[c0 + threadIdx.x];
-  __syncthreads();
+  __shared__ int s_hi;
+  const int rb = blockIdx.x, r0 = rb * 64;
   const int lrow = threadIdx.x / kSub, sub = threadIdx.x % kSub;
   const int row = r0 + lrow;
   const bool row_ok = row < M;
+  const int my_hi = row_ok ? seg_hi_of_pos[row] : 0;
+  if (threadIdx.x == 0) s_hi = 0;
+  __syncthreads();
+  if (sub == 0 && row_ok) atomicMax(&s_hi, my_hi);
+  // batched-NMS coordinate offsets, fp32 like the reference: axis-aligned box + idx*(max+1); rotated centre + idx*(max-min+1)
+  float scale = 0.f;
+  if (apply_offsets) scale = ROT ? (dec_f(ctrl->mx) - (-dec_f(ctrl->mn_neg)) + 1.0f) : (dec_f(ctrl->mx) + 1.0f);
   float a[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) a[c] = sb[(size_t)(row_ok ? row : M - 1) * D + c];
-  unsigned long long bits = 0ull;
-  const int start = (cb == rb) ? lrow + 1 : 0;
-  const int my_cls = cls ? cls[row_ok ? row : M - 1] : 0;
-  const int jbeg = max(start, sub * kCols), jend = min(nc, (sub + 1) * kCols);
-  if (row_ok) {
+  if (apply_offsets) {
+    const float off = clsf_of_pos[row_ok ? row : M - 1] * scale;
+    a[0] += off;
+    a[1] += off;
+    if (!ROT) {
+      a[2] += off;
+      a[3] += off;
+    }
+  }
+  __syncthreads();
+  const int cb_last = (s_hi - 1) >> 6;
+  const float area_a = ROT ? 0.f : (a[2] - a[0]) * (a[3] - a[1]);
+  for (int cb = rb; cb <= cb_last; ++cb) {
+    const int c0 = cb * 64;
+    const int nc = min(64, M - c0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nc * D; t += 64 * kSub) {
+      const int j = t / D, q = t - j * D;
+      float v = sb[(size_t)c0 * D + t];
+      if (apply_offsets && (ROT ? q < 2 : true)) v += clsf_of_pos[c0 + j] * scale;
+      cbox[t] = v;
+    }
+    __syncthreads();
+    if (!row_ok || c0 >= my_hi) continue;  // this row's category ends before the block
+    unsigned long long bits = 0ull;
+    const int jbeg = max(sub * kCols, row + 1 - c0), jend = min(min(nc, (sub + 1) * kCols), my_hi - c0);
     if (ROT) {
       for (int j = jbeg; j < jend; ++j) {
-        if (cls && ccls[j] != my_cls) continue;
-        float iou = rotated_iou(a, cbox + j * 5);
+        const float iou = rotated_iou(a, cbox + j * 5);
         if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
       }
     } else {
-      const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
       for (int j = jbeg; j < jend; ++j) {
-        if (cls && ccls[j] != my_cls) continue;
         const float* b = cbox + j * 4;
-        float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
-        float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
-        float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
-        float inter = w * h;
-        float area_b = (b[2] - b[0]) * (b[3] - b[1]);
-        float ovr = inter / (area_a + area_b - inter);
+        const float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
+        const float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
+        const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+        const float inter = w * h;
+        const float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+        const float ovr = inter / (area_a + area_b - inter);
         if ((double)ovr > thr) bits |= 1ull << j;  // torchvision nms: strict
       }
     }
-  }
 #pragma unroll
-  for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
-  if (row_ok && sub == 0) maskT[(size_t)cb * M + row] = bits;
+    for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
+    if (sub == 0) maskT[(size_t)(cb - rb) * M + row] = bits;
+  }
 }
 
 constexpr int kScanThreads = 512;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kMaxColsPerWarp = 10;  // register-prefetched column words per warp (covers segments <= 64*16*10 = 10240)
 
-// Exclusive prefix sum of one int per thread over a 1024-thread CTA (shuffle scan inside the warps, one barrier);
-// `total` receives the sum over the CTA.  warp_tot: 32 ints of shared memory.
-__device__ __forceinline__ int block_excl_scan_1024(int v, int* __restrict__ warp_tot, int& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Exclusive prefix sum of one int per thread over the CTA (shuffle scan inside the warps, one barrier); `total` receives
+// the sum over the CTA.  warp_tot: 32 ints of shared memory.  blockDim.x <= 1024, multiple of 32.
+__device__ __forceinline__ int block_excl_scan(int v, int* __restrict__ warp_tot, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -343,7 +412,7 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int* __restrict__ war
   }
   if (lane == 31) warp_tot[warp] = inc;
   __syncthreads();
-  const int wt = warp_tot[lane];
+  const int wt = lane < nwarps ? warp_tot[lane] : 0;
   int winc = wt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -355,49 +424,33 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int* __restrict__ war
   return wbase + inc - v;
 }
 
-// segment table of the class-major order: seg_start[0..nseg], seg_start[nseg] = M.  Single CTA; every thread owns a
-// contiguous strip of positions (count, one block-wide scan, write), so the table comes out in ascending order.
-__global__ void __launch_bounds__(1024) nms_segments_kernel(const int* __restrict__ cls, int M, int* __restrict__ seg_start,
-                                                            int* __restrict__ nseg) {
-  __shared__ int warp_tot[32];
-  const int tid = threadIdx.x;
-  const int per = (M + 1023) / 1024;
-  const int p0 = min(M, tid * per), p1 = min(M, p0 + per);
-  int cnt = 0;
-  for (int p = p0; p < p1; ++p) cnt += (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1])) ? 1 : 0;
-  int total;
-  int idx = block_excl_scan_1024(cnt, warp_tot, total);
-  for (int p = p0; p < p1; ++p)
-    if (cls == nullptr ? p == 0 : (p == 0 || cls[p] != cls[p - 1])) seg_start[idx++] = p;
-  if (tid == 0) {
-    seg_start[total] = M;
-    *nseg = total;
-  }
-}
-
-// Greedy scan over the bitmask, one CTA per class segment (plain NMS = one segment covering everything).
-// dynamic smem: removed[nb] (uint64).  Per 64-box block b of the segment: (B) thread 0 resolves the intra-block chain from
-// removed[b] and the diagonal word of each row; (C) the warps OR the kept rows into the `removed` words of the later
-// column blocks of the segment.  Everything the next block needs from global memory (its diagonal words, its rows of
-// the later columns) is requested one full iteration ahead and parked in registers, so the serial chain never waits on
-// L2.  Output: keepflag[rank] = 1 for every kept box, rank = its position in the global score order.
+// ---- kernel 3: greedy scan over the bitmask, one CTA per category segment (plain NMS = one segment), then -- in the CTA
+// that finishes last -- compaction of the kept boxes in global score order.
+// dynamic smem: removed[] (uint64), one word per 64-box block of the segment.  Per block b: (B) thread 0 resolves the
+// intra-block chain from removed[b] and the diagonal word of each row; (C) the warps OR the kept rows into the `removed`
+// words of the later blocks.  Everything the next block needs from global memory (its diagonal words, its rows of the later
+// columns) is requested one full iteration ahead and parked in registers, so the serial chain never waits on L2.
 __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigned long long* __restrict__ maskT,
-                                                                   const int* __restrict__ pos2,
+                                                                   const int* __restrict__ grank_of_pos,
+                                                                   const int* __restrict__ orig_of_grank,
                                                                    const int* __restrict__ seg_start,
-                                                                   const int* __restrict__ nseg_ptr, int M,
-                                                                   unsigned char* __restrict__ keepflag) {
+                                                                   const int* __restrict__ seg_end, NmsCtrl* __restrict__ ctrl,
+                                                                   int M, unsigned char* __restrict__ keepflag,
+                                                                   long long* __restrict__ keep, long long* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];
   __shared__ __align__(16) unsigned long long s_diag[2][64];
   __shared__ unsigned long long s_kept;
+  __shared__ int warp_tot[32];
+  __shared__ unsigned s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nseg = *nseg_ptr;
+  const int nseg = ctrl->nseg;
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-    const int p0 = seg_start[seg], p1 = seg_start[seg + 1];
+    const int p0 = seg_start[seg], p1 = seg_end[seg];
     const int b0 = p0 >> 6, nb = ((p1 - 1) >> 6) + 1;  // blocks [b0, nb) of the global tiling touch this segment
     __syncthreads();                                     // previous segment done with removed[] / s_diag
-    for (int i = b0 + tid; i < nb; i += kScanThreads) removed[i] = 0ull;
+    for (int i = b0 + tid; i < nb; i += kScanThreads) removed[i - b0] = 0ull;
 
-    // rows 2*lane, 2*lane+1 of block b, column words w = b + 1 + warp + kScanWarps*c
+    // rows 2*lane, 2*lane+1 of block b, column blocks w = b + 1 + warp + kScanWarps*c (stored as word plane w - b)
     auto fetch = [&](int b, ulonglong2 (&dst)[kMaxColsPerWarp]) {
       const int r = b * 64 + 2 * lane;
 #pragma unroll
@@ -405,7 +458,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
         const int w = b + 1 + warp + kScanWarps * c;
         dst[c] = make_ulonglong2(0ull, 0ull);
         if (b < nb && w < nb) {
-          const unsigned long long* p = maskT + (size_t)w * M + r;
+          const unsigned long long* p = maskT + (size_t)(w - b) * M + r;
+          // rows outside [p0, p1) of a boundary block belong to other segments: their words are never set in `kept`
           if (r + 1 < M) {
             if ((M & 1) == 0) dst[c] = *reinterpret_cast<const ulonglong2*>(p);  // 16 B aligned when M is even
             else dst[c] = make_ulonglong2(p[0], p[1]);
@@ -417,7 +471,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
     };
     auto diag_word = [&](int b) -> unsigned long long {
       const int r = b * 64 + tid;
-      return (b < nb && tid < 64 && r >= p0 && r < p1) ? maskT[(size_t)b * M + r] : 0ull;
+      return (b < nb && tid < 64 && r >= p0 && r < p1) ? maskT[r] : 0ull;  // word plane 0
     };
     ulonglong2 bufA[kMaxColsPerWarp], bufB[kMaxColsPerWarp];
     fetch(b0, bufA);
@@ -428,15 +482,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
     // one block of 64 boxes; `cur` holds its rows (requested one iteration ago), `nxt` receives the next block's rows.
     // The two register buffers ping-pong (no copies: a copy would be a use and would expose the load latency).
     auto process = [&](int b, ulonglong2 (&cur)[kMaxColsPerWarp], ulonglong2 (&nxt)[kMaxColsPerWarp]) {
-      // rows of this block that belong to the segment
-      const int lo = max(p0 - b * 64, 0), hi = min(p1 - b * 64, 64);  // [lo, hi)
+      const int lo = max(p0 - b * 64, 0), hi = min(p1 - b * 64, 64);  // rows [lo, hi) of this block belong to the segment
       const unsigned long long vmask =
           (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
       // ---- step B: intra-block chain.  One thread, branch-free: per row the dependent path is
       //      bit test -> mask -> and/or (about four ALU latencies); the diagonal words are pre-read from shared memory
       //      sixteen rows at a time so that no load sits on the chain.
       if (tid == 0) {
-        const unsigned long long rem = removed[b];
+        const unsigned long long rem = removed[b - b0];
         unsigned rlo = (unsigned)rem, rhi = (unsigned)(rem >> 32), klo = 0u, khi = 0u;
         const ulonglong2* dg = reinterpret_cast<const ulonglong2*>(s_diag[b & 1]);
         const unsigned vlo = (unsigned)vmask, vhi = (unsigned)(vmask >> 32);
@@ -478,10 +531,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
       if (tid < 64) s_diag[(b + 1) & 1][tid] = dnext;
       dnext = diag_word(b + 2);
       // ---- publish the kept boxes of this block at their score rank
-      if (tid < 64 && ((kept >> tid) & 1ull)) {
-        const int p = b * 64 + tid;
-        keepflag[pos2 ? pos2[p] : p] = 1;
-      }
+      if (tid < 64 && ((kept >> tid) & 1ull)) keepflag[grank_of_pos[b * 64 + tid]] = 1;
       // ---- step C: OR kept rows into later column words
       const unsigned long long k0 = (kept >> (2 * lane)) & 1ull ? ~0ull : 0ull;
       const unsigned long long k1 = (kept >> (2 * lane + 1)) & 1ull ? ~0ull : 0ull;
@@ -492,18 +542,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
           unsigned long long v = (cur[c].x & k0) | (cur[c].y & k1);
           unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)v);
           unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-          if (lane == 0) removed[w] |= ((unsigned long long)hi32 << 32) | lo32;
+          if (lane == 0) removed[w - b0] |= ((unsigned long long)hi32 << 32) | lo32;
         }
       }
       // columns beyond the register-prefetched window (very large segments): plain loads
       for (int w = b + 1 + warp + kScanWarps * kMaxColsPerWarp; w < nb; w += kScanWarps) {
         const int r = b * 64 + 2 * lane;
         unsigned long long v = 0ull;
-        if (r < M) v |= maskT[(size_t)w * M + r] & k0;
-        if (r + 1 < M) v |= maskT[(size_t)w * M + r + 1] & k1;
+        if (r < M) v |= maskT[(size_t)(w - b) * M + r] & k0;
+        if (r + 1 < M) v |= maskT[(size_t)(w - b) * M + r + 1] & k1;
         unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)v);
         unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-        if (lane == 0) removed[w] |= ((unsigned long long)hi32 << 32) | lo32;
+        if (lane == 0) removed[w - b0] |= ((unsigned long long)hi32 << 32) | lo32;
       }
       __syncthreads();  // removed[], s_diag[(b+1)&1] visible; s_kept consumed
     };
@@ -512,46 +562,45 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
       if (b + 1 < nb) process(b + 1, bufB, bufA);
     }
   }
-}
-
-// keep[] = original indices of the flagged ranks, in rank (= score) order; single CTA, contiguous strip per thread.
-__global__ void __launch_bounds__(1024) nms_compact_kernel(const unsigned char* __restrict__ keepflag,
-                                                           const int* __restrict__ order, int M,
-                                                           long long* __restrict__ keep, long long* __restrict__ num_keep) {
-  __shared__ int warp_tot[32];
-  const int tid = threadIdx.x;
-  const int per = (M + 1023) / 1024;
+  // ---- the last CTA to get here compacts the flags in score order: keep[] = kept original indices, 0-padded to M
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile unsigned char* kf = keepflag;
+  const int per = (M + kScanThreads - 1) / kScanThreads;
   const int r0 = min(M, tid * per), r1 = min(M, r0 + per);
   int cnt = 0;
-  for (int r = r0; r < r1; ++r) cnt += keepflag[r] ? 1 : 0;
+  for (int r = r0; r < r1; ++r) cnt += kf[r] ? 1 : 0;
   int total;
-  int idx = block_excl_scan_1024(cnt, warp_tot, total);
+  int idx = block_excl_scan(cnt, warp_tot, total);
   for (int r = r0; r < r1; ++r)
-    if (keepflag[r]) keep[idx++] = (long long)order[r];
-  if (tid == 0) *num_keep = (long long)total;
+    if (kf[r]) keep[idx++] = (long long)orig_of_grank[r];
+  for (int r = total + tid; r < M; r += kScanThreads) keep[r] = 0;  // deterministic padding
+  if (tid == 0) *num_keep = ctrl->error ? -1LL : (long long)total;
 }
 
 struct NmsWorkspace {
-  float* sorted_scores;
-  int* iota;
-  int* order;
-  int* cls;
-  int* cls_sorted;
-  int* pos2;
-  int* seg_start;
-  int* nseg;
+  NmsCtrl* ctrl;
   unsigned char* keepflag;
+  int* grank_of_pos;
+  int* orig_of_grank;
+  int* seg_hi_of_pos;
+  float* clsf_of_pos;
+  int* seg_start;
+  int* seg_end;
   float* sorted_boxes;
-  float* mm;
   unsigned long long* maskT;
-  void* cub_temp;
-  size_t cub_bytes;
+  size_t zero_bytes;  // ctrl + keepflag are contiguous: one memset
+  int wcap;
   size_t total;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-NmsWorkspace carve(void* base, int64_t M, int rotated) {
+NmsWorkspace carve(void* base, int64_t M, int rotated, int64_t max_segment) {
   NmsWorkspace w;
   size_t off = 0;
   char* p = (char*)base;
@@ -561,37 +610,32 @@ NmsWorkspace carve(void* base, int64_t M, int rotated) {
     return r;
   };
   const size_t m = (size_t)(M > 0 ? M : 1);
-  const size_t nb = (m + 63) / 64;
-  w.sorted_scores = (float*)take(m * 4);
-  w.iota = (int*)take(m * 4);
-  w.order = (int*)take(m * 4);
-  w.cls = (int*)take(m * 4);
-  w.cls_sorted = (int*)take(m * 4);
-  w.pos2 = (int*)take(m * 4);
-  w.seg_start = (int*)take((m + 1) * 4);
-  w.nseg = (int*)take(16);
+  const size_t ms = (size_t)((max_segment <= 0 || max_segment > M) ? m : max_segment);
+  w.wcap = (int)((ms + 62) / 64 + 1);  // word planes: a row meets at most ms - 1 later boxes, starting anywhere in its block
+  w.ctrl = (NmsCtrl*)take(256);
   w.keepflag = (unsigned char*)take(m);
+  w.zero_bytes = off;
+  w.grank_of_pos = (int*)take(m * 4);
+  w.orig_of_grank = (int*)take(m * 4);
+  w.seg_hi_of_pos = (int*)take(m * 4);
+  w.clsf_of_pos = (float*)take(m * 4);
+  w.seg_start = (int*)take(m * 4);
+  w.seg_end = (int*)take(m * 4);
   w.sorted_boxes = (float*)take(m * (rotated ? 5 : 4) * 4);
-  w.mm = (float*)take(16);
-  w.maskT = (unsigned long long*)take(nb * m * 8);
-  size_t b1 = 0, b2 = 0;
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
-                                            (int*)nullptr, (int)m);
-  cub::DeviceRadixSort::SortPairs(nullptr, b2, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr,
-                                  (int)m);
-  w.cub_bytes = b1 > b2 ? b1 : b2;
-  w.cub_temp = take(w.cub_bytes);
+  w.maskT = (unsigned long long*)take((size_t)w.wcap * m * 8);
   w.total = off;
   return w;
 }
 
 }  // namespace
 
-D2B_API size_t d2b_nms_workspace_bytes(int64_t M, int flags) { return carve(nullptr, M, (flags & D2B_NMS_ROTATED) ? 1 : 0).total; }
+D2B_API size_t d2b_nms_workspace_bytes(int64_t M, int flags, int64_t max_segment) {
+  return carve(nullptr, M, (flags & D2B_NMS_ROTATED) ? 1 : 0, max_segment).total;
+}
 
 D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
-                    int flags, int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes,
-                    void* stream_) {
+                    int flags, int64_t max_segment, int64_t* keep, int64_t* num_keep, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int rotated = (flags & D2B_NMS_ROTATED) ? 1 : 0;
   const bool no_offset = (flags & D2B_NMS_NO_OFFSET) != 0;  // idxs only segment the boxes; coordinates are used as given
@@ -602,51 +646,38 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   }
   if (!boxes || !scores || !keep || !workspace) return D2B_EINVAL;
   if (M > (1 << 30)) return D2B_EUNSUPPORTED;
-  NmsWorkspace w = carve(workspace, M, rotated);
+  if (max_segment <= 0 || max_segment > M) max_segment = M;
+  NmsWorkspace w = carve(workspace, M, rotated, max_segment);
   if (workspace_bytes < w.total) return D2B_EWORKSPACE;
   const int m = (int)M, nb = (m + 63) / 64;
-  const size_t smem = (size_t)nb * sizeof(unsigned long long);
+  const size_t smem = (size_t)(w.wcap + 1) * sizeof(unsigned long long);
   if (smem > 200 * 1024) return D2B_EUNSUPPORTED;
-  // 1. global stable descending score order
-  iota_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(w.iota, w.keepflag, m);
+  D2B_CUDA(cudaMemsetAsync(w.ctrl, 0, w.zero_bytes, stream));
+  const int apply_offsets = (idxs && !no_offset) ? 1 : 0;
+  // 1. positions in the score order and in the category-major order, segments, coordinate range
+  const int rank_grid = d2b_cdiv(m, 2 * kRankWarps);
+  if (rotated)
+    nms_rank_kernel<true><<<rank_grid, kRankWarps * 32, 0, stream>>>(boxes, scores, idxs, m, (int)max_segment, apply_offsets, w.ctrl,
+                                                                     w.grank_of_pos, w.orig_of_grank, w.seg_hi_of_pos,
+                                                                     w.clsf_of_pos, w.sorted_boxes, w.seg_start, w.seg_end, w.keepflag);
+  else
+    nms_rank_kernel<false><<<rank_grid, kRankWarps * 32, 0, stream>>>(boxes, scores, idxs, m, (int)max_segment, apply_offsets, w.ctrl,
+                                                                      w.grank_of_pos, w.orig_of_grank, w.seg_hi_of_pos,
+                                                                      w.clsf_of_pos, w.sorted_boxes, w.seg_start, w.seg_end, w.keepflag);
   D2B_CHECK_LAUNCH();
-  size_t cub_bytes = w.cub_bytes;
-  D2B_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, scores, w.sorted_scores, w.iota, w.order, m,
-                                                     0, 32, stream));
-  // 2. batched: class-major order (stable, so scores stay descending inside each class) + segment table
-  const int* cls_sorted = nullptr;
-  const int* pos2 = nullptr;
-  if (idxs) {
-    if (!no_offset) {
-      if (rotated) coord_range_kernel<true><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
-      else coord_range_kernel<false><<<1, 1024, 0, stream>>>(boxes, m, w.mm);
-      D2B_CHECK_LAUNCH();
-    }
-    class_of_rank_kernel<<<d2b_cdiv(m, 256), 256, 0, stream>>>(idxs, w.order, m, w.cls);
-    D2B_CHECK_LAUNCH();
-    cub_bytes = w.cub_bytes;
-    D2B_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, w.cls, w.cls_sorted, w.iota, w.pos2, m, 0, 32, stream));
-    cls_sorted = w.cls_sorted;
-    pos2 = w.pos2;
-  }
-  nms_segments_kernel<<<1, 1024, 0, stream>>>(cls_sorted, m, w.seg_start, w.nseg);
+  // 2. IoU bitmask inside the categories (coordinate offsets of the reference's batched-NMS trick applied in fp32)
+  if (rotated)
+    nms_mask_kernel<true, 8><<<nb, 512, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
+                                                     iou_threshold, w.maskT);
+  else
+    nms_mask_kernel<false, 4><<<nb, 256, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
+                                                      iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
-  // 3. boxes in that order (coordinate offsets of the reference's batched-NMS trick applied in fp32)
-  const int64_t* off_idxs = no_offset ? nullptr : idxs;
-  if (rotated) gather_boxes_kernel<true><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, off_idxs, w.mm, m, w.sorted_boxes);
-  else gather_boxes_kernel<false><<<d2b_cdiv(m, 256), 256, 0, stream>>>(boxes, w.order, pos2, off_idxs, w.mm, m, w.sorted_boxes);
-  D2B_CHECK_LAUNCH();
-  // 4. IoU bitmask (same-class tiles only)
-  dim3 grid(nb, nb);
-  if (rotated) nms_mask_kernel<true, 8><<<grid, 512, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
-  else nms_mask_kernel<false, 4><<<grid, 256, 0, stream>>>(w.sorted_boxes, cls_sorted, m, iou_threshold, w.maskT);
-  D2B_CHECK_LAUNCH();
-  // 5. per-segment greedy scans in parallel, then compaction in global score order
+  // 3. per-segment greedy scans in parallel + compaction in global score order by the last CTA
   D2B_ALLOW_BIG_SMEM(nms_scan_kernel);
   const int scan_grid = idxs ? (m < 2 * kNumSMs ? m : 2 * kNumSMs) : 1;
-  nms_scan_kernel<<<scan_grid, kScanThreads, smem, stream>>>(w.maskT, pos2, w.seg_start, w.nseg, m, w.keepflag);
-  D2B_CHECK_LAUNCH();
-  nms_compact_kernel<<<1, 1024, 0, stream>>>(w.keepflag, w.order, m, (long long*)keep, (long long*)num_keep);
+  nms_scan_kernel<<<scan_grid, kScanThreads, smem, stream>>>(w.maskT, w.grank_of_pos, w.orig_of_grank, w.seg_start, w.seg_end,
+                                                             w.ctrl, m, w.keepflag, (long long*)keep, (long long*)num_keep);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

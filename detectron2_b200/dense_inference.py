@@ -106,9 +106,9 @@ def dense_detector_inference(anchors: List[torch.Tensor], pred_scores: List[torc
     offs = torch.where(use_trick[:, None] & live, offs, torch.zeros_like(offs))
     nms_boxes = torch.where(live[..., None], boxes + offs[..., None], zeros).reshape(-1, 4)
     nms_scores = torch.where(live, scores, torch.full_like(scores, float("-inf"))).reshape(-1)
-    cat_ids = torch.where(live, classes + batch_idx[:, None] * (ncls + 1),
-                          torch.full_like(classes, ncls) + batch_idx[:, None] * (ncls + 1)).reshape(-1)
-    keep, num_keep = ops.nms_fixed(nms_boxes, nms_scores, cat_ids, float(nms_thresh), False, apply_offsets=False)
+    cat_ids = torch.where(live, classes + batch_idx[:, None] * (ncls + 1), torch.full_like(classes, -1)).reshape(-1)  # -1: ignored
+    keep, num_keep = ops.nms_fixed(nms_boxes, nms_scores, cat_ids, float(nms_thresh), False, apply_offsets=False,
+                                   max_segment=max(t, 1))
 
     # 5. per-image first max_detections_per_image of the score-ordered keep list (:308), on the device
     m = keep.shape[0]

@@ -76,7 +76,6 @@ def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], i
     device = boxes[0].device
     ncls = scores[0].shape[1] - 1
     kreg = boxes[0].shape[1] // 4
-    dummy_cls = ncls  # category of empty candidate slots (per image)
     cand_boxes, cand_scores, cand_cat, cand_flat, cand_live, n_cand_l, row_maps, offs_l = [], [], [], [], [], [], [], []
     caps = []
     for i in range(num_images):
@@ -102,7 +101,7 @@ def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], i
         cb = torch.where(live[:, None], cb, torch.zeros_like(cb))
         cand_boxes.append(cb)
         cand_scores.append(torch.where(live, top_s, torch.full_like(top_s, float("-inf"))))
-        cand_cat.append(torch.where(live, cls + i * (ncls + 1), torch.full_like(cls, dummy_cls + i * (ncls + 1))))
+        cand_cat.append(torch.where(live, cls + i * (ncls + 1), torch.full_like(cls, -1)))  # -1: slot ignored by the NMS kernels
         cand_flat.append(top_f)
         cand_live.append(live)
         # torchvision batched_nms offsets of this image: class * (max coordinate of its candidate boxes + 1), fp32
@@ -118,7 +117,10 @@ def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], i
     all_cat = torch.cat(cand_cat, dim=0)
     all_live = torch.cat(cand_live, dim=0)
     img_of = torch.cat([torch.full((caps[i],), i, dtype=torch.int64, device=device) for i in range(num_images)])
-    keep, num_keep = ops.nms_fixed(nms_boxes, all_scores, all_cat, float(nms_thresh), False, apply_offsets=False)
+    # a (image, class) category holds at most one candidate per proposal row
+    max_segment = max([min(caps[i], boxes[i].shape[0]) for i in range(num_images)] + [1])
+    keep, num_keep = ops.nms_fixed(nms_boxes, all_scores, all_cat, float(nms_thresh), False, apply_offsets=False,
+                                   max_segment=max_segment)
 
     # per-image first topk of the score-ordered keep list, on the device
     m = keep.shape[0]

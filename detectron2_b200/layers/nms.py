@@ -17,25 +17,16 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     return ops.nms_op(boxes, scores, None, float(iou_threshold), False)
 
 
-def _batched_nms_vanilla(boxes, scores, idxs, iou_threshold, rotated):
-    keep_mask = torch.zeros_like(scores, dtype=torch.bool)
-    for class_id in torch.unique(idxs):
-        curr = torch.where(idxs == class_id)[0]
-        keep = ops.nms_op(boxes[curr], scores[curr], None, float(iou_threshold), rotated)
-        keep_mask[curr[keep]] = True
-    keep_indices = torch.where(keep_mask)[0]
-    return keep_indices[scores[keep_indices].sort(descending=True, stable=True)[1]]
-
-
 def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
     """Per-category NMS (layers/nms.py:11-22 -> torchvision batched_nms, always on boxes.float())."""
     assert boxes.shape[-1] == 4
     boxes = boxes.float()
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
-    if boxes.numel() > _TRICK_MAX_NUMEL:
-        return _batched_nms_vanilla(boxes, scores, idxs, iou_threshold, False)
-    return ops.nms_op(boxes, scores, idxs, float(iou_threshold), False)
+    # torchvision leaves the coordinate-offset trick for a per-class Python loop above 25 000 boxes (ops/boxes.py
+    # _batched_nms_vanilla: raw coordinates, one nms + host sync per class).  Same results in ONE call here: the
+    # categories only segment the boxes (D2B_NMS_NO_OFFSET).
+    return ops.nms_op(boxes, scores, idxs, float(iou_threshold), False, boxes.numel() <= _TRICK_MAX_NUMEL)
 
 
 def batched_nms_fixed(boxes, scores, idxs, iou_threshold):

@@ -371,34 +371,39 @@ roi_align_rotated_op.register_autograd(_roi_rot_bwd, setup_context=_roi_rot_setu
 
 # =================================================================================== NMS / rotated IoU
 def nms_fixed(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,
-              rotated: bool, apply_offsets: bool = True) -> Tuple[Tensor, Tensor]:
-    """Sync-free NMS: returns (keep[M] int64 padded buffer, num_keep[1] int64 device tensor).
-    keep[:num_keep] are the kept original indices in descending-score order.  CUDA-graph friendly."""
+              rotated: bool, apply_offsets: bool = True, max_segment: int = 0) -> Tuple[Tensor, Tensor]:
+    """Sync-free NMS: returns (keep[M] int64, 0-padded, num_keep[1] int64 device tensor).
+    keep[:num_keep] are the kept original indices in descending-score order.  CUDA-graph friendly.
+    max_segment: upper bound on the boxes per category when the caller knows one (sizes the IoU bitmask; 0 = M).  If a
+    category exceeds it num_keep comes back as -1 (the eager op below raises)."""
     _C.require_cuda(boxes, scores, idxs)
     b, s = _f32c(boxes), _f32c(scores)
     ix = None if idxs is None else idxs.to(dtype=torch.int64).contiguous()
     m = b.shape[0]
     keep = torch.empty((m,), dtype=torch.int64, device=b.device)
-    num = torch.zeros((1,), dtype=torch.int64, device=b.device)
+    num = torch.zeros((1,), dtype=torch.int64, device=b.device) if m == 0 else torch.empty((1,), dtype=torch.int64, device=b.device)
     if m:
         flags = (1 if rotated else 0) | (0 if apply_offsets else 2)  # D2B_NMS_ROTATED | D2B_NMS_NO_OFFSET
-        ws_bytes = _C.lib().d2b_nms_workspace_bytes(m, flags)
+        ws_bytes = _C.lib().d2b_nms_workspace_bytes(m, flags, int(max_segment))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=b.device)
         with torch.cuda.device(b.device):
-            check(_C.lib().d2b_nms(ptr(b), ptr(s), ptr(ix), m, float(iou_threshold), flags, ptr(keep),
+            check(_C.lib().d2b_nms(ptr(b), ptr(s), ptr(ix), m, float(iou_threshold), flags, int(max_segment), ptr(keep),
                                    ptr(num), ptr(ws), ws_bytes, stream_ptr(b.device)), "nms")
     return keep, num
 
 
 @torch.library.custom_op("d2b200::nms", mutates_args=(), device_types="cuda")
-def nms_op(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float, rotated: bool) -> Tensor:
-    keep, num = nms_fixed(boxes, scores, idxs, iou_threshold, rotated)
+def nms_op(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float, rotated: bool,
+           apply_offsets: bool = True) -> Tensor:
+    keep, num = nms_fixed(boxes, scores, idxs, iou_threshold, rotated, apply_offsets)
     n = int(num.item())  # the one host sync: the reference contract returns an exactly-sized tensor
+    if n < 0:
+        raise RuntimeError("nms: a category exceeded the max_segment bound")
     return keep[:n].clone()
 
 
 @nms_op.register_fake
-def _(boxes, scores, idxs, iou_threshold, rotated):
+def _(boxes, scores, idxs, iou_threshold, rotated, apply_offsets=True):
     ctx = torch.library.get_ctx()
     n = ctx.new_dynamic_size()
     return boxes.new_empty((n,), dtype=torch.int64)

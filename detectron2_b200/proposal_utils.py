@@ -76,11 +76,12 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
     nonempty = ((x2 - x1) > min_box_size) & ((y2 - y1) > min_box_size)
     valid = finite & nonempty
 
-    # 3. one NMS over all images: category = image * L + level; removed boxes go to a dummy category with score -inf
+    # 3. one NMS over all images: category = image * L + level; removed boxes get category -1 (ignored by the kernels).
+    #    Every category holds at most `pre_nms_topk` boxes: the IoU bitmask and the scans stay linear in the batch size.
     img_of = batch_idx[:, None].expand(n, t)
     cat_ids = img_of * num_levels + levels[None, :]
-    dummy = num_images * num_levels
-    cat_ids = torch.where(valid, cat_ids, torch.full_like(cat_ids, dummy)).reshape(-1)
+    cat_ids = torch.where(valid, cat_ids, torch.full_like(cat_ids, -1)).reshape(-1)
+    max_segment = max(x.shape[1] for x in scores_l)
     flat_boxes = torch.where(valid[..., None], clipped, torch.zeros_like(clipped)).reshape(-1, 4)
     flat_scores = torch.where(valid, scores.float(), torch.full_like(scores, float("-inf"), dtype=torch.float32)).reshape(-1)
     # torchvision's batched_nms (reached per image from proposal_utils.py:121) shifts the boxes of level l by
@@ -94,7 +95,8 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
         nms_boxes = torch.where(valid[..., None], nms_boxes, torch.zeros_like(nms_boxes)).reshape(-1, 4)
     else:
         nms_boxes = flat_boxes
-    keep, num_keep = ops.nms_fixed(nms_boxes, flat_scores, cat_ids, float(nms_thresh), False, apply_offsets=False)
+    keep, num_keep = ops.nms_fixed(nms_boxes, flat_scores, cat_ids, float(nms_thresh), False, apply_offsets=False,
+                                   max_segment=max_segment)
 
     # 4. per-image top post_nms_topk of the score-ordered keep list (:129), on the device
     m = keep.shape[0]

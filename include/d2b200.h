@@ -122,13 +122,20 @@ int d2b_roi_align_rotated_backward(const float* grad_out, const float* rois, int
  * flags: D2B_NMS_ROTATED selects the rotated variant; D2B_NMS_NO_OFFSET makes `idxs` pure segment ids -- the
  *        coordinates are used as given (the caller already applied whatever offsets it wants, e.g. the per-image offsets
  *        of a multi-image RPN batch, detectron2_b200/proposal_utils.py).
- * workspace: d2b_nms_workspace_bytes(M, flags) bytes of device scratch. */
+ *   idxs   negative category ids mark boxes to be IGNORED: they suppress nothing and are never kept (callers with a
+ *          fixed-capacity candidate list park their empty slots there instead of compacting the list).
+ * max_segment: upper bound on the number of boxes of one category (0 = unknown, i.e. M).  It sizes the IoU bitmask
+ *        ((max_segment/64 + 2) words per box instead of M/64), so a batched caller that knows its per-category limit (RPN:
+ *        pre_nms_topk per image and level) keeps memory and work linear in the batch size.  If a category turns out larger,
+ *        nothing is written out of bounds and num_keep is set to -1.
+ *   keep   entries past num_keep are 0.
+ * workspace: d2b_nms_workspace_bytes(M, flags, max_segment) bytes of device scratch. */
 #define D2B_NMS_ROTATED 1
 #define D2B_NMS_NO_OFFSET 2
-size_t d2b_nms_workspace_bytes(int64_t M, int flags);
+size_t d2b_nms_workspace_bytes(int64_t M, int flags, int64_t max_segment);
 int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
-            double iou_threshold, int flags, int64_t* keep, int64_t* num_keep, void* workspace,
-            size_t workspace_bytes, void* stream);
+            double iou_threshold, int flags, int64_t max_segment, int64_t* keep, int64_t* num_keep,
+            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Rotated-box IoU --------------------------------------------------------------------
  * Replaces torch.ops.detectron2.box_iou_rotated (csrc/vision.cpp:117,

@@ -27,9 +27,10 @@ def test_header_symbols_exported():
 def test_workspace_queries_run_on_host():
     from detectron2_b200 import _C
 
-    small, big = _C.lib().d2b_nms_workspace_bytes(1000, 0), _C.lib().d2b_nms_workspace_bytes(10000, 0)
+    small, big = _C.lib().d2b_nms_workspace_bytes(1000, 0, 0), _C.lib().d2b_nms_workspace_bytes(10000, 0, 0)
     assert 0 < small < big
-    assert _C.lib().d2b_nms_workspace_bytes(10000, 1) > big  # 5 floats per rotated box
+    assert _C.lib().d2b_nms_workspace_bytes(10000, 1, 0) > big  # 5 floats per rotated box
+    assert _C.lib().d2b_nms_workspace_bytes(10000, 0, 1000) < big / 4  # bounded categories: bitmask linear in M
 
 
 def test_surface_matches_reference_names():

@@ -205,6 +205,49 @@ def test_batched_nms_vanilla_path_large(L):
     assert torch.equal(got, ki[scores[ki].sort(descending=True, stable=True)[1]])
 
 
+def test_batched_nms_100k_stress_one_call(L):
+    # BASELINE cfg-4 stress case: 100 000 boxes, 80 classes -- one call (the reference loops over the classes in Python)
+    g = torch.Generator().manual_seed(7)
+    m = 100000
+    boxes, scores = _random_boxes(g, m, 1333), torch.rand(m, generator=g)
+    idxs = torch.randint(0, 80, (m,), generator=g)
+    got = L.batched_nms(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), 0.5).cpu()
+    keep_mask = torch.zeros(m, dtype=torch.bool)
+    for c in idxs.unique():
+        cur = torch.where(idxs == c)[0]
+        keep_mask[cur[orc.nms(boxes[cur], scores[cur], 0.5)]] = True
+    ki = torch.where(keep_mask)[0]
+    assert torch.equal(got, ki[scores[ki].sort(descending=True, stable=True)[1]])
+
+
+def test_nms_ignored_slots_padding_and_category_bound():
+    from detectron2_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    m = 3000
+    boxes, scores = _random_boxes(g, m, 600), torch.rand(m, generator=g)
+    idxs = torch.randint(0, 40, (m,), generator=g)
+    dead = torch.rand(m, generator=g) < 0.4
+    idxs_dead = torch.where(dead, torch.full_like(idxs, -1), idxs)
+    # ignored slots (category -1) == the same call on the live boxes only
+    keep, num = ops.nms_fixed(boxes.to(DEV), scores.to(DEV), idxs_dead.to(DEV), 0.5, False, apply_offsets=False, max_segment=200)
+    n = int(num.item())
+    live_idx = torch.nonzero(~dead, as_tuple=True)[0]
+    parts = []
+    for c in idxs[live_idx].unique():
+        cur = live_idx[idxs[live_idx] == c]
+        parts.append(cur[orc.nms(boxes[cur], scores[cur], 0.5)])
+    ref = torch.cat(parts)
+    ref = ref[torch.sort(scores[ref], descending=True, stable=True).indices]
+    # ties between categories: the stable global score order breaks them by original index
+    ref = torch.tensor(sorted(ref.tolist(), key=lambda i: (-scores[i].item(), i)))
+    assert n == ref.numel() and torch.equal(keep[:n].cpu(), ref)
+    assert (keep[n:] == 0).all()  # deterministic padding
+    # a category larger than the caller's bound is reported, not silently mishandled
+    _, num_bad = ops.nms_fixed(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), 0.5, False, apply_offsets=False, max_segment=8)
+    assert int(num_bad.item()) == -1
+
+
 # ------------------------------------------------------------------------------- rotated IoU / NMS
 def test_rotated_golden_bit_exact(L, golden):
     d = golden("rotated")

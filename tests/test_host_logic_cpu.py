@@ -12,7 +12,7 @@ from oracle import oracle as orc
 T = torch.from_numpy
 
 
-def oracle_nms_fixed(boxes, scores, idxs, iou_threshold, rotated, apply_offsets=True):
+def oracle_nms_fixed(boxes, scores, idxs, iou_threshold, rotated, apply_offsets=True, max_segment=0):
     """Same contract as detectron2_b200.ops.nms_fixed (padded keep buffer + count), computed by the CPU oracle."""
     assert not rotated
     boxes, scores = boxes.float().contiguous(), scores.float().contiguous()
@@ -24,7 +24,10 @@ def oracle_nms_fixed(boxes, scores, idxs, iou_threshold, rotated, apply_offsets=
     else:  # D2B_NMS_NO_OFFSET: idxs are pure segment ids, coordinates used as given
         parts = []
         for c in torch.unique(idxs):
+            if c < 0:  # ignored slots
+                continue
             ii = torch.nonzero(idxs == c, as_tuple=True)[0]
+            assert max_segment <= 0 or len(ii) <= max_segment, "caller's max_segment bound violated"
             parts.append(ii[orc.nms(boxes[ii], scores[ii], iou_threshold)])
         kept = torch.cat(parts).sort().values if parts else torch.zeros(0, dtype=torch.int64)
         kept = kept[torch.sort(scores[kept], descending=True, stable=True).indices]  # score order, lower index first on ties

@@ -50,7 +50,8 @@ def test_two_rank_gloo_aggregation():
         assert p.exitcode == 0
     assert red == [15.0, 40.0]  # element-wise max over ranks
     assert set(gathered[0]).isdisjoint(gathered[1])  # replicas never share an image
-    assert abs(value - 2 * 50 / 0.015) < 1e-6  # whole-job images/s from the slowest rank's time
+    # whole-job images/s from the slowest rank's time: 2 ranks x 50 steps x IMGS_PER_GPU images per step
+    assert abs(value - 2 * 50 * 2 / 0.015) < 1e-6
 
 
 def test_single_rank_is_identity():
@@ -58,4 +59,5 @@ def test_single_rank_is_identity():
     import bench
 
     assert bench.max_over_ranks([3.0, 4.0], None, torch.device("cpu")) == [3.0, 4.0]
-    assert bench.aggregate_throughput(1, 10, 1000.0) == 10.0
+    assert bench.aggregate_throughput(1, 10, 1000.0) == 10.0 * bench.IMGS_PER_GPU
+    assert bench.aggregate_throughput(1, 10, 1000.0, images_per_step=1) == 10.0
