@@ -53,6 +53,8 @@ def _declare(lib):
         "d2b_roi_pooler_backward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
         "d2b_roi_align_rotated_backward": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
+        "d2b_roi_align_rotated_forward_nhwc": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),
+        "d2b_roi_align_rotated_backward_nhwc": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
         "d2b_nms_workspace_bytes": (sz, [i64, i, i64]),
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64, i64p, i64p, vp, sz, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
@@ -124,3 +126,77 @@ def has_cuda():
 
 def get_compiler_version():
     return "nvcc (sm_100a)"
+
+
+# --- the five pybind deform-conv entry points of detectron2._C (csrc/vision.cpp:90-102, deform_conv.h:116-375) -----------
+# Same positional signatures and the same in-place contract: outputs are CALLER-ALLOCATED tensors written in place
+# (detectron2/layers/deform_conv.py:43-45,97-98,121,219,250-254); `columns` / `ones` are scratch tensors of the reference's
+# im2col design that a fused implementation has no use for.  With this module bound as `detectron2._C`, the reference's own
+# `_DeformConv` / `_ModulatedDeformConv` autograd Functions run unchanged on our kernels.
+# Note the reference's argument order for DCNv1: kW, kH, dW, dH, padW, padH, dilW, dilH (width first, deform_conv.py:69-76).
+DCN_PRECISION = -1  # -1 auto (bf16x3 tcgen05 when the shape is taken, else fp32 FFMA); see include/d2b200.h
+
+
+def _into(dst, src):
+    if dst.shape != src.shape:
+        dst.resize_(src.shape)  # the reference resizes its outputs as well (deform_conv_cuda.cu:340-344)
+    dst.copy_(src)
+
+
+def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilW, dilH, group,
+                        deformable_group, im2col_step):
+    from . import ops
+
+    if weight.shape[3] != kW or weight.shape[2] != kH:
+        raise RuntimeError("deform_conv_forward: kernel size does not match the weight tensor")
+    y = ops.deform_conv_op(input, offset, None, weight, None, [dH, dW], [padH, padW], [dilH, dilW], group, deformable_group,
+                           DCN_PRECISION)
+    _into(output, y)
+    return 1
+
+
+def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH, padW,
+                               padH, dilW, dilH, group, deformable_group, im2col_step):
+    from . import ops
+
+    gx, go, _, _, _ = ops.deform_conv_backward_op(input, offset, None, weight, gradOutput, [dH, dW], [padH, padW],
+                                                  [dilH, dilW], group, deformable_group, False, True, False, DCN_PRECISION)
+    _into(gradInput, gx)
+    _into(gradOffset, go)
+    return 1
+
+
+def deform_conv_backward_filter(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW, padH, dilW,
+                                dilH, group, deformable_group, scale, im2col_step):
+    from . import ops
+
+    _, _, _, gw, _ = ops.deform_conv_backward_op(input, offset, None, gradWeight.new_empty(gradWeight.shape), gradOutput,
+                                                 [dH, dW], [padH, padW], [dilH, dilW], group, deformable_group, False,
+                                                 False, True, DCN_PRECISION)
+    gradWeight.add_(gw, alpha=float(scale))  # the reference accumulates scale * dW into the caller's buffer
+    return 1
+
+
+def modulated_deform_conv_forward(input, weight, bias, ones, offset, mask, output, columns, kernel_h, kernel_w, stride_h,
+                                  stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, with_bias):
+    from . import ops
+
+    y = ops.deform_conv_op(input, offset, mask, weight, bias if with_bias else None, [stride_h, stride_w], [pad_h, pad_w],
+                           [dilation_h, dilation_w], group, deformable_group, DCN_PRECISION)
+    _into(output, y)
+
+
+def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, columns, grad_input, grad_weight, grad_bias,
+                                   grad_offset, grad_mask, grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                                   pad_w, dilation_h, dilation_w, group, deformable_group, with_bias):
+    from . import ops
+
+    gx, go, gm, gw, gb = ops.deform_conv_backward_op(input, offset, mask, weight, grad_output, [stride_h, stride_w],
+                                                     [pad_h, pad_w], [dilation_h, dilation_w], group, deformable_group,
+                                                     bool(with_bias), True, True, DCN_PRECISION)
+    _into(grad_input, gx)
+    _into(grad_offset, go)
+    _into(grad_mask, gm)
+    grad_weight.add_(gw)  # accumulated into the caller's zero-initialised buffers (deform_conv_cuda.cu:1196-1203)
+    if with_bias:
+        grad_bias.add_(gb)

@@ -1095,6 +1095,117 @@ static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   return D2B_OK;
 }
 
+// ------------------------------------------------------------------ rotated RoIAlign on channels-last storage
+// The sample grid of a rotated RoI is not a product grid, so the axis-aligned tables do not apply; what carries over is the
+// layout: lane = 4 channels, a warp owns one bin at a time, the taps of a sample (4 pixel offsets + 4 weights, built once
+// per CTA into shared memory) are warp-uniform, every tap is one 512-byte LDG.128 (forward) or one red.global.add.v4.f32
+// (backward) per warp.  The reference runs one thread per output element with scalar taps and, in the backward, 4*g*g
+// scalar atomics per element (ROIAlignRotated_cuda.cu:143-222, :224-323).
+constexpr int kRotMaxTap = 1024;  // (bins x samples) entries of the shared tap table; larger grids compute taps on the fly
+
+template <bool BWD>
+__global__ void __launch_bounds__(kBwdThreads) roi_align_rot_nhwc_kernel(const float* __restrict__ in, float* __restrict__ gin,
+                                                                       const float* __restrict__ rois, float scale, int C,
+                                                                       int H, int W, int PH, int PW, int sr,
+                                                                       const float* __restrict__ gout,
+                                                                       float* __restrict__ out) {
+  extern __shared__ __align__(16) float tile[];  // forward: [128 ch][bins | 1] results; backward: [bin][128 ch] swizzled grads
+  __shared__ Tap2 taps[kRotMaxTap];
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * kNhwcCh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kBwdThreads / 32;
+  const RoiGeom g = load_geom<true>(rois + (size_t)k * 6, scale, PH, PW, sr, 1);
+  const int bins = PH * PW;
+  const int spb = g.gh * g.gw;
+  const int ncta = min(kNhwcCh, C - c0);
+  const bool lane_live = lane * 4 < ncta;
+  const bool tab = (long long)bins * spb <= kRotMaxTap;
+  const int pitch = bins | 1;
+  if (tab) {
+    for (int i = tid; i < bins * spb; i += kBwdThreads) {
+      const int bin = i / spb, sidx = i - bin * spb;
+      const int ph = bin / PW, pw = bin - ph * PW, iy = sidx / g.gw, ix = sidx - iy * g.gw;
+      float y, x;
+      rot_xy(g, ph, pw, iy, ix, y, x);
+      taps[i] = make_tap2(y, x, H, W);
+    }
+  }
+  if (BWD) {
+    const float* __restrict__ go = gout + ((size_t)k * C + c0) * bins;
+    for (int e = tid; e < ncta * bins; e += kBwdThreads) {
+      const int c = e / bins, bin = e - c * bins;
+      tile[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] = __ldg(go + e) / g.count_raw;
+    }
+  }
+  __syncthreads();
+  const size_t img = (size_t)g.b * H * W * C + c0 + (lane_live ? lane * 4 : 0);
+  for (int bin = warp; bin < bins; bin += kWarps) {
+    const int ph = bin / PW, pw = bin - ph * PW;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BWD) gv = *reinterpret_cast<const float4*>(tile + bin * kNhwcCh + (((lane ^ bin) & 31) << 2));
+    for (int sidx = 0; sidx < spb; ++sidx) {
+      Tap2 t;
+      if (tab) t = taps[bin * spb + sidx];
+      else {
+        const int iy = sidx / g.gw, ix = sidx - iy * g.gw;
+        float y, x;
+        rot_xy(g, ph, pw, iy, ix, y, x);
+        t = make_tap2(y, x, H, W);
+      }
+      if (t.p1 < 0) continue;  // warp-uniform
+      if (BWD) {
+        if (lane_live) {
+          float* __restrict__ gb = gin + img;
+          red_add_v4(gb + (size_t)t.p1 * C, make_float4(gv.x * t.w1, gv.y * t.w1, gv.z * t.w1, gv.w * t.w1));
+          red_add_v4(gb + (size_t)t.p2 * C, make_float4(gv.x * t.w2, gv.y * t.w2, gv.z * t.w2, gv.w * t.w2));
+          red_add_v4(gb + (size_t)t.p3 * C, make_float4(gv.x * t.w3, gv.y * t.w3, gv.z * t.w3, gv.w * t.w3));
+          red_add_v4(gb + (size_t)t.p4 * C, make_float4(gv.x * t.w4, gv.y * t.w4, gv.z * t.w4, gv.w * t.w4));
+        }
+      } else {
+        const float* __restrict__ fb = in + img;
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)t.p1 * C));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)t.p2 * C));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)t.p3 * C));
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)t.p4 * C));
+        acc.x += t.w1 * v1.x + t.w2 * v2.x + t.w3 * v3.x + t.w4 * v4.x;
+        acc.y += t.w1 * v1.y + t.w2 * v2.y + t.w3 * v3.y + t.w4 * v4.y;
+        acc.z += t.w1 * v1.z + t.w2 * v2.z + t.w3 * v3.z + t.w4 * v4.z;
+        acc.w += t.w1 * v1.w + t.w2 * v2.w + t.w3 * v3.w + t.w4 * v4.w;
+      }
+    }
+    if (!BWD) {
+      float* __restrict__ o = tile + lane * pitch + bin;  // odd pitch: the 32 lanes hit 32 banks
+      o[0] = acc.x * g.inv_count;
+      o[32 * pitch] = acc.y * g.inv_count;
+      o[64 * pitch] = acc.z * g.inv_count;
+      o[96 * pitch] = acc.w * g.inv_count;
+    }
+  }
+  if (!BWD) {
+    __syncthreads();
+    float* __restrict__ obase = out + ((size_t)k * C + c0) * bins;
+    for (int i = tid; i < ncta * bins; i += kBwdThreads) {  // channel-major write-out: contiguous runs of the NCHW-shaped output
+      const int cl = i / bins, bl = i - cl * bins;
+      obase[i] = tile[((cl & 3) * 32 + (cl >> 2)) * pitch + bl];
+    }
+  }
+}
+
+template <bool BWD>
+static int launch_rot_nhwc(const float* in, float* gin, const float* rois, int K, float scale, int C, int H, int W, int PH,
+                           int PW, int sr, const float* gout, float* out, cudaStream_t stream) {
+  if (C % 4 != 0 || (long long)H * W * (C / 4) >= (1LL << 28)) return D2B_EUNSUPPORTED;
+  const size_t smem = sizeof(float) * 128 * (size_t)(BWD ? PH * PW : ((PH * PW) | 1));
+  if (smem > 150 * 1024) return D2B_EUNSUPPORTED;
+  D2B_ALLOW_BIG_SMEM(roi_align_rot_nhwc_kernel<BWD>);
+  dim3 grid(K, d2b_cdiv(C, kNhwcCh));
+  roi_align_rot_nhwc_kernel<BWD><<<grid, kBwdThreads, smem, stream>>>(in, gin, rois, scale, C, H, W, PH, PW, sr, gout, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
 // NCHW -> NHWC of every pyramid level in one launch: 32 channels x 64 pixels per CTA through a padded tile.
 struct XposeLevels {
   int num_levels;
@@ -1295,6 +1406,29 @@ D2B_API int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float
   nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
+}
+
+D2B_API int d2b_roi_align_rotated_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois, int K,
+                                               float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                               float* out, void* stream) {
+  if (K == 0 || C == 0) return D2B_OK;
+  if (!input || !rois || !out || N <= 0 || H <= 0 || W <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0) return D2B_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(input) & 15) != 0) return D2B_EINVAL;
+  return launch_rot_nhwc<false>(input, nullptr, rois, K, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, nullptr,
+                                out, (cudaStream_t)stream);
+}
+
+D2B_API int d2b_roi_align_rotated_backward_nhwc(const float* grad_out, const float* rois, int K, float spatial_scale,
+                                                int pooled_h, int pooled_w, int N, int C, int H, int W,
+                                                int sampling_ratio, float* grad_in, void* stream) {
+  if (!grad_in || N < 0 || C < 0 || H < 0 || W < 0) return D2B_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(grad_in) & 15) != 0) return D2B_EINVAL;
+  size_t bytes = sizeof(float) * (size_t)N * C * H * W;
+  if (bytes) D2B_CUDA(cudaMemsetAsync(grad_in, 0, bytes, (cudaStream_t)stream));
+  if (K == 0 || bytes == 0) return D2B_OK;
+  if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
+  return launch_rot_nhwc<true>(nullptr, grad_in, rois, K, spatial_scale, C, H, W, pooled_h, pooled_w, sampling_ratio, grad_out,
+                               nullptr, (cudaStream_t)stream);
 }
 
 D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,

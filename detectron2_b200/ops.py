@@ -315,19 +315,44 @@ def _pooler_bwd(ctx, grad):
 roi_pooler_op.register_autograd(_pooler_bwd, setup_context=_pooler_setup)
 
 
+_ROT_NCHW_PS = (30.0, 64.0)  # rotated NCHW kernels: picoseconds per output element (forward, backward)
+_ROT_NHWC_PS = (10.0, 16.0)  # rotated channels-last kernels
+
+
+def _rot_layout(n: int, c: int, h: int, w: int, n_out: int, channels_last: bool, bwd: bool) -> str:
+    if c % 4 != 0 or POOLER_LAYOUT == "nchw" or h * w * (c // 4) >= 2 ** 28:
+        return "nchw"
+    if channels_last:
+        return "cl"
+    if POOLER_LAYOUT == "nhwc":
+        return "xpose"
+    i = 1 if bwd else 0
+    return "xpose" if n_out * _ROT_NHWC_PS[i] + 4 * n * c * h * w * _XPOSE_PS_PER_BYTE < n_out * _ROT_NCHW_PS[i] else "nchw"
+
+
 @torch.library.custom_op("d2b200::roi_align_rotated", mutates_args=(), device_types="cuda")
 def roi_align_rotated_op(input: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
                          sampling_ratio: int) -> Tensor:
     _roi_common(input, rois, 6)
-    x, r = _f32c(input), _f32c(rois)
+    x, r = input.to(dtype=torch.float32), _f32c(rois)
     n, c, h, w = x.shape
     k = r.shape[0]
     out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=x.device)
     if out.numel():
+        layout = _rot_layout(n, c, h, w, out.numel(), _is_channels_last(x) and x.data_ptr() % 16 == 0, False)
         with torch.cuda.device(x.device):
-            check(_C.lib().d2b_roi_align_rotated_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h,
-                                                         pooled_w, sampling_ratio, ptr(out), stream_ptr(x.device)),
-                  "roi_align_rotated_forward")
+            if layout == "nchw":
+                x = x.contiguous()
+                check(_C.lib().d2b_roi_align_rotated_forward(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h,
+                                                             pooled_w, sampling_ratio, ptr(out), stream_ptr(x.device)),
+                      "roi_align_rotated_forward")
+            else:
+                if layout == "xpose":
+                    x = x.contiguous()
+                    x = _to_nhwc([x], _pyramid([x], None, [spatial_scale], 0, 0, 0, 1.0), n, c, x.device)[0]
+                check(_C.lib().d2b_roi_align_rotated_forward_nhwc(ptr(x), n, c, h, w, ptr(r), k, spatial_scale, pooled_h,
+                                                                  pooled_w, sampling_ratio, ptr(out),
+                                                                  stream_ptr(x.device)), "roi_align_rotated_forward_nhwc")
     return out.to(input.dtype)
 
 
@@ -338,32 +363,42 @@ def _(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
 
 @torch.library.custom_op("d2b200::roi_align_rotated_backward", mutates_args=(), device_types="cuda")
 def roi_align_rotated_backward_op(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
-                                  n: int, c: int, h: int, w: int, sampling_ratio: int) -> Tensor:
+                                  n: int, c: int, h: int, w: int, sampling_ratio: int,
+                                  channels_last: bool = False) -> Tensor:
     _C.require_cuda(grad, rois)
     g, r = _f32c(grad), _f32c(rois)
-    gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+    layout = _rot_layout(n, c, h, w, g.numel(), channels_last, True) if n * c * h * w else "nchw"
     with torch.cuda.device(g.device):
-        check(_C.lib().d2b_roi_align_rotated_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w,
-                                                      n, c, h, w, sampling_ratio, ptr(gin), stream_ptr(g.device)),
-              "roi_align_rotated_backward")
+        if layout == "nchw":
+            gin = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+            check(_C.lib().d2b_roi_align_rotated_backward(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h, pooled_w,
+                                                          n, c, h, w, sampling_ratio, ptr(gin), stream_ptr(g.device)),
+                  "roi_align_rotated_backward")
+        else:
+            buf = torch.empty((n, h, w, c), dtype=torch.float32, device=g.device)
+            check(_C.lib().d2b_roi_align_rotated_backward_nhwc(ptr(g), ptr(r), r.shape[0], spatial_scale, pooled_h,
+                                                               pooled_w, n, c, h, w, sampling_ratio, ptr(buf),
+                                                               stream_ptr(g.device)), "roi_align_rotated_backward_nhwc")
+            gin = buf.permute(0, 3, 1, 2) if layout == "cl" else _from_nhwc([buf], n, c, g.device)[0]
     return gin.to(grad.dtype)
 
 
 @roi_align_rotated_backward_op.register_fake
-def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio):
-    return grad.new_empty((n, c, h, w))
+def _(grad, rois, spatial_scale, pooled_h, pooled_w, n, c, h, w, sampling_ratio, channels_last=False):
+    out = grad.new_empty((n, c, h, w))
+    return out.contiguous(memory_format=torch.channels_last) if channels_last else out
 
 
 def _roi_rot_setup(ctx, inputs, output):
     input, rois, spatial_scale, ph, pw, sr = inputs
     ctx.save_for_backward(rois)
-    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr)
+    ctx.args = (spatial_scale, ph, pw, tuple(input.shape), sr, _is_channels_last(input))
 
 
 def _roi_rot_bwd(ctx, grad):
     (rois,) = ctx.saved_tensors
-    scale, ph, pw, (n, c, h, w), sr = ctx.args
-    return roi_align_rotated_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr), None, None, None, None, None
+    scale, ph, pw, (n, c, h, w), sr, cl = ctx.args
+    return roi_align_rotated_backward_op(grad, rois, scale, ph, pw, n, c, h, w, sr, cl), None, None, None, None, None
 
 
 roi_align_rotated_op.register_autograd(_roi_rot_bwd, setup_context=_roi_rot_setup)

@@ -107,6 +107,14 @@ int d2b_roi_align_rotated_forward(const float* input, int N, int C, int H, int W
 int d2b_roi_align_rotated_backward(const float* grad_out, const float* rois, int K,
                                    float spatial_scale, int pooled_h, int pooled_w, int N, int C,
                                    int H, int W, int sampling_ratio, float* grad_in, void* stream);
+/* Channels-last variants (input / grad_in are [N,H,W,C] fp32 storage, 16-byte aligned, C % 4 == 0); out / grad_out stay
+ * [K,C,PH,PW].  Same results contract. */
+int d2b_roi_align_rotated_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois,
+                                       int K, float spatial_scale, int pooled_h, int pooled_w,
+                                       int sampling_ratio, float* out, void* stream);
+int d2b_roi_align_rotated_backward_nhwc(const float* grad_out, const float* rois, int K,
+                                        float spatial_scale, int pooled_h, int pooled_w, int N, int C,
+                                        int H, int W, int sampling_ratio, float* grad_in, void* stream);
 
 /* ---- NMS --------------------------------------------------------------------------------
  * Replaces torchvision::nms reached from detectron2/layers/nms.py:5-22 (nms, batched_nms) and

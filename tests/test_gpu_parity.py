@@ -117,6 +117,37 @@ def test_roi_align_rotated_golden(L, golden):
         assert torch.equal(y2, y.detach())
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc", "cl"])
+@pytest.mark.parametrize("c,ph,pw,sr", [(132, 7, 7, 0), (64, 14, 14, 2), (8, 17, 5, 0)])
+def test_roi_align_rotated_layouts_vs_oracle(L, layout, c, ph, pw, sr, monkeypatch):
+    # rotated RoIAlign: NCHW kernels, channels-last kernels via layout change, channels-last in place -- fwd and bwd.
+    # (17, 5) with adaptive sampling exceeds the shared tap table: taps on the fly.
+    from detectron2_b200 import ops
+
+    g = torch.Generator().manual_seed(c + ph + sr)
+    n, h, w, k = 2, 40, 60, 70
+    x = torch.randn(n, c, h, w, generator=g)
+    rois = torch.cat([torch.randint(0, n, (k, 1), generator=g).float(), torch.rand(k, 1, generator=g) * 480,
+                      torch.rand(k, 1, generator=g) * 320, 4 + torch.rand(k, 2, generator=g) * 250,
+                      (torch.rand(k, 1, generator=g) - 0.5) * 400], 1)
+    rois[0, 3:5] = 0.0                                   # empty box
+    rois[1] = torch.tensor([1.0, 240, 160, 900, 700, 30])  # larger than the map
+    ref = orc.roi_align_rotated_forward(x, rois, 0.125, ph, pw, sr)
+    go = torch.randn(k, c, ph, pw, generator=g)
+    gref = orc.roi_align_rotated_backward(go, rois, 0.125, ph, pw, n, c, h, w, sr)
+    if layout == "cl":
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    else:
+        monkeypatch.setattr(ops, "POOLER_LAYOUT", layout)
+        xd = x.to(DEV).requires_grad_(True)
+    y = L.ROIAlignRotated((ph, pw), 0.125, sr)(xd, rois.to(DEV))
+    ok, err = rel_close(y, ref, atol=5e-5)
+    assert ok, err
+    y.backward(go.to(DEV))
+    ok, err = rel_close(xd.grad, gref, atol=3e-4)
+    assert ok, err
+
+
 def test_roi_align_rotated_kats(L):
     # /root/reference/tests/layers/test_roi_align_rotated.py:30-71,102-105,127-172
     img = torch.arange(25, dtype=torch.float32).reshape(5, 5)
