@@ -64,6 +64,9 @@ def _declare(lib):
         "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i, i, i]),
         "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, f32p, f32p,
                                          f32p, f32p, vp, sz, vp]),
+        "d2b_deform_conv_fused_forward": (i, [f32p, f32p, f32p, f32p, f32p, i, C.POINTER(DcnParams), i, i, f32p, vp, sz, vp]),
+        "d2b_deform_conv_fused_backward": (i, [f32p, f32p, f32p, f32p, i, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, f32p,
+                                               f32p, vp, sz, vp]),
         "d2b_paste_masks": (i, [f32p, f32p, i, i, i, i, f, u8p, vp]),
     }
     for name, (res, args) in sig.items():

@@ -376,13 +376,14 @@ int d2b_deform_conv_tc_supported(const d2b_dcn_params* p);
 int d2b_deform_conv_tc_bwd_supported(const d2b_dcn_params* p);
 size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc);
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                               const float* bias, const d2b_dcn_params* p, int precision, int x_nhwc, float* out,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               const float* scale, const float* shift, int relu, const d2b_dcn_params* p, int precision,
+                               int tcflags, float* out, void* workspace, size_t workspace_bytes, void* stream);
 size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int need_data, int need_weight);
 int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                                const float* grad_out, const d2b_dcn_params* p, int precision, int x_nhwc,
-                                float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                const float* grad_out, const float* scale, const float* y_saved, int relu,
+                                const d2b_dcn_params* p, int precision, int tcflags, float* grad_x, float* grad_offset,
+                                float* grad_mask, float* grad_weight, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 // precision: 0 = fp32 FFMA, 1 = bf16x3 on tcgen05, 2 = bf16 on tcgen05, -1 = auto (1 when the tensor-core kernels take
 // the shape, else 0 -- both are fp32-class, so "auto" never lowers accuracy)
@@ -406,8 +407,8 @@ D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const f
   if (precision < -1 || precision > 2) return D2B_EINVAL;
   if (precision == -1) precision = d2b_deform_conv_tc_supported(p) ? 1 : 0;
   if (precision != 0)  // no silent precision / path change: an unsupported shape is reported, not rerouted
-    return d2b_deform_conv_forward_tc(x, offset, mask, weight, bias, p, precision, (flags & D2B_DCN_X_NHWC) ? 1 : 0, out,
-                                      workspace, workspace_bytes, stream);
+    return d2b_deform_conv_forward_tc(x, offset, mask, weight, nullptr, bias, 0, p, precision,
+                                      (flags & D2B_DCN_X_NHWC) ? 1 : 0, out, workspace, workspace_bytes, stream);
   if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;  // the FFMA parity path reads NCHW planes
   dim3 grid(d2b_cdiv(d.HoWo, BN), d2b_cdiv(d.opg, BM), d.N * d.G);
   dcn_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, offset, mask, weight, bias, d, out);
@@ -441,8 +442,9 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
     }
   }
   if (precision != 0)
-    return d2b_deform_conv_backward_tc(x, offset, mask, weight, grad_out, p, precision, (flags & D2B_DCN_X_NHWC) ? 1 : 0,
-                                       grad_x, grad_offset, grad_mask, grad_weight, workspace, workspace_bytes, stream_);
+    return d2b_deform_conv_backward_tc(x, offset, mask, weight, grad_out, nullptr, nullptr, 0, p, precision,
+                                       (flags & D2B_DCN_X_NHWC) ? 1 : 0, grad_x, grad_offset, grad_mask, grad_weight,
+                                       workspace, workspace_bytes, stream_);
   if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;
   const size_t nx = (size_t)d.N * d.Cin * d.H * d.W, noff = (size_t)d.N * d.DG * 2 * d.KK * d.HoWo;
   const size_t nm = (size_t)d.N * d.DG * d.KK * d.HoWo, nw = (size_t)d.Cout * d.cpg * d.KK;
@@ -480,4 +482,35 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
     D2B_CHECK_LAUNCH();
   }
   return D2B_OK;
+}
+
+// ---- conv2 of a DeformBottleneckBlock in one pass (detectron2/modeling/backbone/resnet.py:305-318):
+//   offset_mask [N, 3*DG*kh*kw, Ho, Wo] is the raw output of conv2_offset -- the chunk / cat / sigmoid of :307-311 happen
+//   while the sampling taps are built;  y = relu(conv * scale + shift) -- FrozenBatchNorm folded to scale / shift, or
+//   scale = NULL and shift = bias -- happens in the TMEM epilogue.  Tensor-core precisions only.
+D2B_API int d2b_deform_conv_fused_forward(const float* x, const float* offset_mask, const float* weight, const float* scale,
+                                          const float* shift, int relu, const d2b_dcn_params* p, int precision, int flags,
+                                          float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Dims d;
+  if (!make_dims(p, d)) return D2B_EINVAL;
+  if (d.N == 0) return D2B_OK;
+  if (!x || !offset_mask || !weight || !out || precision == 0 || precision < -1 || precision > 2) return D2B_EINVAL;
+  if (precision == -1) precision = 1;
+  return d2b_deform_conv_forward_tc(x, offset_mask, nullptr, weight, scale, shift, relu, p, precision,
+                                    ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, out, workspace, workspace_bytes, stream);
+}
+
+// grad_out is the gradient of y; y itself (saved by the caller) gates the ReLU.  grad_offset_mask [N, 3*DG*kh*kw, Ho, Wo].
+D2B_API int d2b_deform_conv_fused_backward(const float* x, const float* offset_mask, const float* weight, const float* scale,
+                                           int relu, const float* y, const float* grad_out, const d2b_dcn_params* p,
+                                           int precision, int flags, float* grad_x, float* grad_offset_mask,
+                                           float* grad_weight, void* workspace, size_t workspace_bytes, void* stream) {
+  Dims d;
+  if (!make_dims(p, d)) return D2B_EINVAL;
+  if (precision == 0 || precision < -1 || precision > 2) return D2B_EINVAL;
+  if (precision == -1) precision = 1;
+  if (d.N > 0 && (!x || !offset_mask || !weight || !grad_out)) return D2B_EINVAL;
+  return d2b_deform_conv_backward_tc(x, offset_mask, nullptr, weight, grad_out, scale, y, relu, p, precision,
+                                     ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, grad_x, grad_offset_mask, nullptr, grad_weight,
+                                     workspace, workspace_bytes, stream);
 }

@@ -49,6 +49,18 @@ struct TC {
   int stages_img;                  // 64-pixel stages per image (K3)
   int MC;                          // macro-chunks (pairs of units) per super-group
   int nks;                         // 64-wide K stages over the super-group's output channels (K2)
+  // offset / mask addressing: element strides between images, element offset of the mask block relative to `mask`
+  // pointer (fused layout: offset and mask logits live in ONE [N, 3*DG*KK, Ho, Wo] tensor, backbone/resnet.py:307-312)
+  long long off_bs, mask_bs;
+  int mask_sigmoid;                // mask values are logits: sigmoid applied while the taps are built
+};
+
+// optional epilogue of the forward (and its transpose in the backward): y = relu(acc * scale[oc] + shift[oc]) --
+// the FrozenBatchNorm / bias + ReLU that follow conv2 of a DeformBottleneckBlock (backbone/resnet.py:313-318)
+struct Epi {
+  const float* scale;  // may be null (1)
+  const float* shift;  // may be null (0)
+  int relu;
 };
 
 struct K1P { int BN, noct, gspan, nkp, ksplit, S, tap_bytes, stage_bytes, red; };  // red: k-split partial sums meet through red.add
@@ -90,7 +102,17 @@ bool make_tc(const d2b_dcn_params* p, TC& d) {
   d.MC = (d.U + 1) / 2;
   d.nks = d.ops / 64;
   if ((long long)d.N * d.tiles_img > 0x7fffffffLL) return false;
+  d.off_bs = (long long)d.DG * 2 * d.KK * d.HoWo;
+  d.mask_bs = (long long)d.DG * d.KK * d.HoWo;
+  d.mask_sigmoid = 0;
   return true;
+}
+
+// fused offset+mask tensor: returns the mask pointer inside it and switches the strides / sigmoid on
+const float* use_fused_offset_mask(TC& d, const float* offset_mask) {
+  d.off_bs = d.mask_bs = (long long)d.DG * 3 * d.KK * d.HoWo;
+  d.mask_sigmoid = 1;
+  return offset_mask + (size_t)d.DG * 2 * d.KK * d.HoWo;
 }
 
 int largest_tile(int n) {  // largest of {256,...,16} dividing n
@@ -166,12 +188,13 @@ __device__ __forceinline__ int4 make_tap(const TC& d, const float* __restrict__ 
   if (p < d.HoWo) {
     const int ho = p / d.Wo, wo = p - ho * d.Wo;
     const int ki = kp / d.kw, kj = kp - ki * d.kw;
-    const size_t ob = ((size_t)(b * d.DG + dg) * 2 * d.KK) * d.HoWo;
+    const size_t ob = (size_t)b * d.off_bs + ((size_t)dg * 2 * d.KK) * d.HoWo;
     const float oh = __ldg(offset + ob + (size_t)(2 * kp) * d.HoWo + p);       // deform_conv_cuda_kernel.cu:263-269
     const float ow = __ldg(offset + ob + (size_t)(2 * kp + 1) * d.HoWo + p);
     const float hf = (float)(ho * d.sh - d.ph + ki * d.dh) + oh;
     const float wf = (float)(wo * d.sw - d.pw + kj * d.dw) + ow;
-    const float m = mask ? __ldg(mask + ((size_t)(b * d.DG + dg) * d.KK + kp) * d.HoWo + p) : 1.f;
+    float m = mask ? __ldg(mask + (size_t)b * d.mask_bs + ((size_t)dg * d.KK + kp) * d.HoWo + p) : 1.f;
+    if (d.mask_sigmoid) m = 1.f / (1.f + expf(-m));  // resnet.py:311 mask.sigmoid()
     if (hf > -1.f && wf > -1.f && hf < (float)d.H && wf < (float)d.W) {
       const float hfl = floorf(hf), wfl = floorf(wf);
       const int hl = (int)hfl, wl = (int)wfl;
@@ -202,10 +225,16 @@ __device__ __forceinline__ void load_corners(const float* __restrict__ xc, int C
 }
 
 __device__ __forceinline__ void interp4(const Taps4& t, float w0, float w1, float w2, float w3, float (&v)[4]) {
-  v[0] = fmaf(w3, t.v3.x, fmaf(w2, t.v2.x, fmaf(w1, t.v1.x, w0 * t.v0.x)));
-  v[1] = fmaf(w3, t.v3.y, fmaf(w2, t.v2.y, fmaf(w1, t.v1.y, w0 * t.v0.y)));
-  v[2] = fmaf(w3, t.v3.z, fmaf(w2, t.v2.z, fmaf(w1, t.v1.z, w0 * t.v0.z)));
-  v[3] = fmaf(w3, t.v3.w, fmaf(w2, t.v2.w, fmaf(w1, t.v1.w, w0 * t.v0.w)));
+  const F2 z = f2_pack(0.f, 0.f), p0 = f2_pack(w0, w0), p1 = f2_pack(w1, w1), p2 = f2_pack(w2, w2), p3 = f2_pack(w3, w3);
+  F2 a = f2_fma(p0, f2_pack(t.v0.x, t.v0.y), z), b = f2_fma(p0, f2_pack(t.v0.z, t.v0.w), z);
+  a = f2_fma(p1, f2_pack(t.v1.x, t.v1.y), a);
+  b = f2_fma(p1, f2_pack(t.v1.z, t.v1.w), b);
+  a = f2_fma(p2, f2_pack(t.v2.x, t.v2.y), a);
+  b = f2_fma(p2, f2_pack(t.v2.z, t.v2.w), b);
+  a = f2_fma(p3, f2_pack(t.v3.x, t.v3.y), a);
+  b = f2_fma(p3, f2_pack(t.v3.z, t.v3.w), b);
+  f2_unpack(a, v[0], v[1]);
+  f2_unpack(b, v[2], v[3]);
 }
 
 // gather 4 channels of one (pixel, unit) and store them as bf16 hi / lo into a swizzled 128-byte row
@@ -227,8 +256,7 @@ template <int kTmemCols>
 __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __restrict__ xh,
                                                                  const float* __restrict__ offset,
                                                                  const float* __restrict__ mask,
-                                                                 const uint8_t* __restrict__ wt,
-                                                                 const float* __restrict__ bias, const TC d,
+                                                                 const uint8_t* __restrict__ wt, const Epi ep, const TC d,
                                                                  const K1P k, const int split, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -309,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
     const bool pix_ok = p < d.HoWo;
     const int ntot = k.gspan * k.BN;
     const int oc0 = sg0 * d.ops + oct * k.BN;
-    const bool add_bias = bias != nullptr && blockIdx.z == 0;
+    const bool add_shift = ep.shift != nullptr && blockIdx.z == 0;
     for (int c16 = cgrp; c16 * 16 < ntot; c16 += 4) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
@@ -319,9 +347,15 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
         for (int i = 0; i < 16; ++i) {
           const int oc = oc0 + c16 * 16 + i;
           float* dst = out + ((size_t)b * d.Cout + oc) * d.HoWo + p;
-          const float v = __uint_as_float(r[i]) + (add_bias ? __ldg(bias + oc) : 0.f);
-          if (k.red) red_add(dst, v);
-          else *dst = v;
+          float v = __uint_as_float(r[i]);
+          if (k.red) {  // k-split partial sums: scale / relu run in dcn_epilogue_kernel once all partials are in
+            red_add(dst, v + ((add_shift && !ep.scale && !ep.relu) ? __ldg(ep.shift + oc) : 0.f));
+          } else {
+            if (ep.scale) v *= __ldg(ep.scale + oc);
+            if (ep.shift) v += __ldg(ep.shift + oc);
+            if (ep.relu) v = fmaxf(v, 0.f);
+            *dst = v;
+          }
         }
       }
     }
@@ -466,9 +500,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
         const int p = p0 + warp * 8 + j * 2 + half;
         if (p < d.HoWo) {
           if (which < 2) {
-            if (goff) red_add(goff + ((size_t)(b * d.DG + cur_dg) * 2 * d.KK + 2 * cur_kp + which) * d.HoWo + p, v);
+            if (goff) red_add(goff + (size_t)b * d.off_bs + ((size_t)cur_dg * 2 * d.KK + 2 * cur_kp + which) * d.HoWo + p, v);
           } else if (gmask) {
-            red_add(gmask + ((size_t)(b * d.DG + cur_dg) * d.KK + cur_kp) * d.HoWo + p, v);
+            if (d.mask_sigmoid) {  // gradient w.r.t. the logit: m (1 - m)
+              const float m = __int_as_float(taps[((cur_dg - dg0) * nkp + (cur_kp - kp0)) * 128 + warp * 8 + j * 2 + half].w);
+              v *= m * (1.f - m);
+            }
+            red_add(gmask + (size_t)b * d.mask_bs + ((size_t)cur_dg * d.KK + cur_kp) * d.HoWo + p, v);
           }
         }
       }
@@ -842,7 +880,17 @@ __global__ void dcn_wtile_bwd_kernel(const float* __restrict__ w, const TC d, ui
 }
 
 // K2 A tiles: gout [N,Cout,HoWo] -> [b][pixel tile][sg][K stage] -> [128 rows = px][64 oc], hi then lo.  One CTA per tile.
-__global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __restrict__ gout, const TC d,
+// grad w.r.t. the convolution result when the forward ended in y = relu(acc * scale + shift)
+__device__ __forceinline__ float gout_elem(const float* __restrict__ gout, const float* __restrict__ ysaved, const Epi& ep,
+                                           size_t idx, int oc) {
+  float g = __ldg(gout + idx);
+  if (ep.relu && !(__ldg(ysaved + idx) > 0.f)) g = 0.f;
+  if (ep.scale) g *= __ldg(ep.scale + oc);
+  return g;
+}
+
+__global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __restrict__ gout,
+                                                                const float* __restrict__ ysaved, const Epi ep, const TC d,
                                                                 uint8_t* __restrict__ dst) {
   __shared__ float t[64][129];
   const long long tile = blockIdx.x;
@@ -855,7 +903,7 @@ __global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __r
   for (int e = tid; e < 64 * 128; e += 256) {
     const int o = e >> 7, pp = e & 127;
     const int p = p0 + pp;
-    t[o][pp] = p < d.HoWo ? __ldg(gout + ((size_t)b * d.Cout + oc0 + o) * d.HoWo + p) : 0.f;
+    t[o][pp] = p < d.HoWo ? gout_elem(gout, ysaved, ep, ((size_t)b * d.Cout + oc0 + o) * d.HoWo + p, oc0 + o) : 0.f;
   }
   __syncthreads();
   uint8_t* base = dst + tile * (size_t)(2 * kTile);
@@ -872,8 +920,8 @@ __global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __r
 }
 
 // K3 B tiles: gout -> [b][64-pixel stage][sg][oc tile] -> [BN rows = oc][64 px], K-major swizzled, hi then lo
-__global__ void dcn_gout_oc_tiles_kernel(const float* __restrict__ gout, const TC d, int BN, int noct,
-                                         uint8_t* __restrict__ dst) {
+__global__ void dcn_gout_oc_tiles_kernel(const float* __restrict__ gout, const float* __restrict__ ysaved, const Epi ep,
+                                         const TC d, int BN, int noct, uint8_t* __restrict__ dst) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)d.N * d.stages_img * d.SG * noct * BN * 8;
   if (idx >= total) return;
@@ -885,12 +933,12 @@ __global__ void dcn_gout_oc_tiles_kernel(const float* __restrict__ gout, const T
   const int ps = (int)((tile / ((long long)noct * d.SG)) % d.stages_img);
   const int b = (int)(tile / ((long long)noct * d.SG * d.stages_img));
   const int oc = sg * d.ops + oct * BN + r;
-  const float* __restrict__ src = gout + ((size_t)b * d.Cout + oc) * d.HoWo;
+  const size_t src = ((size_t)b * d.Cout + oc) * d.HoWo;
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int p = ps * 64 + c16 * 8 + e;
-    v[e] = p < d.HoWo ? __ldg(src + p) : 0.f;
+    v[e] = p < d.HoWo ? gout_elem(gout, ysaved, ep, src + p, oc) : 0.f;
   }
   uint4 hi, lo;
   split8(v, hi, lo);
@@ -916,6 +964,18 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
     const int cc = e >> 6, pp = e & 63;
     if (hw0 + pp < HW && c0 + cc < C) o[(size_t)(c0 + cc) * HW + hw0 + pp] = t[pp][cc];
   }
+}
+
+// y = relu(y * scale + shift) in place: the forward's epilogue when the reduction was split over kernel points
+__global__ void dcn_epilogue_kernel(float* __restrict__ y, long long total, int Cout, int HoWo, const Epi ep) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int oc = (int)((i / HoWo) % Cout);
+  float v = y[i];
+  if (ep.scale) v *= __ldg(ep.scale + oc);
+  if (ep.shift) v += __ldg(ep.shift + oc);
+  if (ep.relu) v = fmaxf(v, 0.f);
+  y[i] = v;
 }
 
 int to_nhwc(const float* x, const TC& d, float* dst, cudaStream_t stream) {
@@ -955,14 +1015,20 @@ size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc) {
   return b;
 }
 
+// tcflags: bit 0 = x is NHWC, bit 1 = `offset` is the fused [N, 3*DG*KK, Ho, Wo] offset + mask-logit tensor (mask must be null)
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                               const float* bias, const d2b_dcn_params* p, int precision, int x_nhwc, float* out,
-                               void* workspace, size_t workspace_bytes, void* stream_) {
+                               const float* scale, const float* shift, int relu, const d2b_dcn_params* p, int precision,
+                               int tcflags, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int x_nhwc = tcflags & 1;
   TC d;
   K1P k;
   if (!make_tc(p, d) || !plan_k1(d, k)) return D2B_EUNSUPPORTED;  // argument validity was checked by the caller
   if (d.N == 0) return D2B_OK;
+  if (tcflags & 2) {
+    if (mask) return D2B_EINVAL;
+    mask = use_fused_offset_mask(d, offset);
+  }
   if (!workspace || workspace_bytes < d2b_deform_conv_tc_fwd_workspace(p, x_nhwc)) return D2B_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15))) return D2B_EINVAL;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -984,11 +1050,12 @@ int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float*
   const int smem_bytes = k.S * k.stage_bytes + k.tap_bytes + 1024 + 256;
   const int cols = pow2_cols(k.gspan * k.BN);
   const int split = precision == 1 ? 1 : 0;
+  const Epi ep = {scale, shift, relu};
   dim3 grid(d.N * d.tiles_img, (d.SG / k.gspan) * k.noct, k.ksplit);
 #define D2B_LAUNCH_K1(COLS)                                                                                            \
   {                                                                                                                    \
     D2B_ALLOW_BIG_SMEM(dcn_fwd_tc_kernel<COLS>);                                                                       \
-    dcn_fwd_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, wt, bias, d, k, split, out);     \
+    dcn_fwd_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, wt, ep, d, k, split, out);       \
   }
   if (cols <= 32) D2B_LAUNCH_K1(32)
   else if (cols == 64) D2B_LAUNCH_K1(64)
@@ -996,6 +1063,11 @@ int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float*
   else D2B_LAUNCH_K1(256)
 #undef D2B_LAUNCH_K1
   D2B_CHECK_LAUNCH();
+  if (k.red && (scale || relu)) {
+    const long long total = (long long)d.N * d.Cout * d.HoWo;
+    dcn_epilogue_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(out, total, d.Cout, d.HoWo, ep);
+    D2B_CHECK_LAUNCH();
+  }
   return D2B_OK;
 }
 
@@ -1017,20 +1089,32 @@ size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int
 }
 
 // grad_x: NCHW (or NHWC when x_nhwc) fully written; grad_offset / grad_mask / grad_weight fully written.
+// With the fused offset + mask-logit tensor (tcflags bit 1) grad_offset is its [N, 3*DG*KK, Ho, Wo] gradient (mask part through
+// the sigmoid) and grad_mask must be null.  scale / y_saved / relu: transpose of the forward's epilogue.
 int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
-                                const float* grad_out, const d2b_dcn_params* p, int precision, int x_nhwc,
-                                float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
-                                void* workspace, size_t workspace_bytes, void* stream_) {
+                                const float* grad_out, const float* scale, const float* y_saved, int relu,
+                                const d2b_dcn_params* p, int precision, int tcflags, float* grad_x, float* grad_offset,
+                                float* grad_mask, float* grad_weight, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int x_nhwc = tcflags & 1;
   TC d;
   K2P k2;
   K3P k3;
   if (!make_tc(p, d) || !plan_k2(d, k2) || !plan_k3(d, k3)) return D2B_EUNSUPPORTED;
   const int need_data = (grad_x || grad_offset || grad_mask) ? 1 : 0, need_weight = grad_weight ? 1 : 0;
-  const size_t nx = (size_t)d.N * d.H * d.W * d.Cin, noff = (size_t)d.N * d.DG * 2 * d.KK * d.HoWo;
+  const bool fused_om = (tcflags & 2) != 0;
+  if (fused_om && (mask || grad_mask)) return D2B_EINVAL;
+  if (relu && !y_saved) return D2B_EINVAL;
+  const size_t nx = (size_t)d.N * d.H * d.W * d.Cin, noff = (size_t)d.N * d.DG * (fused_om ? 3 : 2) * d.KK * d.HoWo;
   const size_t nm = (size_t)d.N * d.DG * d.KK * d.HoWo, nw = (size_t)d.Cout * d.cpg * d.KK;
+  if (fused_om) {
+    mask = use_fused_offset_mask(d, offset);
+    if (grad_offset) grad_mask = grad_offset + (size_t)d.DG * 2 * d.KK * d.HoWo;
+  }
+  const Epi ep = {scale, nullptr, relu};
   if (grad_offset && noff) D2B_CUDA(cudaMemsetAsync(grad_offset, 0, noff * 4, stream));
-  if (grad_mask && nm) D2B_CUDA(cudaMemsetAsync(grad_mask, 0, nm * 4, stream));
+  if (grad_mask && nm && !fused_om) D2B_CUDA(cudaMemsetAsync(grad_mask, 0, nm * 4, stream));  // fused: inside grad_offset
   if (grad_weight) D2B_CUDA(cudaMemsetAsync(grad_weight, 0, nw * 4, stream));
   if (d.N == 0) return D2B_OK;
   if (!need_data && !need_weight) return D2B_OK;
@@ -1061,7 +1145,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     ws += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);
     uint8_t* wt = ws;
     ws += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);
-    dcn_gout_px_tiles_kernel<<<(unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 256, 0, stream>>>(grad_out, d, gt);
+    dcn_gout_px_tiles_kernel<<<(unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 256, 0, stream>>>(grad_out, y_saved, ep, d, gt);
     D2B_CHECK_LAUNCH();
     {
       const long long total = (long long)d.SG * d.MC * d.nks * 128 * 8;
@@ -1084,7 +1168,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     uint8_t* gt = ws;
     {
       const long long total = (long long)d.N * d.stages_img * d.SG * k3.noct * k3.BN * 8;
-      dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, d, k3.BN, k3.noct, gt);
+      dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, y_saved, ep, d, k3.BN, k3.noct, gt);
       D2B_CHECK_LAUNCH();
     }
     const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;

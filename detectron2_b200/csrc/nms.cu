@@ -328,7 +328,7 @@ template <bool ROT, int kSub>
 __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __restrict__ sb, const int* __restrict__ seg_hi_of_pos,
                                                              const float* __restrict__ clsf_of_pos,
                                                              const NmsCtrl* __restrict__ ctrl, int apply_offsets, int M,
-                                                             double thr, unsigned long long* __restrict__ maskT) {
+                                                             int wcap, double thr, unsigned long long* __restrict__ maskT) {
   constexpr int D = ROT ? 5 : 4;
   constexpr int kCols = 64 / kSub;
   __shared__ float cbox[64 * D];
@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __rest
     }
   }
   __syncthreads();
-  const int cb_last = (s_hi - 1) >> 6;
+  // a category larger than the caller's bound (flagged by the rank kernel) is truncated to the planes that exist
+  const int cb_last = min((s_hi - 1) >> 6, rb + wcap - 1);
   const float area_a = ROT ? 0.f : (a[2] - a[0]) * (a[3] - a[1]);
   for (int cb = rb; cb <= cb_last; ++cb) {
     const int c0 = cb * 64;
@@ -370,9 +371,11 @@ __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __rest
       cbox[t] = v;
     }
     __syncthreads();
-    if (!row_ok || c0 >= my_hi) continue;  // this row's category ends before the block
+    // rows whose category ends before this block have an empty column range (jend <= jbeg) and write nothing, but stay in
+    // the loop: the shuffles and barriers below are executed by every lane
+    const bool active = row_ok && c0 < my_hi;
     unsigned long long bits = 0ull;
-    const int jbeg = max(sub * kCols, row + 1 - c0), jend = min(min(nc, (sub + 1) * kCols), my_hi - c0);
+    const int jbeg = max(sub * kCols, row + 1 - c0), jend = active ? min(min(nc, (sub + 1) * kCols), my_hi - c0) : 0;
     if (ROT) {
       for (int j = jbeg; j < jend; ++j) {
         const float iou = rotated_iou(a, cbox + j * 5);
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __rest
     }
 #pragma unroll
     for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
-    if (sub == 0) maskT[(size_t)(cb - rb) * M + row] = bits;
+    if (active && sub == 0) maskT[(size_t)(cb - rb) * M + row] = bits;
   }
 }
 
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
                                                                    const int* __restrict__ orig_of_grank,
                                                                    const int* __restrict__ seg_start,
                                                                    const int* __restrict__ seg_end, NmsCtrl* __restrict__ ctrl,
-                                                                   int M, unsigned char* __restrict__ keepflag,
+                                                                   int M, int wcap, unsigned char* __restrict__ keepflag,
                                                                    long long* __restrict__ keep, long long* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];
   __shared__ __align__(16) unsigned long long s_diag[2][64];
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
     const int p0 = seg_start[seg], p1 = seg_end[seg];
     const int b0 = p0 >> 6, nb = ((p1 - 1) >> 6) + 1;  // blocks [b0, nb) of the global tiling touch this segment
+    if (nb - b0 > wcap + 1) continue;                    // larger than the caller's bound (error already flagged): skipped
     __syncthreads();                                     // previous segment done with removed[] / s_diag
     for (int i = b0 + tid; i < nb; i += kScanThreads) removed[i - b0] = 0ull;
 
@@ -668,16 +672,16 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   // 2. IoU bitmask inside the categories (coordinate offsets of the reference's batched-NMS trick applied in fp32)
   if (rotated)
     nms_mask_kernel<true, 8><<<nb, 512, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
-                                                     iou_threshold, w.maskT);
+                                                     w.wcap, iou_threshold, w.maskT);
   else
     nms_mask_kernel<false, 4><<<nb, 256, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
-                                                      iou_threshold, w.maskT);
+                                                      w.wcap, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 3. per-segment greedy scans in parallel + compaction in global score order by the last CTA
   D2B_ALLOW_BIG_SMEM(nms_scan_kernel);
   const int scan_grid = idxs ? (m < 2 * kNumSMs ? m : 2 * kNumSMs) : 1;
   nms_scan_kernel<<<scan_grid, kScanThreads, smem, stream>>>(w.maskT, w.grank_of_pos, w.orig_of_grank, w.seg_start, w.seg_end,
-                                                             w.ctrl, m, w.keepflag, (long long*)keep, (long long*)num_keep);
+                                                             w.ctrl, m, w.wcap, w.keepflag, (long long*)keep, (long long*)num_keep);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

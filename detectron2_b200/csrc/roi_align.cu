@@ -717,55 +717,68 @@ constexpr int kNhwcCh = 128;    // channels per CTA
 constexpr int kNhwcChunk = 64;  // bins per output chunk (shared-memory transpose tile: 128 ch x chunk)
 constexpr int kNhwcThreads = 224;  // 7 warps: the 49 bins of a 7x7 output (and 7-multiples of a 14x14 chunk) split evenly
 
-// One bin: XC x-taps (offsets / weights held in registers) times RY rows per step = XC * RY independent 512-byte loads in
-// flight per warp.  Table entries hold element offsets premultiplied for the NHWC layout (row: y*W*C/4, column: x*C/4).
+// Packed fp32 FMA (sm_100 FFMA2): d.xy = w * v.xy + c.xy in ONE issue slot.  The tap loop is issue-bound, not FMA-pipe-bound.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_pack(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 w, F2 v, F2 c) {
+  F2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(w.v), "l"(v.v), "l"(c.v));
+  return d;
+}
+
+// One bin: XC x-taps (byte offsets / weights held in registers) times RY rows per step = XC * RY independent 512-byte loads in
+// flight per warp.  Table entries hold BYTE offsets premultiplied for the NHWC layout (row: y*W*C*4, column: x*C*4) and the
+// lists are padded to multiples of XC / RY with zero-weight taps on a valid pixel, so the loop carries no predicates: per tap
+// one address add, one LDG.128 and two packed FMAs (+ two per row for the y weight).
 template <int XC, int RY>
-__device__ __forceinline__ void nhwc_bin(const float4* __restrict__ base, const CTap* __restrict__ yt0,
+__device__ __forceinline__ void nhwc_bin(const char* __restrict__ base, const CTap* __restrict__ yt0,
                                          const CTap* __restrict__ xt0, int ny, int nx, float4& acc) {
+  F2 a01 = f2_pack(acc.x, acc.y), a23 = f2_pack(acc.z, acc.w);
   for (int x0 = 0; x0 < nx; x0 += XC) {
-    int xo[XC];
-    float xw[XC];
+    unsigned xo[XC];
+    F2 xw[XC];
 #pragma unroll
     for (int e = 0; e < XC; ++e) {
-      const CTap t = xt0[min(x0 + e, nx - 1) * kMaxP];
-      xo[e] = t.idx;
-      xw[e] = (x0 + e < nx) ? t.w : 0.f;
+      const CTap t = xt0[(x0 + e) * kMaxP];
+      xo[e] = (unsigned)t.idx;
+      xw[e] = f2_pack(t.w, t.w);
     }
     for (int ey = 0; ey < ny; ey += RY) {
-      int yo[RY];
-      float wy[RY];
+      const char* __restrict__ rowp[RY];
+      F2 wy[RY];
 #pragma unroll
       for (int j = 0; j < RY; ++j) {
-        const CTap t = yt0[min(ey + j, ny - 1) * kMaxP];
-        yo[j] = t.idx;
-        wy[j] = (ey + j < ny) ? t.w : 0.f;
+        const CTap t = yt0[(ey + j) * kMaxP];
+        rowp[j] = base + (size_t)(unsigned)t.idx;
+        wy[j] = f2_pack(t.w, t.w);
       }
       float4 v[RY][XC];
 #pragma unroll
       for (int j = 0; j < RY; ++j)
 #pragma unroll
-        for (int e = 0; e < XC; ++e) {  // 32-bit element offset inside the image, one IMAD.WIDE to the address
-          const unsigned off = (unsigned)(yo[j] + xo[e]);
-          v[j][e] = (x0 + e < nx) ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(base) + (size_t)off * 16u))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int e = 0; e < XC; ++e) v[j][e] = __ldg(reinterpret_cast<const float4*>(rowp[j] + xo[e]));
 #pragma unroll
       for (int j = 0; j < RY; ++j) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        F2 r01 = f2_pack(0.f, 0.f), r23 = r01;
 #pragma unroll
         for (int e = 0; e < XC; ++e) {
-          r.x = fmaf(xw[e], v[j][e].x, r.x);
-          r.y = fmaf(xw[e], v[j][e].y, r.y);
-          r.z = fmaf(xw[e], v[j][e].z, r.z);
-          r.w = fmaf(xw[e], v[j][e].w, r.w);
+          r01 = f2_fma(xw[e], f2_pack(v[j][e].x, v[j][e].y), r01);
+          r23 = f2_fma(xw[e], f2_pack(v[j][e].z, v[j][e].w), r23);
         }
-        acc.x = fmaf(wy[j], r.x, acc.x);
-        acc.y = fmaf(wy[j], r.y, acc.y);
-        acc.z = fmaf(wy[j], r.z, acc.z);
-        acc.w = fmaf(wy[j], r.w, acc.w);
+        a01 = f2_fma(wy[j], r01, a01);
+        a23 = f2_fma(wy[j], r23, a23);
       }
     }
   }
+  f2_unpack(a01, acc.x, acc.y);
+  f2_unpack(a23, acc.z, acc.w);
 }
 
 // 4 CTAs x 7 warps per SM at 72 registers: measured faster than 3 CTAs at 80 (95 vs 97 us on the box-head call)
@@ -797,6 +810,7 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   __syncthreads();
   const float4* __restrict__ base =
       reinterpret_cast<const float4*>(P.feat[lvl]) + (size_t)sg.b * H * W * C4 + (c0 >> 2) + (lane_live ? lane : 0);
+  const char* __restrict__ base_b = reinterpret_cast<const char*>(base);
   if (!s_overflow) {
     if (tid < PH) {
       const RoiGeom g = sg;
@@ -807,7 +821,9 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
         add_tap(list, kMaxP, n, t.lo, t.wl, ov);
         add_tap(list, kMaxP, n, t.hi, t.wh, ov);
       }
-      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= W * C4;  // row offset in float4 units
+      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= W * C4 * 16;  // row offset in bytes
+      if (n > 0)  // pad to a whole number of row pairs: zero-weight taps on a valid row
+        for (; n & 1; ++n) list[n * kMaxP] = CTap{list[0].idx, 0.f};
       yn[tid] = n;
       if (ov) atomicOr(&s_tapov, 1);
     } else if (tid >= 32 && tid < 32 + PW) {
@@ -820,7 +836,9 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
         add_tap(list, kMaxP, n, t.lo, t.wl, ov);
         add_tap(list, kMaxP, n, t.hi, t.wh, ov);
       }
-      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4;
+      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4 * 16;  // column offset in bytes
+      if (n > 0)  // pad to a multiple of the x-tap chunk (4, or 8 for long lists): zero-weight taps on a valid column
+        for (const int m = n <= 4 ? 3 : 7; n & m; ++n) list[n * kMaxP] = CTap{list[0].idx, 0.f};
       xn[pw] = n;
       if (ov) atomicOr(&s_tapov, 1);
     }
@@ -837,8 +855,8 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (!onfly) {
         const int ny = yn[ph], nx = xn[pw];
-        if (nx <= 4) nhwc_bin<4, 2>(base, ytab + ph, xtab + pw, ny, nx, acc);
-        else nhwc_bin<8, 1>(base, ytab + ph, xtab + pw, ny, nx, acc);
+        if (nx <= 4) nhwc_bin<4, 2>(base_b, ytab + ph, xtab + pw, ny, nx, acc);
+        else nhwc_bin<8, 1>(base_b, ytab + ph, xtab + pw, ny, nx, acc);
       } else {  // rare: sampling grid too large for the tap lists (or pooled size > 16): taps on the fly
         const RoiGeom g = sg;
         for (int iy = 0; iy < g.gh; ++iy) {

@@ -145,6 +145,22 @@ __device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo
   hi = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
   lo = make_uint2(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]));
 }
+// Packed fp32 FMA (sm_100 FFMA2): two lanes of fp32 FMA in ONE issue slot -- the gather loops are issue-bound
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_pack(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 w, F2 v, F2 c) {
+  F2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(w.v), "l"(v.v), "l"(c.v));
+  return d;
+}
+
 // byte offset of the 16-byte chunk `c16` of row `r` inside a 128-byte-swizzled tile of 128-byte rows
 __device__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 

@@ -125,3 +125,33 @@ class ModulatedDeformConv(nn.Module):
                 "deformable_groups={}, bias={}").format(self.in_channels, self.out_channels, self.kernel_size,
                                                         self.stride, self.padding, self.dilation, self.groups,
                                                         self.deformable_groups, self.with_bias)
+
+
+class DeformBottleneckConv2(nn.Module):
+    """conv2 of the reference's DeformBottleneckBlock with modulated deformable convolution, as ONE op
+    (detectron2/modeling/backbone/resnet.py:291-318): takes the raw output of `conv2_offset` (27 channels for a 3x3
+    kernel), applies chunk / cat / sigmoid, the ModulatedDeformConv, its norm (FrozenBatchNorm folded into a per-channel
+    scale and shift) and the ReLU that follows.  `weight` keeps the reference's name / shape, so `conv2.weight` of a
+    checkpoint loads unchanged; `norm_scale` / `norm_shift` are buffers (call `load_frozen_bn` with the norm's tensors)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, dilation=1, groups=1,
+                 deformable_groups=1, relu=True):
+        super().__init__()
+        self.kernel_size = _pair(kernel_size)
+        self.stride, self.padding, self.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups, self.relu = groups, deformable_groups, relu
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        nn.init.kaiming_uniform_(self.weight, nonlinearity="relu")
+        self.register_buffer("norm_scale", torch.ones(out_channels))
+        self.register_buffer("norm_shift", torch.zeros(out_channels))
+
+    def load_frozen_bn(self, weight, bias, running_mean, running_var, eps=1e-5):
+        """Fold FrozenBatchNorm2d (layers/batch_norm.py:50-58): y = x * scale + shift."""
+        scale = weight * (running_var + eps).rsqrt()
+        self.norm_scale.copy_(scale)
+        self.norm_shift.copy_(bias - running_mean * scale)
+
+    def forward(self, x, offset_mask):
+        return ops.deform_conv_fused_op(x, offset_mask, self.weight, self.norm_scale, self.norm_shift, self.relu,
+                                        list(self.stride), list(self.padding), list(self.dilation), self.groups,
+                                        self.deformable_groups, DEFAULT_PRECISION if DEFAULT_PRECISION != 0 else 1)

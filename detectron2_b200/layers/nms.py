@@ -14,11 +14,12 @@ _TRICK_MAX_NUMEL = 100_000
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """torchvision.ops.nms semantics (layers/nms.py:6): keep indices sorted by decreasing score, suppress IoU > thr."""
-    return ops.nms_op(boxes, scores, None, float(iou_threshold), False)
+    return torch.ops.d2b200.nms(boxes, scores, None, float(iou_threshold), False, True)
 
 
-def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
-    """Per-category NMS (layers/nms.py:11-22 -> torchvision batched_nms, always on boxes.float())."""
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """Per-category NMS (layers/nms.py:11-22 -> torchvision batched_nms, always on boxes.float()).  Scriptable like the
+    reference (tests/layers/test_nms.py:16-29): the body is dispatcher ops only."""
     assert boxes.shape[-1] == 4
     boxes = boxes.float()
     if boxes.numel() == 0:
@@ -26,7 +27,7 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
     # torchvision leaves the coordinate-offset trick for a per-class Python loop above 25 000 boxes (ops/boxes.py
     # _batched_nms_vanilla: raw coordinates, one nms + host sync per class).  Same results in ONE call here: the
     # categories only segment the boxes (D2B_NMS_NO_OFFSET).
-    return ops.nms_op(boxes, scores, idxs, float(iou_threshold), False, boxes.numel() <= _TRICK_MAX_NUMEL)
+    return torch.ops.d2b200.nms(boxes, scores, idxs, float(iou_threshold), False, boxes.numel() <= 100000)
 
 
 def batched_nms_fixed(boxes, scores, idxs, iou_threshold):
@@ -34,16 +35,16 @@ def batched_nms_fixed(boxes, scores, idxs, iou_threshold):
     return ops.nms_fixed(boxes.float(), scores, idxs, float(iou_threshold), False)
 
 
-def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float):
+def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """Rotated NMS over (cx, cy, w, h, angle_deg) boxes (layers/nms.py:28-89); suppress IoU >= thr like the
     reference CPU kernel (nms_rotated_cpu.cpp:54)."""
     return torch.ops.detectron2.nms_rotated(boxes, scores, iou_threshold)
 
 
-def batched_nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
+def batched_nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """Per-category rotated NMS (layers/nms.py:97-147); the min/max-coordinate offsets of :137-146 are computed and
     applied inside the kernel pipeline in fp32."""
     assert boxes.shape[-1] == 5
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
-    return ops.nms_op(boxes.float(), scores, idxs, float(iou_threshold), True)
+    return torch.ops.d2b200.nms(boxes.float(), scores, idxs, float(iou_threshold), True, True)

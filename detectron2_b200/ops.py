@@ -597,13 +597,96 @@ def _dcn_bwd(ctx, grad):
 deform_conv_op.register_autograd(_dcn_bwd, setup_context=_dcn_setup)
 
 
+# ----------------------------------------------------------------------------------- DeformBottleneckBlock conv2, fused
+@torch.library.custom_op("d2b200::deform_conv_fused", mutates_args=(), device_types="cuda")
+def deform_conv_fused_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+                         relu: bool, stride: List[int], padding: List[int], dilation: List[int], groups: int,
+                         deformable_groups: int, precision: int) -> Tensor:
+    """y = relu(modulated_deform_conv(x, offset, sigmoid(mask), weight) * scale + shift) with offset / mask taken straight
+    from the raw conv2_offset output `offset_mask` [N, 3*dg*kh*kw, Ho, Wo] (detectron2/modeling/backbone/resnet.py:305-318):
+    the chunk / cat / sigmoid happen while the sampling taps are built, scale / shift / relu in the TMEM epilogue."""
+    _C.require_cuda(x, offset_mask, weight, scale, shift)
+    kh, kw = weight.shape[2:]
+    n, cout, ho, wo = dcn_output_shape(x, weight, stride, padding, dilation)
+    if x.dim() != 4:
+        raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(x.dim()))
+    if tuple(offset_mask.shape) != (n, 3 * deformable_groups * kh * kw, ho, wo):
+        raise RuntimeError("invalid shape of offset_mask: got %s, expected %s" %
+                           (tuple(offset_mask.shape), (n, 3 * deformable_groups * kh * kw, ho, wo)))
+    om, wf, sc, sh = _f32c(offset_mask), _f32c(weight), _f32c(scale), _f32c(shift)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    if precision == 0 or not _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(p), 0):
+        raise RuntimeError("deform_conv_fused: the tensor-core kernels do not take this shape / precision "
+                           "(use layers.modulated_deform_conv and apply the epilogue separately)")
+    xf, flags = _dcn_x(x, p, precision, False)
+    out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), 1, flags)
+    ws = _ws(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        check(_C.lib().d2b_deform_conv_fused_forward(ptr(xf), ptr(om), ptr(wf), ptr(sc), ptr(sh), int(relu), C.byref(p),
+                                                     precision, flags, ptr(out), ptr(ws), ws_bytes, stream_ptr(x.device)),
+              "deform_conv_fused_forward")
+    return out.to(x.dtype)
+
+
+@deform_conv_fused_op.register_fake
+def _(x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups, deformable_groups, precision):
+    return x.new_empty(dcn_output_shape(x, weight, stride, padding, dilation))
+
+
+@torch.library.custom_op("d2b200::deform_conv_fused_backward", mutates_args=(), device_types="cuda")
+def deform_conv_fused_backward_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor], relu: bool,
+                                  y: Tensor, grad_out: Tensor, stride: List[int], padding: List[int],
+                                  dilation: List[int], groups: int, deformable_groups: int,
+                                  precision: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _C.require_cuda(x, offset_mask, weight, scale, y, grad_out)
+    om, wf, sc, yf, gf = _f32c(offset_mask), _f32c(weight), _f32c(scale), _f32c(y), _f32c(grad_out)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    if not _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(p), 1):
+        raise RuntimeError("deform_conv_fused_backward: the tensor-core backward does not take this shape")
+    xf, flags = _dcn_x(x, p, precision, True)
+    gx, gom, gw = torch.empty_like(xf), torch.empty_like(om), torch.empty_like(wf)
+    ws_bytes = _C.lib().d2b_deform_conv_backward_workspace_bytes(C.byref(p), 1, flags, 1, 1)
+    ws = _ws(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        check(_C.lib().d2b_deform_conv_fused_backward(ptr(xf), ptr(om), ptr(wf), ptr(sc), int(relu), ptr(yf), ptr(gf),
+                                                      C.byref(p), precision, flags, ptr(gx), ptr(gom), ptr(gw), ptr(ws),
+                                                      ws_bytes, stream_ptr(x.device)), "deform_conv_fused_backward")
+    return gx, gom, gw
+
+
+@deform_conv_fused_backward_op.register_fake
+def _(x, offset_mask, weight, scale, relu, y, grad_out, stride, padding, dilation, groups, deformable_groups, precision):
+    return torch.empty_like(x), torch.empty_like(offset_mask), torch.empty_like(weight)
+
+
+def _dcnf_setup(ctx, inputs, output):
+    x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups, dg, precision = inputs
+    ctx.save_for_backward(x, offset_mask, weight, scale, output)
+    ctx.args = (relu, stride, padding, dilation, groups, dg, precision)
+
+
+def _dcnf_bwd(ctx, grad):
+    x, offset_mask, weight, scale, y = ctx.saved_tensors
+    relu, stride, padding, dilation, groups, dg, precision = ctx.args
+    gx, gom, gw = deform_conv_fused_backward_op(x, offset_mask, weight, scale, relu, y, grad, stride, padding, dilation,
+                                                groups, dg, precision)
+    # scale / shift are FrozenBatchNorm buffers (or a folded bias): no gradient is produced for them
+    return (gx.to(x.dtype), gom.to(offset_mask.dtype), gw.to(weight.dtype), None, None, None, None, None, None, None, None,
+            None)
+
+
+deform_conv_fused_op.register_autograd(_dcnf_bwd, setup_context=_dcnf_setup)
+
+
 # =================================================================================== paste masks
 @torch.library.custom_op("d2b200::paste_masks", mutates_args=(), device_types="cuda")
 def paste_masks_op(masks: Tensor, boxes: Tensor, img_h: int, img_w: int, threshold: float) -> Tensor:
     _C.require_cuda(masks, boxes)
     mk, bx = _f32c(masks), _f32c(boxes)
     n, m = mk.shape[0], mk.shape[-1]
-    out = torch.empty((n, img_h, img_w), dtype=torch.uint8, device=mk.device)
+    # bool output (1 byte per pixel, 0/1) for threshold >= 0, uint8 (value * 255) otherwise: mask_ops.py:137-141
+    out = torch.empty((n, img_h, img_w), dtype=torch.bool if threshold >= 0 else torch.uint8, device=mk.device)
     if out.numel():
         with torch.cuda.device(mk.device):
             check(_C.lib().d2b_paste_masks(ptr(mk), ptr(bx), n, m, img_h, img_w, threshold, ptr(out),
@@ -613,7 +696,7 @@ def paste_masks_op(masks: Tensor, boxes: Tensor, img_h: int, img_w: int, thresho
 
 @paste_masks_op.register_fake
 def _(masks, boxes, img_h, img_w, threshold):
-    return masks.new_empty((masks.shape[0], img_h, img_w), dtype=torch.uint8)
+    return masks.new_empty((masks.shape[0], img_h, img_w), dtype=torch.bool if threshold >= 0 else torch.uint8)
 
 
 # =================================================================================== detectron2::* dispatcher ops

@@ -187,6 +187,20 @@ int d2b_deform_conv_backward(const float* x, const float* offset, const float* m
                              float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* conv2 of a DeformBottleneckBlock fused (detectron2/modeling/backbone/resnet.py:305-318): `offset_mask`
+ * [N, 3*DG*kh*kw, Ho, Wo] is the raw conv2_offset output (chunk / cat / sigmoid of :307-311 applied while the sampling taps
+ * are built), y = relu(conv * scale[oc] + shift[oc]) (FrozenBatchNorm folded, or scale NULL and shift = bias; relu 0/1) is
+ * applied in the TMEM epilogue.  Tensor-core precisions only (1, 2 or -1); workspace sizes are those of
+ * d2b_deform_conv_forward / backward_workspace_bytes.  The backward takes y (to gate the ReLU) and returns the gradient of
+ * the fused offset_mask tensor (mask part through the sigmoid). */
+int d2b_deform_conv_fused_forward(const float* x, const float* offset_mask, const float* weight, const float* scale,
+                                  const float* shift, int relu, const d2b_dcn_params* p, int precision, int flags,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream);
+int d2b_deform_conv_fused_backward(const float* x, const float* offset_mask, const float* weight, const float* scale,
+                                   int relu, const float* y, const float* grad_out, const d2b_dcn_params* p,
+                                   int precision, int flags, float* grad_x, float* grad_offset_mask, float* grad_weight,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- paste_masks_in_image ---------------------------------------------------------------
  * Replaces detectron2/layers/mask_ops.py:74-147 (GPU branch: every pixel of the image for every mask).
  * masks [N,M,M] fp32, boxes [N,4] xyxy fp32 -> out [N,H,W] uint8: (v >= threshold) as 0/1 when

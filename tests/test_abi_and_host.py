@@ -114,7 +114,7 @@ def test_fake_kernels_trace_shapes():
         assert out.shape == (2, 24, 10, 15)
         assert ops.box_iou_rotated_op(torch.empty(5, 5, device="cuda"), torch.empty(9, 5, device="cuda")).shape == (5, 9)
         pm = ops.paste_masks_op(torch.empty(3, 28, 28, device="cuda"), torch.empty(3, 4, device="cuda"), 40, 50, 0.5)
-        assert pm.shape == (3, 40, 50) and pm.dtype == torch.uint8
+        assert pm.shape == (3, 40, 50) and pm.dtype == torch.bool  # threshold >= 0: bool output like the reference
 
 
 def test_pooler_layout_policy_host_logic(monkeypatch):
@@ -152,3 +152,26 @@ def test_roi_pooler_no_images():  # /root/reference/tests/modeling/test_roi_pool
         ROIPooler(output_size=7, scales=(0.25,), sampling_ratio=0, pooler_type="ROIPool")
     with pytest.raises(AssertionError):  # scales that do not form a pyramid (poolers.py:186-190)
         ROIPooler(output_size=7, scales=(0.25, 0.0625), sampling_ratio=0, pooler_type="ROIAlignV2")
+
+
+class _RotNms(torch.nn.Module):  # /root/reference/tests/layers/test_nms_rotated.py:153-168
+    def forward(self, boxes, scores, threshold: float):
+        import detectron2_b200.layers as L
+
+        return L.nms_rotated(boxes, scores, threshold)
+
+
+def test_wrappers_are_scriptable():
+    """The wrappers the reference scripts in its own tests (tests/layers/test_nms.py:16-29, test_nms_rotated.py:153-168,
+    test_mask_ops.py:156-165) compile with torch.jit.script: their bodies are dispatcher ops only.  (Scripted == eager
+    is checked on the GPU in tests/test_gpu_parity.py.)"""
+    import detectron2_b200.layers as L
+
+    for fn in (L.batched_nms, L.nms, L.batched_nms_rotated, L.paste_masks_in_image):
+        f = fn.__original_fn if hasattr(fn, "__original_fn") else fn  # script_if_tracing wrapper
+        assert torch.jit.script(f) is not None
+    assert "detectron2::nms_rotated" in str(torch.jit.script(_nms_rotated_fn).graph)
+
+
+def _nms_rotated_fn(boxes: torch.Tensor, scores: torch.Tensor, threshold: float) -> torch.Tensor:
+    return torch.ops.detectron2.nms_rotated(boxes, scores, threshold)

@@ -279,6 +279,33 @@ def test_nms_ignored_slots_padding_and_category_bound():
     assert int(num_bad.item()) == -1
 
 
+def _rot_nms(boxes: torch.Tensor, scores: torch.Tensor, thr: float) -> torch.Tensor:
+    return torch.ops.detectron2.nms_rotated(boxes, scores, thr)
+
+
+def test_scripted_wrappers_equal_eager(L):
+    # /root/reference/tests/layers/test_nms.py:16-29, test_nms_rotated.py:153-168, test_mask_ops.py:156-165
+    g = torch.Generator().manual_seed(21)
+    n, ncls = 2000, 50
+    boxes, scores = _random_boxes(g, n, 200).to(DEV), torch.rand(n, generator=g).to(DEV)
+    idxs = torch.randint(0, ncls, (n,), generator=g).to(DEV)
+    sb = torch.jit.script(L.batched_nms)
+    for iou in (0.2, 0.5, 0.8):
+        backup = boxes.clone()
+        assert torch.equal(sb(boxes, scores, idxs, iou), L.batched_nms(boxes, scores, idxs, iou))
+        assert torch.equal(boxes, backup)
+    rb = torch.cat([torch.rand(300, 2, generator=g) * 100, 1 + torch.rand(300, 2, generator=g) * 40,
+                    (torch.rand(300, 1, generator=g) - 0.5) * 360], 1).to(DEV)
+    rs = torch.rand(300, generator=g).to(DEV)
+    assert torch.equal(torch.jit.script(_rot_nms)(rb, rs, 0.5), L.nms_rotated(rb, rs, 0.5))
+    paste = L.paste_masks_in_image
+    sp = torch.jit.script(paste.__original_fn if hasattr(paste, "__original_fn") else paste)
+    masks = torch.rand(10, 28, 28, generator=g).to(DEV)
+    pb = _random_boxes(g, 10, 100).to(DEV)
+    out = L.paste_masks_in_image(masks, pb, (150, 150))
+    assert out.dtype == torch.bool and torch.equal(out, sp(masks, pb, (150, 150), 0.5))
+
+
 # ------------------------------------------------------------------------------- rotated IoU / NMS
 def test_rotated_golden_bit_exact(L, golden):
     d = golden("rotated")
@@ -747,6 +774,59 @@ def test_deform_conv_tensor_core_backward_vs_oracle(cin, cout, h, w, grp, dg, mo
             assert err <= tol * scale + 1e-5, (name, cl, err, scale)
         if cl:
             assert gs[0].is_contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("c,co,h,w,grp,dg,stride,use_scale,relu", [(64, 64, 12, 20, 1, 1, 1, True, True),
+                                                                    (128, 128, 25, 42, 1, 1, 1, True, True),
+                                                                    (256, 256, 9, 11, 1, 2, 2, False, True),
+                                                                    (128, 128, 13, 17, 8, 1, 1, True, False),
+                                                                    (512, 512, 7, 9, 1, 1, 1, True, True)])
+def test_deform_bottleneck_conv2_fused_vs_unfused(L, c, co, h, w, grp, dg, stride, use_scale, relu):
+    # the raw conv2_offset output goes straight into the kernel (chunk / cat / sigmoid in the tap build), the
+    # FrozenBN scale / shift and the ReLU run in the epilogue; compared with the reference's expression
+    # (backbone/resnet.py:305-318) evaluated on the oracle (forward) and on our unfused ops + torch autograd (backward).
+    # The last row splits the reduction over kernel points (small map): epilogue in the follow-up pass.
+    from detectron2_b200 import ops
+
+    g = torch.Generator().manual_seed(c + h)
+    n, k, p = 2, 3, 1
+    ho, wo = (h + 2 * p - k) // stride + 1, (w + 2 * p - k) // stride + 1
+    x = torch.randn(n, c, h, w, generator=g)
+    om = torch.randn(n, 3 * dg * 9, ho, wo, generator=g) * 1.5
+    wt = torch.randn(co, c // grp, 3, 3, generator=g) * (1.0 / math.sqrt(c // grp * 9))
+    scale = (0.5 + torch.rand(co, generator=g)) if use_scale else None
+    shift = torch.randn(co, generator=g) * 0.3
+    go = torch.randn(n, co, ho, wo, generator=g)
+    ox, oy, m = torch.chunk(om, 3, dim=1)
+    off, mask = torch.cat((ox, oy), dim=1), m.sigmoid()
+    ref = orc.deform_conv_forward(x, off, mask, wt, None, stride, p, 1, grp, dg)
+    ref = ref * (scale[None, :, None, None] if use_scale else 1.0) + shift[None, :, None, None]
+    if relu:
+        ref = ref.relu()
+    dev = lambda t: None if t is None else t.to(DEV)  # noqa: E731
+    xd, omd, wd = [t.to(DEV).requires_grad_(True) for t in (x, om, wt)]
+    y = ops.deform_conv_fused_op(xd, omd, wd, dev(scale), dev(shift), relu, [stride, stride], [p, p], [1, 1], grp, dg, 1)
+    err = (y.detach().cpu() - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-5, err
+    y.backward(go.to(DEV))
+    # unfused composition on our own (oracle-pinned) ops with torch autograd for chunk / sigmoid / scale / relu
+    xu, omu, wu = [t.to(DEV).requires_grad_(True) for t in (x, om, wt)]
+    a, b_, mm = torch.chunk(omu, 3, dim=1)
+    yu = ops.deform_conv_op(xu, torch.cat((a, b_), dim=1), mm.sigmoid(), wu, None, [stride, stride], [p, p], [1, 1], grp, dg, 1)
+    yu = yu * (dev(scale)[None, :, None, None] if use_scale else 1.0) + dev(shift)[None, :, None, None]
+    if relu:
+        yu = yu.relu()
+    yu.backward(go.to(DEV))
+    for name, t, r in (("gx", xd.grad, xu.grad), ("gom", omd.grad, omu.grad), ("gw", wd.grad, wu.grad)):
+        e = (t - r).abs().max().item()
+        assert e <= 2e-4 * r.abs().max().item() + 1e-5, (name, e)
+    mod = L.DeformBottleneckConv2(c, co, 3, stride, p, 1, grp, dg, relu).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(wt)
+        mod.norm_shift.copy_(shift)
+        if use_scale:
+            mod.norm_scale.copy_(scale)
+    assert torch.allclose(mod(x.to(DEV), om.to(DEV)), y.detach(), rtol=1e-5, atol=1e-5)
 
 
 def test_deform_conv_tensor_core_unsupported_shape_is_loud():
