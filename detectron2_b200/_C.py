@@ -34,6 +34,11 @@ class Pyramid(C.Structure):
                 ("canonical_box_size", C.c_float)]
 
 
+class RpnLevels(C.Structure):
+    _fields_ = [("num_levels", C.c_int), ("proposals", C.c_void_p * MAX_LEVELS), ("topk_idx", C.c_void_p * MAX_LEVELS),
+                ("topk_scores", C.c_void_p * MAX_LEVELS), ("A", C.c_int * MAX_LEVELS), ("k", C.c_int * MAX_LEVELS)]
+
+
 def _declare(lib):
     vp, f32p, i64p, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     i, f, d, sz, i64 = C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_int64
@@ -57,6 +62,8 @@ def _declare(lib):
         "d2b_roi_align_rotated_backward_nhwc": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, f32p, vp]),
         "d2b_nms_workspace_bytes": (sz, [i64, i, i64]),
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64, i64p, i64p, vp, sz, vp]),
+        "d2b_rpn_prepare": (i, [C.POINTER(RpnLevels), i, f32p, f, i, f32p, f32p, f32p, f32p, i64p, vp, vp]),
+        "d2b_rpn_select": (i, [i64p, i64p, i, i, i, f32p, f32p, i64p, f32p, f32p, i64p, i64p, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
         "d2b_deform_conv_tc_shape_supported": (i, [C.POINTER(DcnParams), i]),
         "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i]),

@@ -23,6 +23,7 @@ SOURCES = {
     "roi_align.cu": [],
     "paste_masks.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
+    "postproc.cu": ["-fmad=false"],
     "deform_conv.cu": [],
     "deform_conv_tc.cu": [],
 }

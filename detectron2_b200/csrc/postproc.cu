@@ -1,0 +1,200 @@
+// Batched RPN proposal selection around the NMS: the two data-dependent stages of
+// detectron2/modeling/proposal_generator/proposal_utils.py:22-135 as fixed-capacity kernels, one CTA per image.
+//
+//   d2b_rpn_prepare   gathers the per-level top-k candidates, clips them to the image (Boxes.clip, :112), marks non-finite
+//                     (:104-110) and too-small (:115-119) boxes as IGNORED (category -1) instead of removing them, and
+//                     applies torchvision's batched-NMS coordinate offsets per image -- level * (max coordinate of that
+//                     image's surviving boxes + 1), fp32 -- so that every IoU rounds like the reference's;
+//   d2b_rpn_select    walks the score-ordered keep list of ONE NMS over all images and hands every image its first
+//                     post_nms_topk survivors (:129) in a fixed [N, post_nms_topk] layout + a count.
+//
+// Together with d2b_nms (category = image * L + level, per-category bound = pre_nms_topk) the whole selection is a
+// sync-free launch sequence with static shapes: capturable in a CUDA graph; the reference loops over images in Python
+// with boolean indexing and one `.item()` per image.  Compiled with -fmad=false like nms.cu (bit-exact clip / offsets).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+
+struct RpnLevels {
+  int L;
+  const float* proposals[D2B_MAX_LEVELS];    // [N, A_l, 4]
+  const int64_t* topk_idx[D2B_MAX_LEVELS];   // [N, k_l]
+  const float* topk_scores[D2B_MAX_LEVELS];  // [N, k_l]
+  int A[D2B_MAX_LEVELS], k[D2B_MAX_LEVELS], t0[D2B_MAX_LEVELS + 1];  // t0: prefix of k
+};
+
+__device__ __forceinline__ bool finitef(float v) { return fabsf(v) <= 3.402823466e38f; }  // false for inf and NaN
+
+__global__ void __launch_bounds__(kThreads) rpn_prepare_kernel(const RpnLevels P, int T, const float* __restrict__ image_hw,
+                                                               float min_box_size, int use_offsets,
+                                                               float* __restrict__ flat_boxes, float* __restrict__ nms_boxes,
+                                                               float* __restrict__ nms_scores, float* __restrict__ raw_scores,
+                                                               long long* __restrict__ cat_ids, int* __restrict__ nonfinite) {
+  __shared__ float s_red[32];
+  __shared__ float s_max;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float ih = image_hw[2 * n], iw = image_hw[2 * n + 1];
+  float mx = -INFINITY;
+  int bad = 0;
+  for (int t = tid; t < T; t += kThreads) {
+    int l = 0;
+    while (l + 1 < P.L && t >= P.t0[l + 1]) ++l;
+    const int j = t - P.t0[l];
+    const long long a = P.topk_idx[l][(size_t)n * P.k[l] + j];
+    const float s = P.topk_scores[l][(size_t)n * P.k[l] + j];
+    const float4 b = *reinterpret_cast<const float4*>(P.proposals[l] + ((size_t)n * P.A[l] + a) * 4);
+    const bool fin = finitef(b.x) && finitef(b.y) && finitef(b.z) && finitef(b.w) && finitef(s);
+    // Boxes.clip: x to [0, w], y to [0, h]   (torch.clamp(min=0) then minimum with the size, like the host restatement)
+    const float x1 = fminf(fmaxf(b.x, 0.f), iw), y1 = fminf(fmaxf(b.y, 0.f), ih);
+    const float x2 = fminf(fmaxf(b.z, 0.f), iw), y2 = fminf(fmaxf(b.w, 0.f), ih);
+    const bool valid = fin && (x2 - x1) > min_box_size && (y2 - y1) > min_box_size;
+    const size_t o = (size_t)n * T + t;
+    *reinterpret_cast<float4*>(flat_boxes + o * 4) = valid ? make_float4(x1, y1, x2, y2) : make_float4(0.f, 0.f, 0.f, 0.f);
+    raw_scores[o] = s;
+    nms_scores[o] = valid ? s : -INFINITY;
+    cat_ids[o] = valid ? (long long)n * P.L + l : -1LL;
+    if (valid) mx = fmaxf(mx, fmaxf(fmaxf(x1, y1), fmaxf(x2, y2)));
+    bad |= fin ? 0 : 1;
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  if (bad) atomicOr(nonfinite, 1);
+  __syncthreads();
+  if (tid < 32) {
+    mx = s_red[tid];
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (tid == 0) s_max = mx;
+  }
+  __syncthreads();
+  const float scale = s_max + 1.0f;  // torchvision _batched_nms_coordinate_trick: idxs * (boxes.max() + 1)
+  for (int t = tid; t < T; t += kThreads) {
+    int l = 0;
+    while (l + 1 < P.L && t >= P.t0[l + 1]) ++l;
+    const size_t o = (size_t)n * T + t;
+    float4 b = *reinterpret_cast<const float4*>(flat_boxes + o * 4);
+    if (use_offsets && cat_ids[o] >= 0) {
+      const float off = (float)l * scale;
+      b.x += off;
+      b.y += off;
+      b.z += off;
+      b.w += off;
+    }
+    *reinterpret_cast<float4*>(nms_boxes + o * 4) = b;
+  }
+}
+
+// Exclusive prefix sum of one int per thread over a 1024-thread CTA; `total` = sum.
+__device__ __forceinline__ int block_scan(int v, int* __restrict__ warp_tot, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // warp_tot reuse between calls
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  const int wt = warp_tot[lane];
+  int winc = wt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += t;
+  }
+  total = __shfl_sync(0xffffffffu, winc, 31);
+  const int wbase = __shfl_sync(0xffffffffu, winc, warp) - __shfl_sync(0xffffffffu, wt, warp);
+  return wbase + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads) rpn_select_kernel(const long long* __restrict__ keep,
+                                                              const long long* __restrict__ num_keep, int T, int post_topk,
+                                                              const float* __restrict__ flat_boxes,
+                                                              const float* __restrict__ raw_scores,
+                                                              const long long* __restrict__ cat_ids,
+                                                              float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                              long long* __restrict__ out_index, long long* __restrict__ counts) {
+  __shared__ int warp_tot[32];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const long long nk = max(0LL, *num_keep);
+  int have = 0;
+  for (long long j0 = 0; j0 < nk && have < post_topk; j0 += kThreads) {
+    const long long j = j0 + tid;
+    long long kidx = -1;
+    int mine = 0;
+    if (j < nk) {
+      kidx = keep[j];
+      mine = (kidx / T == n && cat_ids[kidx] >= 0) ? 1 : 0;
+    }
+    int total;
+    const int rank = have + block_scan(mine, warp_tot, total);
+    if (mine && rank < post_topk) {
+      const size_t o = (size_t)n * post_topk + rank;
+      *reinterpret_cast<float4*>(out_boxes + o * 4) = *reinterpret_cast<const float4*>(flat_boxes + (size_t)kidx * 4);
+      out_scores[o] = raw_scores[kidx];
+      out_index[o] = kidx;
+    }
+    have += total;
+  }
+  const int cnt = min(have, post_topk);
+  for (int r = cnt + tid; r < post_topk; r += kThreads) {  // deterministic padding
+    const size_t o = (size_t)n * post_topk + r;
+    *reinterpret_cast<float4*>(out_boxes + o * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    out_scores[o] = 0.f;
+    out_index[o] = 0;
+  }
+  if (tid == 0) counts[n] = cnt;
+}
+
+}  // namespace
+
+D2B_API int d2b_rpn_prepare(const d2b_rpn_levels* lv, int N, const float* image_hw, float min_box_size, int use_offsets,
+                            float* flat_boxes, float* nms_boxes, float* nms_scores, float* raw_scores, int64_t* cat_ids,
+                            int* nonfinite, void* stream) {
+  if (!lv || lv->num_levels < 1 || lv->num_levels > D2B_MAX_LEVELS || N < 0) return D2B_EINVAL;
+  if (!nonfinite) return D2B_EINVAL;
+  D2B_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), (cudaStream_t)stream));
+  if (N == 0) return D2B_OK;
+  if (!image_hw || !flat_boxes || !nms_boxes || !nms_scores || !raw_scores || !cat_ids) return D2B_EINVAL;
+  RpnLevels P = {};
+  P.L = lv->num_levels;
+  int T = 0;
+  for (int l = 0; l < P.L; ++l) {
+    if (!lv->proposals[l] || !lv->topk_idx[l] || !lv->topk_scores[l] || lv->A[l] <= 0 || lv->k[l] < 0 || lv->k[l] > lv->A[l])
+      return D2B_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(lv->proposals[l]) & 15) != 0) return D2B_EINVAL;
+    P.proposals[l] = lv->proposals[l];
+    P.topk_idx[l] = lv->topk_idx[l];
+    P.topk_scores[l] = lv->topk_scores[l];
+    P.A[l] = lv->A[l];
+    P.k[l] = lv->k[l];
+    P.t0[l] = T;
+    T += lv->k[l];
+  }
+  P.t0[P.L] = T;
+  if (T == 0) return D2B_OK;
+  rpn_prepare_kernel<<<N, kThreads, 0, (cudaStream_t)stream>>>(P, T, image_hw, min_box_size, use_offsets, flat_boxes, nms_boxes,
+                                                               nms_scores, raw_scores, (long long*)cat_ids, nonfinite);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, int T, int post_nms_topk,
+                           const float* flat_boxes, const float* raw_scores, const int64_t* cat_ids, float* out_boxes,
+                           float* out_scores, int64_t* out_index, int64_t* counts, void* stream) {
+  if (N < 0 || T < 0 || post_nms_topk < 0) return D2B_EINVAL;
+  if (N == 0) return D2B_OK;
+  if (!counts) return D2B_EINVAL;
+  if (T == 0 || post_nms_topk == 0) {
+    D2B_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * N, (cudaStream_t)stream));
+    return D2B_OK;
+  }
+  if (!keep || !num_keep || !flat_boxes || !raw_scores || !cat_ids || !out_boxes || !out_scores || !out_index) return D2B_EINVAL;
+  rpn_select_kernel<<<N, kThreads, 0, (cudaStream_t)stream>>>((const long long*)keep, (const long long*)num_keep, T, post_nms_topk,
+                                                              flat_boxes, raw_scores, (const long long*)cat_ids, out_boxes,
+                                                              out_scores, (long long*)out_index, (long long*)counts);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}

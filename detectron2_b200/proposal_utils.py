@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 
-__all__ = ["find_top_rpn_proposals", "ProposalBoxes", "Proposals"]
+__all__ = ["find_top_rpn_proposals", "find_top_rpn_proposals_fixed", "ProposalBoxes", "Proposals"]
 
 
 class ProposalBoxes:
@@ -43,9 +43,84 @@ class Proposals:
         return len(self.proposal_boxes)
 
 
+def find_top_rpn_proposals_fixed(proposals: List[torch.Tensor], pred_objectness_logits: List[torch.Tensor],
+                                 image_sizes: List[Tuple[int, int]], nms_thresh: float, pre_nms_topk: int,
+                                 post_nms_topk: int, min_box_size: float):
+    """Sync-free, fixed-capacity form (CUDA tensors only): returns (boxes [N, post_nms_topk, 4], objectness logits
+    [N, post_nms_topk], counts [N] int64, nonfinite [1] int32) -- rows beyond counts[i] are zero.  The launch sequence
+    (torch.topk per level, d2b_rpn_prepare, d2b_nms, d2b_rpn_select) has static shapes: it can be captured in a CUDA graph."""
+    import ctypes as C
+
+    from . import _C
+    from ._C import check, ptr, stream_ptr
+
+    n = len(image_sizes)  # a list of (h, w), or an [N, 2] float32 CUDA tensor (needed inside a CUDA-graph capture)
+    device = proposals[0].device
+    _C.require_cuda(*proposals, *pred_objectness_logits)
+    L = len(proposals)
+    if L > _C.MAX_LEVELS:
+        raise RuntimeError("find_top_rpn_proposals: at most %d feature levels" % _C.MAX_LEVELS)
+    lv = _C.RpnLevels()
+    lv.num_levels = L
+    keepalive = []
+    t = 0
+    for l, (p_l, s_l) in enumerate(zip(proposals, pred_objectness_logits)):
+        k = min(s_l.shape[1], pre_nms_topk)
+        top_s, top_i = s_l.float().topk(k, dim=1)      # proposal_utils.py:84-88 (library top-k, one call per level)
+        p_c = p_l.float().contiguous()
+        keepalive += [top_s, top_i, p_c]
+        lv.proposals[l], lv.topk_idx[l], lv.topk_scores[l] = p_c.data_ptr(), top_i.data_ptr(), top_s.data_ptr()
+        lv.A[l], lv.k[l] = p_c.shape[1], k
+        t += k
+    if isinstance(image_sizes, torch.Tensor):
+        hw = image_sizes.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        hw = torch.tensor([[float(h), float(w)] for (h, w) in image_sizes], dtype=torch.float32).to(device)
+    m = n * t
+    f32 = dict(dtype=torch.float32, device=device)
+    flat_boxes, nms_boxes = torch.empty((m, 4), **f32), torch.empty((m, 4), **f32)
+    nms_scores, raw_scores = torch.empty((m,), **f32), torch.empty((m,), **f32)
+    cat_ids = torch.empty((m,), dtype=torch.int64, device=device)
+    nonfinite = torch.empty((1,), dtype=torch.int32, device=device)
+    out_boxes = torch.empty((n, post_nms_topk, 4), **f32)
+    out_scores = torch.empty((n, post_nms_topk), **f32)
+    out_index = torch.empty((n, post_nms_topk), dtype=torch.int64, device=device)
+    counts = torch.zeros((n,), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        # torchvision's batched_nms applies the coordinate trick per image only up to 100 000 coordinates (25 000 boxes)
+        check(_C.lib().d2b_rpn_prepare(C.byref(lv), n, ptr(hw), float(min_box_size), int(t * 4 <= 100_000), ptr(flat_boxes),
+                                       ptr(nms_boxes), ptr(nms_scores), ptr(raw_scores), ptr(cat_ids), ptr(nonfinite),
+                                       stream_ptr(device)), "rpn_prepare")
+        if m:
+            keep, num_keep = ops.nms_fixed(nms_boxes, nms_scores, cat_ids, float(nms_thresh), False, apply_offsets=False,
+                                           max_segment=max(int(lv.k[l]) for l in range(L)))
+            check(_C.lib().d2b_rpn_select(ptr(keep), ptr(num_keep), n, t, int(post_nms_topk), ptr(flat_boxes),
+                                          ptr(raw_scores), ptr(cat_ids), ptr(out_boxes), ptr(out_scores), ptr(out_index),
+                                          ptr(counts), stream_ptr(device)), "rpn_select")
+    del keepalive
+    return out_boxes, out_scores, counts, nonfinite
+
+
 def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits: List[torch.Tensor],
                            image_sizes: List[Tuple[int, int]], nms_thresh: float, pre_nms_topk: int,
                            post_nms_topk: int, min_box_size: float, training: bool):
+    if proposals[0].is_cuda:  # fused, fixed-capacity kernels + ONE host read of the output lengths
+        out_boxes, out_scores, counts, nonfinite = find_top_rpn_proposals_fixed(
+            proposals, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk, min_box_size)
+        host = torch.cat([counts, nonfinite.to(torch.int64)]).tolist()  # the one host sync: exactly-sized results
+        if training and host[-1]:  # same failure mode as the reference (:106-110); training only
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        dt = pred_objectness_logits[0].dtype
+        return [Proposals(sz, ProposalBoxes(out_boxes[i, :host[i]]), out_scores[i, :host[i]].to(dt))
+                for i, sz in enumerate(image_sizes)]
+    return _find_top_rpn_proposals_host(proposals, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk,
+                                        post_nms_topk, min_box_size, training)
+
+
+def _find_top_rpn_proposals_host(proposals, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk,
+                                 min_box_size, training):
+    """The same selection written with torch ops (the host-logic restatement that tests/test_host_logic_cpu.py pins to the
+    real reference function with the NMS call replaced by the oracle; the CUDA path above is the product)."""
     num_images = len(image_sizes)
     device = proposals[0].device
     num_levels = len(proposals)

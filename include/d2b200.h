@@ -145,6 +145,32 @@ int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_
             double iou_threshold, int flags, int64_t max_segment, int64_t* keep, int64_t* num_keep,
             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Batched RPN proposal selection around the NMS ----------------------------------------
+ * Replaces the per-image Python loop of detectron2/modeling/proposal_generator/proposal_utils.py:96-133 (boolean filtering,
+ * `.item()` sync, per-image batched_nms, slicing) by a fixed-capacity launch sequence for ALL images:
+ *   torch.topk per level (library)  ->  d2b_rpn_prepare  ->  d2b_nms(category = image*L + level, D2B_NMS_NO_OFFSET,
+ *   max_segment = pre_nms_topk)  ->  d2b_rpn_select.
+ * d2b_rpn_prepare: lv->proposals[l] [N,A_l,4] decoded boxes, lv->topk_idx[l] / topk_scores[l] [N,k_l] (the per-level top-k of
+ *   the objectness logits), image_hw [N,2] (h, w) on the device.  T = sum_l k_l candidates per image.  Writes, for all N*T
+ *   candidates: flat_boxes (clipped to the image; zeros for removed ones), nms_boxes (+ torchvision's per-image
+ *   level offsets when use_offsets), nms_scores (-inf for removed), raw_scores, cat_ids (image*L + level, or -1 = removed:
+ *   non-finite or not larger than min_box_size after clipping), nonfinite[1] (1 if any candidate was non-finite).
+ * d2b_rpn_select: keep / num_keep as returned by d2b_nms over the N*T candidates; out_boxes [N,post_nms_topk,4],
+ *   out_scores / out_index [N,post_nms_topk] (0-padded), counts [N] int64. */
+typedef struct {
+  int num_levels;
+  const float* proposals[D2B_MAX_LEVELS];
+  const int64_t* topk_idx[D2B_MAX_LEVELS];
+  const float* topk_scores[D2B_MAX_LEVELS];
+  int A[D2B_MAX_LEVELS], k[D2B_MAX_LEVELS];
+} d2b_rpn_levels;
+int d2b_rpn_prepare(const d2b_rpn_levels* lv, int N, const float* image_hw, float min_box_size, int use_offsets,
+                    float* flat_boxes, float* nms_boxes, float* nms_scores, float* raw_scores, int64_t* cat_ids,
+                    int* nonfinite, void* stream);
+int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, int T, int post_nms_topk,
+                   const float* flat_boxes, const float* raw_scores, const int64_t* cat_ids, float* out_boxes,
+                   float* out_scores, int64_t* out_index, int64_t* counts, void* stream);
+
 /* ---- Rotated-box IoU --------------------------------------------------------------------
  * Replaces torch.ops.detectron2.box_iou_rotated (csrc/vision.cpp:117,
  * csrc/box_iou_rotated/box_iou_rotated.h:20-33).  boxes1 [N,5], boxes2 [M,5] fp32 -> ious [N,M] fp32. */

@@ -855,6 +855,39 @@ def test_find_top_rpn_proposals_golden(golden):
         find_top_rpn_proposals([p.to(DEV) for p in props], [x.to(DEV) for x in logits], sizes, thr, pre, post, mbs, True)
 
 
+def test_find_top_rpn_proposals_fixed_in_cuda_graph(golden):
+    # the fixed-capacity form is a static launch sequence: captured once, replayed on new inputs, same results as eager
+    from detectron2_b200.proposal_utils import find_top_rpn_proposals, find_top_rpn_proposals_fixed
+    from test_oracle_pins import _rpn_fixture
+
+    d, props, logits, sizes, thr, pre, post, mbs = _rpn_fixture(golden)
+    pd, ld = [p.to(DEV).clone() for p in props], [x.to(DEV).clone() for x in logits]
+    hw = torch.tensor([[float(h), float(w)] for (h, w) in sizes], device=DEV)
+    find_top_rpn_proposals_fixed(pd, ld, hw, thr, pre, post, mbs)  # warm-up (allocations, smem opt-in) outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            ob, osc, cnt, bad = find_top_rpn_proposals_fixed(pd, ld, hw, thr, pre, post, mbs)
+    for rep in range(2):
+        if rep == 1:  # new inputs in the captured buffers: reversed image order
+            for p_ in pd:
+                p_.copy_(p_.flip(0).clone())
+            for l_ in ld:
+                l_.copy_(l_.flip(0).clone())
+            hw.copy_(hw.flip(0).clone())
+        g.replay()
+        torch.cuda.synchronize()
+        szs = sizes if rep == 0 else list(reversed(sizes))
+        ref = find_top_rpn_proposals([p_.clone() for p_ in pd], [l_.clone() for l_ in ld], szs, thr, pre, post, mbs, False)
+        for i, r in enumerate(ref):
+            c = int(cnt[i].item())
+            assert c == len(r) and torch.equal(ob[i, :c], r.proposal_boxes.tensor) and torch.equal(osc[i, :c], r.objectness_logits)
+            assert (ob[i, c:] == 0).all()
+    assert int(bad.item()) == 0
+
+
 def test_find_top_rpn_proposals_fpn_size_vs_oracle():
     # BASELINE config-2 shape: 5 levels, pre-NMS top 1000 per level, 2 images; oracle = per-image reference loop on CPU
     from detectron2_b200.proposal_utils import find_top_rpn_proposals
