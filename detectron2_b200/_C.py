@@ -64,6 +64,8 @@ def _declare(lib):
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64, i64p, i64p, vp, sz, vp]),
         "d2b_rpn_prepare": (i, [C.POINTER(RpnLevels), i, f32p, f, i, f32p, f32p, f32p, f32p, i64p, vp, vp]),
         "d2b_rpn_select": (i, [i64p, i64p, i, i, i, f32p, f32p, i64p, f32p, f32p, i64p, i64p, vp]),
+        "d2b_mask_loss_forward": (i, [f32p, i, i, i, u8p, i, i, i, f32p, i64p, i64p, f32p, u8p, vp]),
+        "d2b_mask_loss_backward": (i, [f32p, i, i, i, u8p, i64p, f32p, f32p, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
         "d2b_deform_conv_tc_shape_supported": (i, [C.POINTER(DcnParams), i]),
         "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i]),

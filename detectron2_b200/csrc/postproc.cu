@@ -198,3 +198,149 @@ D2B_API int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, 
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
+
+// ================================================================================================ mask targets + loss
+// Mask-head training target and loss in one pass:
+//   BitMasks.crop_and_resize (detectron2/structures/masks.py:193-224): RoIAlign(S x S, scale 1, sampling_ratio 0, aligned)
+//   of the proposal's ground-truth bitmask, thresholded at 0.5
+//   + the per-class gather and binary_cross_entropy_with_logits of mask_rcnn_loss (modeling/roi_heads/mask_head.py:60-112).
+// The reference first materialises one H x W byte mask PER PROPOSAL (BitMasks indexing, K x H x W bytes), converts it to
+// fp32, pools it, thresholds, gathers the class channel of the logits and reduces.  Here a CTA per proposal samples the
+// ground-truth mask it is matched to (mask_index) straight from the [G,H,W] byte tensor, one thread per output bin with the
+// reference's accumulation order (torchvision roi_align: sum over iy, ix of w1 v1 + w2 v2 + w3 v3 + w4 v4, then / count),
+// writes the 0/1 target (kept for the backward and the accuracy statistics) and the proposal's loss sum.
+namespace {
+
+struct Tap1 {
+  int lo, hi;
+  float wl, wh;
+};
+
+__device__ __forceinline__ Tap1 make_tap1(float v, int size) {  // torchvision roi_align bilinear_interpolate
+  Tap1 t;
+  if (v < -1.0f || v > (float)size) {
+    t.lo = t.hi = 0;
+    t.wl = t.wh = 0.f;
+    return t;
+  }
+  v = fmaxf(v, 0.f);
+  int lo = (int)v, hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    v = (float)lo;
+  } else {
+    hi = lo + 1;
+  }
+  const float l = v - (float)lo;
+  t.lo = lo;
+  t.hi = hi;
+  t.wh = l;
+  t.wl = 1.f - l;
+  return t;
+}
+
+__global__ void __launch_bounds__(256) mask_loss_fwd_kernel(const float* __restrict__ logits, int C, int S,
+                                                            const unsigned char* __restrict__ gt, int G, int H, int W,
+                                                            const float* __restrict__ boxes,
+                                                            const long long* __restrict__ mask_index,
+                                                            const long long* __restrict__ classes,
+                                                            float* __restrict__ loss_per_roi,
+                                                            unsigned char* __restrict__ targets) {
+  __shared__ float s_red[8];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const float* b = boxes + (size_t)k * 4;
+  // aligned = True, spatial_scale = 1: box - 0.5, no minimum size
+  const float sw = b[0] * 1.0f - 0.5f, sh = b[1] * 1.0f - 0.5f, ew = b[2] * 1.0f - 0.5f, eh = b[3] * 1.0f - 0.5f;
+  const float rw = ew - sw, rh = eh - sh;
+  const float bin_h = rh / (float)S, bin_w = rw / (float)S;
+  int gh = (int)ceilf(rh / (float)S), gw = (int)ceilf(rw / (float)S);
+  gh = max(gh, 0);
+  gw = max(gw, 0);
+  const float count = (float)max(gh * gw, 1);
+  long long mi = mask_index ? mask_index[k] : k;
+  const bool have_mask = mi >= 0 && mi < G;
+  const unsigned char* __restrict__ m = gt + (size_t)(have_mask ? mi : 0) * H * W;
+  const long long cls = classes ? classes[k] : 0;
+  const bool cls_ok = cls >= 0 && cls < C;
+  const float* __restrict__ lg = logits + ((size_t)k * C + (cls_ok ? cls : 0)) * S * S;
+  float acc_loss = 0.f;
+  for (int bin = tid; bin < S * S; bin += 256) {
+    const int ph = bin / S, pw = bin - ph * S;
+    float v = 0.f;
+    if (have_mask) {
+      for (int iy = 0; iy < gh; ++iy) {
+        const Tap1 ty = make_tap1(sh + (float)ph * bin_h + ((float)iy + .5f) * bin_h / (float)gh, H);
+        for (int ix = 0; ix < gw; ++ix) {
+          const Tap1 tx = make_tap1(sw + (float)pw * bin_w + ((float)ix + .5f) * bin_w / (float)gw, W);
+          const float v1 = m[(size_t)ty.lo * W + tx.lo] ? 1.f : 0.f, v2 = m[(size_t)ty.lo * W + tx.hi] ? 1.f : 0.f;
+          const float v3 = m[(size_t)ty.hi * W + tx.lo] ? 1.f : 0.f, v4 = m[(size_t)ty.hi * W + tx.hi] ? 1.f : 0.f;
+          v += (ty.wl * tx.wl) * v1 + (ty.wl * tx.wh) * v2 + (ty.wh * tx.wl) * v3 + (ty.wh * tx.wh) * v4;
+        }
+      }
+      v /= count;
+    }
+    const float t = v >= 0.5f ? 1.f : 0.f;
+    targets[(size_t)k * S * S + bin] = (unsigned char)(v >= 0.5f);
+    if (cls_ok) {
+      const float x = lg[bin];
+      // binary_cross_entropy_with_logits: (1 - t) x + max(-x, 0) + log(exp(-max) + exp(-x - max)),  max = max(-x, 0)
+      const float mxv = fmaxf(-x, 0.f);
+      acc_loss += (1.f - t) * x + mxv + logf(expf(-mxv) + expf(-x - mxv));
+    }
+  }
+  for (int o = 16; o; o >>= 1) acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = acc_loss;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    loss_per_roi[k] = s;
+  }
+}
+
+// grad_logits[k, c, :] = (c == class_k) ? (sigmoid(x) - t) * grad_scale[k] : 0      grid (K, C)
+__global__ void __launch_bounds__(256) mask_loss_bwd_kernel(const float* __restrict__ logits, int C, int S,
+                                                            const unsigned char* __restrict__ targets,
+                                                            const long long* __restrict__ classes,
+                                                            const float* __restrict__ grad_scale,
+                                                            float* __restrict__ grad_logits) {
+  const int k = blockIdx.x, c = blockIdx.y;
+  const long long cls = classes ? classes[k] : 0;
+  const size_t base = ((size_t)k * C + c) * S * S;
+  const float scale = grad_scale[k];  // d loss / d loss_per_roi[k]
+  for (int bin = threadIdx.x; bin < S * S; bin += 256) {
+    float gval = 0.f;
+    if (c == cls) {
+      const float x = logits[base + bin];
+      const float t = targets[(size_t)k * S * S + bin] ? 1.f : 0.f;
+      gval = (1.f / (1.f + expf(-x)) - t) * scale;
+    }
+    grad_logits[base + bin] = gval;
+  }
+}
+
+}  // namespace
+
+D2B_API int d2b_mask_loss_forward(const float* logits, int K, int C, int S, const uint8_t* gt_masks, int G, int H, int W,
+                                  const float* boxes, const int64_t* mask_index, const int64_t* classes,
+                                  float* loss_per_roi, uint8_t* targets, void* stream) {
+  if (K < 0 || C <= 0 || S <= 0 || G < 0 || H <= 0 || W <= 0) return D2B_EINVAL;
+  if (K == 0) return D2B_OK;
+  if (!logits || !gt_masks || !boxes || !loss_per_roi || !targets) return D2B_EINVAL;
+  mask_loss_fwd_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(logits, C, S, gt_masks, G, H, W, boxes, (const long long*)mask_index,
+                                                            (const long long*)classes, loss_per_roi, targets);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_mask_loss_backward(const float* logits, int K, int C, int S, const uint8_t* targets, const int64_t* classes,
+                                   const float* grad_scale, float* grad_logits, void* stream) {
+  if (K < 0 || C <= 0 || S <= 0 || C > 65535) return D2B_EINVAL;
+  if (K == 0) return D2B_OK;
+  if (!logits || !targets || !grad_scale || !grad_logits) return D2B_EINVAL;
+  dim3 grid(K, C);
+  mask_loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, C, S, targets, (const long long*)classes, grad_scale,
+                                                               grad_logits);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}

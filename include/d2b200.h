@@ -171,6 +171,22 @@ int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, int T, i
                    const float* flat_boxes, const float* raw_scores, const int64_t* cat_ids, float* out_boxes,
                    float* out_scores, int64_t* out_index, int64_t* counts, void* stream);
 
+/* ---- Mask-head training targets + loss ------------------------------------------------------
+ * Replaces, for one image, BitMasks.crop_and_resize (detectron2/structures/masks.py:193-224) + the class gather and
+ * binary_cross_entropy_with_logits of mask_rcnn_loss (modeling/roi_heads/mask_head.py:60-112).
+ *   logits [K,C,S,S] fp32 mask-head outputs of the image's K sampled proposals; gt_masks [G,H,W] bytes (0 / non-0);
+ *   boxes [K,4] proposal boxes; mask_index [K] int64 ground-truth mask of every proposal (NULL: proposal k uses mask k, the
+ *   reference's per-proposal BitMasks); classes [K] int64 (NULL: class-agnostic, channel 0).
+ *   loss_per_roi [K]: sum over the S*S bins of the BCE of the proposal's class channel (the caller sums and divides by the
+ *   total number of elements, "mean" reduction); targets [K,S,S] bytes: the 0/1 targets.
+ * Backward: grad_scale [K] = d loss / d loss_per_roi; grad_logits [K,C,S,S] fully written: (sigmoid(x) - t) * grad_scale[k]
+ * on the class channel, 0 elsewhere. */
+int d2b_mask_loss_forward(const float* logits, int K, int C, int S, const uint8_t* gt_masks, int G, int H, int W,
+                          const float* boxes, const int64_t* mask_index, const int64_t* classes,
+                          float* loss_per_roi, uint8_t* targets, void* stream);
+int d2b_mask_loss_backward(const float* logits, int K, int C, int S, const uint8_t* targets, const int64_t* classes,
+                           const float* grad_scale, float* grad_logits, void* stream);
+
 /* ---- Rotated-box IoU --------------------------------------------------------------------
  * Replaces torch.ops.detectron2.box_iou_rotated (csrc/vision.cpp:117,
  * csrc/box_iou_rotated/box_iou_rotated.h:20-33).  boxes1 [N,5], boxes2 [M,5] fp32 -> ious [N,M] fp32. */

@@ -1066,3 +1066,57 @@ def test_roialignv2_roialignrotated_match():
     rot = ROIPooler(output_size=14, scales=(1.0 / 16,), sampling_ratio=0, pooler_type="ROIAlignRotated")([feature], rois_rotated)
     assert v2.shape == rot.shape == (n * n_rois, c, 14, 14)
     assert torch.allclose(v2, rot, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------- mask targets + loss (8f-4)
+def test_mask_rcnn_loss_fused_vs_reference_expression():
+    # the reference expression: BitMasks[matched] -> crop_and_resize (our host restatement, pinned to the real reference
+    # function by tests/test_host_logic_cpu.py) -> gather of the class channel -> binary_cross_entropy_with_logits(mean)
+    from detectron2_b200.mask_head import mask_rcnn_loss
+    from detectron2_b200.postprocessing import crop_and_resize
+
+    g = torch.Generator().manual_seed(3)
+    ncls, s = 80, 28
+    gt, boxes, cls, midx = [], [], [], []
+    for (h, w, ng, k) in ((120, 167, 5, 37), (96, 133, 3, 20)):
+        m = torch.zeros(ng, h, w, dtype=torch.bool)
+        for j in range(ng):  # a few blobs per mask
+            cy, cx = torch.randint(10, h - 10, (1,), generator=g).item(), torch.randint(10, w - 10, (1,), generator=g).item()
+            ry, rx = torch.randint(5, 40, (1,), generator=g).item(), torch.randint(5, 50, (1,), generator=g).item()
+            yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+            m[j] = ((yy - cy).float() / ry) ** 2 + ((xx - cx).float() / rx) ** 2 <= 1.0
+        gt.append(m)
+        ctr = torch.rand(k, 2, generator=g) * torch.tensor([float(w), float(h)])
+        wh = 6 + torch.rand(k, 2, generator=g) * 70
+        b = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        b[0] = torch.tensor([-20.0, -10.0, w + 30.0, h + 15.0])  # larger than the image
+        boxes.append(b)
+        cls.append(torch.randint(0, ncls, (k,), generator=g))
+        midx.append(torch.randint(0, ng, (k,), generator=g))
+    total = sum(len(b) for b in boxes)
+    logits = torch.randn(total, ncls, s, s, generator=g) * 2
+    ld = logits.to(DEV).requires_grad_(True)
+    loss, targets = mask_rcnn_loss(ld, [m.to(DEV) for m in gt], [b.to(DEV) for b in boxes], [c.to(DEV) for c in cls],
+                                   [i.to(DEV) for i in midx])
+    # reference expression on the GPU ops
+    lr = logits.to(DEV).requires_grad_(True)
+    tref = torch.cat([crop_and_resize(m.to(DEV)[i.to(DEV)], b.to(DEV), s) for m, b, i in zip(gt, boxes, midx)])
+    pred = lr[torch.arange(total, device=DEV), torch.cat(cls).to(DEV)]
+    lref = torch.nn.functional.binary_cross_entropy_with_logits(pred, tref.to(torch.float32), reduction="mean")
+    mism = (targets != tref).sum().item()
+    assert mism <= 4, mism  # samples that land exactly on the 0.5 threshold may round differently (different summation order)
+    if mism == 0:
+        assert abs(loss.item() - lref.item()) <= 1e-5 * abs(lref.item()) + 1e-6
+    else:
+        assert abs(loss.item() - lref.item()) <= 1e-3 * abs(lref.item())
+    loss.backward()
+    lref.backward()
+    if mism == 0:
+        assert torch.allclose(ld.grad, lr.grad, rtol=1e-4, atol=1e-9)
+    # class-agnostic head, one mask per proposal (the reference's Instances layout)
+    la = torch.randn(len(boxes[0]), 1, s, s, generator=g).to(DEV)
+    per_prop = gt[0].to(DEV)[midx[0].to(DEV)]
+    loss_a, tg_a = mask_rcnn_loss(la, [per_prop], [boxes[0].to(DEV)])
+    tref_a = crop_and_resize(per_prop, boxes[0].to(DEV), s)
+    lref_a = torch.nn.functional.binary_cross_entropy_with_logits(la[:, 0], tref_a.float(), reduction="mean")
+    assert (tg_a != tref_a).sum().item() <= 2 and abs(loss_a.item() - lref_a.item()) <= 1e-3 * abs(lref_a.item())
