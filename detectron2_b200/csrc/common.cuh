@@ -25,6 +25,10 @@ __host__ __device__ static inline int d2b_cdiv(long long a, long long b) { retur
 
 constexpr int kNumSMs = 148;  // B200
 
+// up to D2B_MAX_ZERO device buffers zero-filled by one launch (abi.cu); null / empty entries are skipped
+#define D2B_MAX_ZERO 8
+int d2b_zero_buffers(void* const* ptrs, const size_t* bytes, int n, cudaStream_t stream);
+
 // Kernels that need more than 48 KB of dynamic shared memory must opt in once PER DEVICE.  The opt-in is remembered per
 // call site and device ordinal (lock-free bit mask), raised to the device maximum so that it covers every launch
 // configuration, and therefore never runs inside a CUDA-graph capture after the first eager call on that device.

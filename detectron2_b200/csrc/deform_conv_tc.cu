@@ -24,8 +24,8 @@
 //   * precision 1 ("bf16x3"): operands are split x = hi + lo (two bf16) and hi*hi + hi*lo + lo*hi is accumulated in fp32 --
 //     fp32-class accuracy (<= 1e-4 rel) at a third of the bf16 tensor peak.  precision 2: plain bf16 operands.
 //
-// Warp roles (576 threads, one CTA per SM): warps 0-15 gather / scatter / epilogue, warp 16 TMA producer (one lane),
-// warp 17 MMA issuer (one lane) and TMEM owner.
+// Warp roles (320 threads, one CTA per SM): warps 0-7 gather / scatter / epilogue, warp 8 TMA producer (one lane),
+// warp 9 MMA issuer (one lane) and TMEM owner.
 #include <algorithm>
 
 #include "common.cuh"
@@ -35,9 +35,12 @@ using namespace d2b_tc;
 
 namespace {
 
-constexpr int kWorkerWarps = 16;
-constexpr int kWorkers = kWorkerWarps * 32;  // 512
+// 8 worker warps with 200 registers each rather than 16 with 100: the gather is bound by bytes in flight (latency x
+// bandwidth), and a lane that keeps 32 LDG.128 in flight (8 pixels x 4 corners) doubles the bytes in flight per SM.
+constexpr int kWorkerWarps = 8;
+constexpr int kWorkers = kWorkerWarps * 32;  // 256
 constexpr int kThreads = kWorkers + 64;      // + producer warp + MMA warp
+constexpr int kRowsPerHalf = 128 / (2 * kWorkerWarps);  // pixel rows of a 128-row tile owned by one half-warp: 8
 constexpr int kTile = 16384;                 // [128 rows][128 B]
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kGcolPitch = 132;              // floats per pixel row of the drained gcol tile (128 + 4: conflict-free float4)
@@ -182,19 +185,32 @@ bool plan_k3(const TC& d, K3P& k) {
 // One 16-byte entry per (deformable group, kernel point, pixel): {code, lh, lw, mask} with
 // code = ((pos0 + W + 1) << 4) | valid-corner bits, pos0 = floor(h)*W + floor(w) (may be "virtual": row/col -1).
 // An entry of zeros means "sample outside (-1,H)x(-1,W)": contributes nothing (deform_conv_cuda_kernel.cu:273).
-__device__ __forceinline__ int4 make_tap(const TC& d, const float* __restrict__ offset, const float* __restrict__ mask,
-                                         int b, int dg, int kp, int p) {
+struct TapRaw {
+  float oh, ow, m;
+};
+
+// the three global loads of a tap (issued early so that their latency overlaps other work)
+__device__ __forceinline__ TapRaw tap_loads(const TC& d, const float* __restrict__ offset, const float* __restrict__ mask,
+                                            int b, int dg, int kp, int p) {
+  TapRaw r = {0.f, 0.f, 1.f};
+  if (p < d.HoWo) {
+    const size_t ob = (size_t)b * d.off_bs + ((size_t)dg * 2 * d.KK) * d.HoWo;
+    r.oh = __ldg(offset + ob + (size_t)(2 * kp) * d.HoWo + p);       // deform_conv_cuda_kernel.cu:263-269
+    r.ow = __ldg(offset + ob + (size_t)(2 * kp + 1) * d.HoWo + p);
+    if (mask) r.m = __ldg(mask + (size_t)b * d.mask_bs + ((size_t)dg * d.KK + kp) * d.HoWo + p);
+  }
+  return r;
+}
+
+__device__ __forceinline__ int4 tap_finish(const TC& d, const TapRaw& r, bool has_mask, int kp, int p) {
   int4 t = make_int4(0, 0, 0, 0);
   if (p < d.HoWo) {
     const int ho = p / d.Wo, wo = p - ho * d.Wo;
     const int ki = kp / d.kw, kj = kp - ki * d.kw;
-    const size_t ob = (size_t)b * d.off_bs + ((size_t)dg * 2 * d.KK) * d.HoWo;
-    const float oh = __ldg(offset + ob + (size_t)(2 * kp) * d.HoWo + p);       // deform_conv_cuda_kernel.cu:263-269
-    const float ow = __ldg(offset + ob + (size_t)(2 * kp + 1) * d.HoWo + p);
-    const float hf = (float)(ho * d.sh - d.ph + ki * d.dh) + oh;
-    const float wf = (float)(wo * d.sw - d.pw + kj * d.dw) + ow;
-    float m = mask ? __ldg(mask + (size_t)b * d.mask_bs + ((size_t)dg * d.KK + kp) * d.HoWo + p) : 1.f;
-    if (d.mask_sigmoid) m = 1.f / (1.f + expf(-m));  // resnet.py:311 mask.sigmoid()
+    const float hf = (float)(ho * d.sh - d.ph + ki * d.dh) + r.oh;
+    const float wf = (float)(wo * d.sw - d.pw + kj * d.dw) + r.ow;
+    float m = r.m;
+    if (has_mask && d.mask_sigmoid) m = 1.f / (1.f + expf(-m));  // resnet.py:311 mask.sigmoid()
     if (hf > -1.f && wf > -1.f && hf < (float)d.H && wf < (float)d.W) {
       const float hfl = floorf(hf), wfl = floorf(wf);
       const int hl = (int)hfl, wl = (int)wfl;
@@ -207,6 +223,11 @@ __device__ __forceinline__ int4 make_tap(const TC& d, const float* __restrict__ 
     }
   }
   return t;
+}
+
+__device__ __forceinline__ int4 make_tap(const TC& d, const float* __restrict__ offset, const float* __restrict__ mask,
+                                         int b, int dg, int kp, int p) {
+  return tap_finish(d, tap_loads(d, offset, mask, b, dg, kp, p), mask != nullptr, kp, p);
 }
 
 struct Taps4 {
@@ -311,15 +332,18 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
       uint8_t* a_hi = smem + s * k.stage_bytes;
       uint8_t* a_lo = a_hi + kTile;
       mbar_wait(&empty_bar[s], par ^ 1u);
+      {  // the half-warp's 8 pixel rows in ONE batch: 32 loads in flight per lane before the first use
+        int4 tap[kRowsPerHalf];
+        Taps4 c[kRowsPerHalf];
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int r0 = warp * 8 + it * 4 + half, r1 = r0 + 2;
-        const int4 tap0 = tp[r0], tap1 = tp[r1];
-        Taps4 c0, c1;
-        load_corners(xc, d.Cin, d.W, tap0.x, c0);
-        load_corners(xc, d.Cin, d.W, tap1.x, c1);
-        gather_store(c0, tap0, a_hi, a_lo, swz128((uint32_t)r0, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
-        gather_store(c1, tap1, a_hi, a_lo, swz128((uint32_t)r1, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        for (int j = 0; j < kRowsPerHalf; ++j) tap[j] = tp[warp * 2 * kRowsPerHalf + j * 2 + half];
+#pragma unroll
+        for (int j = 0; j < kRowsPerHalf; ++j) load_corners(xc, d.Cin, d.W, tap[j].x, c[j]);
+#pragma unroll
+        for (int j = 0; j < kRowsPerHalf; ++j) {
+          const uint32_t r = (uint32_t)(warp * 2 * kRowsPerHalf + j * 2 + half);
+          gather_store(c[j], tap[j], a_hi, a_lo, swz128(r, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        }
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
     const int ntot = k.gspan * k.BN;
     const int oc0 = sg0 * d.ops + oct * k.BN;
     const bool add_shift = ep.shift != nullptr && blockIdx.z == 0;
-    for (int c16 = cgrp; c16 * 16 < ntot; c16 += 4) {
+    for (int c16 = cgrp; c16 * 16 < ntot; c16 += kWorkerWarps / 4) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
       tmem_ld_wait();
@@ -477,13 +501,16 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
     const int quad = warp & 3, cq = warp >> 2;
     const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin;
     float* __restrict__ gimg = gxh ? gxh + (size_t)b * d.H * d.W * d.Cin : nullptr;
-    float sh[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int R = kRowsPerHalf;  // pixel rows of the tile owned by this half-warp (fixed for the whole kernel)
+    float sh[R], sw[R], sm[R];       // running sums over channels of the current (deformable group, kernel point)
+#pragma unroll
+    for (int j = 0; j < R; ++j) sh[j] = sw[j] = sm[j] = 0.f;
     int cur_kp = -1, cur_dg = -1;
 
     auto flush = [&]() {
       if (cur_kp < 0) return;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < R; ++j) {
 #pragma unroll
         for (int o = 8; o; o >>= 1) {
           sh[j] += __shfl_xor_sync(0xffffffffu, sh[j], o);
@@ -491,19 +518,21 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
           sm[j] += __shfl_xor_sync(0xffffffffu, sm[j], o);
         }
       }
-      if (q < 12) {
-        const int j = q / 3, which = q - j * 3;
+      // 3 * R values per half-warp, written by its 16 lanes
+      for (int o = q; o < 3 * R; o += 16) {
+        const int j = o / 3, which = o - j * 3;
         float v = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
+        for (int jj = 0; jj < R; ++jj)
           if (jj == j) v = which == 0 ? sh[jj] : (which == 1 ? sw[jj] : sm[jj]);
-        const int p = p0 + warp * 8 + j * 2 + half;
+        const int row = warp * 2 * R + j * 2 + half;
+        const int p = p0 + row;
         if (p < d.HoWo) {
           if (which < 2) {
             if (goff) red_add(goff + (size_t)b * d.off_bs + ((size_t)cur_dg * 2 * d.KK + 2 * cur_kp + which) * d.HoWo + p, v);
           } else if (gmask) {
             if (d.mask_sigmoid) {  // gradient w.r.t. the logit: m (1 - m)
-              const float m = __int_as_float(taps[((cur_dg - dg0) * nkp + (cur_kp - kp0)) * 128 + warp * 8 + j * 2 + half].w);
+              const float m = __int_as_float(taps[((cur_dg - dg0) * nkp + (cur_kp - kp0)) * 128 + row].w);
               v *= m * (1.f - m);
             }
             red_add(gmask + (size_t)b * d.mask_bs + ((size_t)cur_dg * d.KK + cur_kp) * d.HoWo + p, v);
@@ -511,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sh[j] = sw[j] = sm[j] = 0.f;
+      for (int j = 0; j < R; ++j) sh[j] = sw[j] = sm[j] = 0.f;
     };
 
     for (int ml = 0; ml < nm; ++ml) {
@@ -520,17 +549,17 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
       const int nu = (2 * m + 1 < d.U) ? 2 : 1;
       mbar_wait(&acc_full[buf], (uint32_t)((ml >> 1) & 1));
       tc_fence_after();
-      // ---- drain: this warp's 32 TMEM lanes (pixels) x 32 of the 128 columns -> gcol[px][col]
-      if (cq * 32 < nu * 64) {
-        float* dst = gcol + (quad * 32 + lane) * kGcolPitch + cq * 32;
+      // ---- drain: this warp's 32 TMEM lanes (pixels) x 64 of the 128 columns -> gcol[px][col]
+      if (cq * 64 < nu * 64) {
+        float* dst = gcol + (quad * 32 + lane) * kGcolPitch + cq * 64;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
+        for (int h4 = 0; h4 < 4; ++h4) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cq * 32 + h2 * 16), r);
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cq * 64 + h4 * 16), r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(dst + h2 * 16 + i * 4) =
+            *reinterpret_cast<float4*>(dst + h4 * 16 + i * 4) =
                 make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                             __uint_as_float(r[4 * i + 3]));
         }
@@ -553,26 +582,25 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
         const int4* __restrict__ tp = taps + ((dg - dg0) * nkp + (kp - kp0)) * 128;
         const float* __restrict__ xc = ximg + cbase + q * 4;
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int ra = warp * 8 + it * 4 + half, rb = ra + 2;
-          const int4 tapa = tp[ra], tapb = tp[rb];
-          Taps4 ca, cbv;
-          load_corners(xc, d.Cin, d.W, tapa.x, ca);
-          load_corners(xc, d.Cin, d.W, tapb.x, cbv);
+        for (int it = 0; it < R / 4; ++it) {  // 4 pixel rows per batch: 16 loads in flight per lane, then 16 reductions
+          int4 tap[4];
+          Taps4 c[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int4 tap = e ? tapb : tapa;
-            if ((tap.x & 15) == 0) continue;  // sample outside the image: no gradient anywhere
-            const Taps4& c = e ? cbv : ca;
-            const int row = e ? rb : ra;
-            const int j = it * 2 + e;
+          for (int e = 0; e < 4; ++e) tap[e] = tp[warp * 2 * R + (it * 4 + e) * 2 + half];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) load_corners(xc, d.Cin, d.W, tap[e].x, c[e]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((tap[e].x & 15) == 0) continue;  // sample outside the image: no gradient anywhere
+            const int j = it * 4 + e;
+            const int row = warp * 2 * R + j * 2 + half;
             const float4 g4 = *reinterpret_cast<const float4*>(gcol + row * kGcolPitch + ul * 64 + q * 4);
-            const float lh = __int_as_float(tap.y), lw = __int_as_float(tap.z), mk = __int_as_float(tap.w);
+            const float lh = __int_as_float(tap[e].y), lw = __int_as_float(tap[e].z), mk = __int_as_float(tap[e].w);
             const float hh = 1.f - lh, hw = 1.f - lw;
             const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
             const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-            const float a0[4] = {c.v0.x, c.v0.y, c.v0.z, c.v0.w}, a1[4] = {c.v1.x, c.v1.y, c.v1.z, c.v1.w};
-            const float a2[4] = {c.v2.x, c.v2.y, c.v2.z, c.v2.w}, a3[4] = {c.v3.x, c.v3.y, c.v3.z, c.v3.w};
+            const float a0[4] = {c[e].v0.x, c[e].v0.y, c[e].v0.z, c[e].v0.w}, a1[4] = {c[e].v1.x, c[e].v1.y, c[e].v1.z, c[e].v1.w};
+            const float a2[4] = {c[e].v2.x, c[e].v2.y, c[e].v2.z, c[e].v2.w}, a3[4] = {c[e].v3.x, c[e].v3.y, c[e].v3.z, c[e].v3.w};
             float gm[4];
             float ah = 0.f, aw = 0.f, am = 0.f;
 #pragma unroll
@@ -587,12 +615,12 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
             sw[j] += aw;
             sm[j] += am;
             if (gimg) {
-              const int pos0 = (tap.x >> 4) - d.W - 1;
+              const int pos0 = (tap[e].x >> 4) - d.W - 1;
               float* gp = gimg + (long long)pos0 * d.Cin + cbase + q * 4;
-              if (tap.x & 1) red_add_v4(gp, gm[0] * w0, gm[1] * w0, gm[2] * w0, gm[3] * w0);
-              if (tap.x & 2) red_add_v4(gp + d.Cin, gm[0] * w1, gm[1] * w1, gm[2] * w1, gm[3] * w1);
-              if (tap.x & 4) red_add_v4(gp + (size_t)d.W * d.Cin, gm[0] * w2, gm[1] * w2, gm[2] * w2, gm[3] * w2);
-              if (tap.x & 8) red_add_v4(gp + (size_t)(d.W + 1) * d.Cin, gm[0] * w3, gm[1] * w3, gm[2] * w3, gm[3] * w3);
+              if (tap[e].x & 1) red_add_v4(gp, gm[0] * w0, gm[1] * w0, gm[2] * w0, gm[3] * w0);
+              if (tap[e].x & 2) red_add_v4(gp + d.Cin, gm[0] * w1, gm[1] * w1, gm[2] * w1, gm[3] * w1);
+              if (tap[e].x & 4) red_add_v4(gp + (size_t)d.W * d.Cin, gm[0] * w2, gm[1] * w2, gm[2] * w2, gm[3] * w2);
+              if (tap[e].x & 8) red_add_v4(gp + (size_t)(d.W + 1) * d.Cin, gm[0] * w3, gm[1] * w3, gm[2] * w3, gm[3] * w3);
             }
           }
         }
@@ -708,35 +736,58 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
     const int kp = u_ok ? u / d.cbs : 0, cb = u_ok ? u - kp * d.cbs : 0;
     const int cbase = sg * d.cps + cb * 64;
     const int dg = cbase / d.cpdg;
-    // lanes 0..7 build the taps of this warp's 4 pixels x 2 units for every stage
-    const int tl_half = (lane >> 2) & 1, tl_j = lane & 3;
+    // lanes 0..15 build the taps of this warp's 8 pixels x 2 units; the loads of the NEXT stage's offsets / mask are issued
+    // before this stage's gather and consumed after it, so that their latency is hidden behind the gather
+    constexpr int PX = 64 / kWorkerWarps;  // pixels of a stage per warp: 8
+    const int tl_half = (lane >> 3) & 1, tl_j = lane & 7;
     const int tl_u = 2 * mb + tl_half;
-    const int tl_kp = tl_u < d.U ? tl_u / d.cbs : 0;
-    const int tl_dg = tl_u < d.U ? (sg * d.cps + (tl_u - tl_kp * d.cbs) * 64) / d.cpdg : 0;
-    int4* my_taps = tap_s + warp * 8;
+    const bool tl_ok = lane < 2 * PX && tl_u < d.U;
+    const int tl_kp = tl_ok ? tl_u / d.cbs : 0;
+    const int tl_dg = tl_ok ? (sg * d.cps + (tl_u - tl_kp * d.cbs) * 64) / d.cpdg : 0;
+    int4* my_taps = tap_s + warp * 2 * (2 * PX);  // [2 buffers][2 units][PX]
+    auto stage_of = [&](int i, int& b, int& pbase) {
+      const int gs = gs0 + i;
+      b = gs / d.stages_img;
+      pbase = (gs - b * d.stages_img) * 64;
+    };
+    if (ns > 0) {
+      int b0, pb0;
+      stage_of(0, b0, pb0);
+      if (lane < 2 * PX) my_taps[lane] = tl_ok ? make_tap(d, offset, mask, b0, tl_dg, tl_kp, pb0 + warp * PX + tl_j) : make_int4(0, 0, 0, 0);
+    }
+    __syncwarp();
     for (int i = 0; i < ns; ++i) {
       const int s = i % k.S;
       const uint32_t par = (uint32_t)((i / k.S) & 1);
-      const int gs = gs0 + i;
-      const int b = gs / d.stages_img, pbase = (gs - b * d.stages_img) * 64;
+      int b, pbase, bn = 0, pbn = 0;
+      stage_of(i, b, pbase);
+      const bool have_next = i + 1 < ns;
+      TapRaw raw = {0.f, 0.f, 1.f};
+      if (have_next) {
+        stage_of(i + 1, bn, pbn);
+        if (tl_ok) raw = tap_loads(d, offset, mask, bn, tl_dg, tl_kp, pbn + warp * PX + tl_j);
+      }
       const float* __restrict__ xc = xh + (size_t)b * d.H * d.W * d.Cin + cbase + q * 4;
       uint8_t* a_hi = smem + s * k.stage_bytes + half * 8192;
       uint8_t* a_lo = a_hi + kTile;
-      if (lane < 8)
-        my_taps[lane] = tl_u < d.U ? make_tap(d, offset, mask, b, tl_dg, tl_kp, pbase + warp * 4 + tl_j) : make_int4(0, 0, 0, 0);
-      __syncwarp();
+      const int4* cur = my_taps + (i & 1) * (2 * PX) + half * PX;
       mbar_wait(&empty_bar[s], par ^ 1u);
+      {
+        int4 tap[PX];
+        Taps4 c[PX];
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int j0 = it * 2, j1 = j0 + 1;
-        const int4 tap0 = my_taps[half * 4 + j0], tap1 = my_taps[half * 4 + j1];
-        Taps4 c0, c1;
-        load_corners(xc, d.Cin, d.W, tap0.x, c0);
-        load_corners(xc, d.Cin, d.W, tap1.x, c1);
-        const int r0 = warp * 4 + j0, r1 = r0 + 1;
-        gather_store(c0, tap0, a_hi, a_lo, swz128((uint32_t)r0, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
-        gather_store(c1, tap1, a_hi, a_lo, swz128((uint32_t)r1, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        for (int j = 0; j < PX; ++j) tap[j] = cur[j];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) load_corners(xc, d.Cin, d.W, tap[j].x, c[j]);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+          const uint32_t r = (uint32_t)(warp * PX + j);
+          gather_store(c[j], tap[j], a_hi, a_lo, swz128(r, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
+        }
       }
+      if (have_next && lane < 2 * PX)
+        my_taps[((i + 1) & 1) * (2 * PX) + lane] =
+            tl_ok ? tap_finish(d, raw, mask != nullptr, tl_kp, pbn + warp * PX + tl_j) : make_int4(0, 0, 0, 0);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
@@ -751,7 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
     const int ekp = row_ok ? eu / d.cbs : 0;
     const int ec = sg * d.cps + (row_ok ? eu - ekp * d.cbs : 0) * 64 + (row & 63);  // global input channel
     const int egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
-    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += 4) {
+    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += kWorkerWarps / 4) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
       tmem_ld_wait();
@@ -892,30 +943,35 @@ __device__ __forceinline__ float gout_elem(const float* __restrict__ gout, const
 __global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __restrict__ gout,
                                                                 const float* __restrict__ ysaved, const Epi ep, const TC d,
                                                                 uint8_t* __restrict__ dst) {
-  __shared__ float t[64][129];
+  // grid (tiles, 4): a CTA converts 32 of the tile's 128 pixel rows -- 4x the CTAs of a tile-per-CTA layout, which matters for
+  // the small maps (res5: 144 tiles on 148 SMs)
+  __shared__ float t[64][33];
   const long long tile = blockIdx.x;
   const int ks = (int)(tile % d.nks);
   const int sg = (int)((tile / d.nks) % d.SG);
   const int pt = (int)((tile / ((long long)d.nks * d.SG)) % d.tiles_img);
   const int b = (int)(tile / ((long long)d.nks * d.SG * d.tiles_img));
-  const int p0 = pt * 128, oc0 = sg * d.ops + ks * 64;
+  const int r0 = blockIdx.y * 32;
+  const int p0 = pt * 128 + r0, oc0 = sg * d.ops + ks * 64;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 128; e += 256) {
-    const int o = e >> 7, pp = e & 127;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // 8 independent loads per thread: 32 pixels (one 128-byte run) of 64 channels
+    const int e = tid + i * 256;
+    const int o = e >> 5, pp = e & 31;
     const int p = p0 + pp;
     t[o][pp] = p < d.HoWo ? gout_elem(gout, ysaved, ep, ((size_t)b * d.Cout + oc0 + o) * d.HoWo + p, oc0 + o) : 0.f;
   }
   __syncthreads();
   uint8_t* base = dst + tile * (size_t)(2 * kTile);
-  for (int e = tid; e < 128 * 8; e += 256) {
-    const int r = e >> 3, c16 = e & 7;
+  {
+    const int r = tid >> 3, c16 = tid & 7;  // 32 rows x 8 chunks = 256 threads
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = t[c16 * 8 + i][r];
     uint4 hi, lo;
     split8(v, hi, lo);
-    *reinterpret_cast<uint4*>(base + swz128((uint32_t)r, (uint32_t)c16)) = hi;
-    *reinterpret_cast<uint4*>(base + kTile + swz128((uint32_t)r, (uint32_t)c16)) = lo;
+    *reinterpret_cast<uint4*>(base + swz128((uint32_t)(r0 + r), (uint32_t)c16)) = hi;
+    *reinterpret_cast<uint4*>(base + kTile + swz128((uint32_t)(r0 + r), (uint32_t)c16)) = lo;
   }
 }
 
@@ -1113,11 +1169,11 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     if (grad_offset) grad_mask = grad_offset + (size_t)d.DG * 2 * d.KK * d.HoWo;
   }
   const Epi ep = {scale, nullptr, relu};
-  if (grad_offset && noff) D2B_CUDA(cudaMemsetAsync(grad_offset, 0, noff * 4, stream));
-  if (grad_mask && nm && !fused_om) D2B_CUDA(cudaMemsetAsync(grad_mask, 0, nm * 4, stream));  // fused: inside grad_offset
-  if (grad_weight) D2B_CUDA(cudaMemsetAsync(grad_weight, 0, nw * 4, stream));
-  if (d.N == 0) return D2B_OK;
-  if (!need_data && !need_weight) return D2B_OK;
+  if (d.N == 0 || (!need_data && !need_weight)) {
+    void* zp[3] = {grad_offset, fused_om ? nullptr : grad_mask, grad_weight};
+    size_t zb[3] = {noff * 4, nm * 4, nw * 4};
+    return d2b_zero_buffers(zp, zb, 3, stream);
+  }
   if (!workspace || workspace_bytes < d2b_deform_conv_tc_bwd_workspace(p, x_nhwc, need_data, need_weight)) return D2B_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15)) ||
       (x_nhwc && grad_x && (reinterpret_cast<uintptr_t>(grad_x) & 15)))
@@ -1133,19 +1189,22 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     if (rc) return rc;
     xh = xn;
   }
+  float* gxh = nullptr;
+  if (need_data && grad_x) gxh = x_nhwc ? grad_x : reinterpret_cast<float*>(ws);
+  {  // every accumulated output of the call zero-filled by one launch (grad_mask of the fused layout lives inside grad_offset)
+    void* zp[4] = {grad_offset, fused_om ? nullptr : grad_mask, grad_weight, gxh};
+    size_t zb[4] = {noff * 4, nm * 4, nw * 4, nx * 4};
+    int rc = d2b_zero_buffers(zp, zb, 4, stream);
+    if (rc) return rc;
+  }
   if (need_data) {
-    float* gxh = nullptr;
-    if (grad_x) {
-      if (x_nhwc) gxh = grad_x;
-      else gxh = reinterpret_cast<float*>(ws);
-      D2B_CUDA(cudaMemsetAsync(gxh, 0, nx * 4, stream));
-    }
     if (!x_nhwc) ws += xbytes;
     uint8_t* gt = ws;
     ws += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);
     uint8_t* wt = ws;
     ws += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);
-    dcn_gout_px_tiles_kernel<<<(unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 256, 0, stream>>>(grad_out, y_saved, ep, d, gt);
+    dcn_gout_px_tiles_kernel<<<dim3((unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 4), 256, 0, stream>>>(grad_out, y_saved,
+                                                                                                       ep, d, gt);
     D2B_CHECK_LAUNCH();
     {
       const long long total = (long long)d.SG * d.MC * d.nks * 128 * 8;

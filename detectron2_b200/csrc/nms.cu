@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(kRankWarps * 32) nms_rank_kernel(const float* 
   }
 }
 
-// ---- kernel 2: IoU bitmask, one CTA per block of 64 rows (positions of the category-major order).  A row only meets the
-// later boxes of its own category: columns (row, seg_hi[row]).  Word w of row r (64 columns starting at block (r/64)+w) lives
+// ---- kernel 2: IoU bitmask, one CTA per 64 x 64 tile (row block x word plane; tiles no row reaches exit at once).  A row only
+// meets the later boxes of its own category: columns (row, seg_hi[row]).  Word w of row r (64 columns starting at block (r/64)+w) lives
 // at maskT[w * M + r] (word-plane-major: the CTA's writes and the scan's reads are both coalesced); `wcap` planes, sized
 // from the caller's bound on the category size -- not from M.
 // Thread layout: kSub threads per row, each testing 64/kSub columns, partial words OR-ed with warp shuffles.  The rotated
@@ -329,18 +329,23 @@ __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __rest
                                                              const float* __restrict__ clsf_of_pos,
                                                              const NmsCtrl* __restrict__ ctrl, int apply_offsets, int M,
                                                              int wcap, double thr, unsigned long long* __restrict__ maskT) {
+  // grid (row blocks, word planes): CTA (rb, w) owns the 64 x 64 tile of rows [64 rb, +64) against columns [64 (rb + w), +64)
   constexpr int D = ROT ? 5 : 4;
   constexpr int kCols = 64 / kSub;
   __shared__ float cbox[64 * D];
   __shared__ int s_hi;
   const int rb = blockIdx.x, r0 = rb * 64;
+  const int cb = rb + (int)blockIdx.y, c0 = cb * 64;
+  if (c0 >= M) return;
   const int lrow = threadIdx.x / kSub, sub = threadIdx.x % kSub;
   const int row = r0 + lrow;
   const bool row_ok = row < M;
   const int my_hi = row_ok ? seg_hi_of_pos[row] : 0;
   if (threadIdx.x == 0) s_hi = 0;
   __syncthreads();
-  if (sub == 0 && row_ok) atomicMax(&s_hi, my_hi);
+  if (sub == 0 && row_ok && my_hi > c0) atomicMax(&s_hi, my_hi);
+  __syncthreads();
+  if (s_hi == 0) return;  // no row of this block reaches the column block (block-uniform): nothing to write
   // batched-NMS coordinate offsets, fp32 like the reference: axis-aligned box + idx*(max+1); rotated centre + idx*(max-min+1)
   float scale = 0.f;
   if (apply_offsets) scale = ROT ? (dec_f(ctrl->mx) - (-dec_f(ctrl->mn_neg)) + 1.0f) : (dec_f(ctrl->mx) + 1.0f);
@@ -356,47 +361,40 @@ __global__ void __launch_bounds__(64 * kSub) nms_mask_kernel(const float* __rest
       a[3] += off;
     }
   }
-  __syncthreads();
-  // a category larger than the caller's bound (flagged by the rank kernel) is truncated to the planes that exist
-  const int cb_last = min((s_hi - 1) >> 6, rb + wcap - 1);
-  const float area_a = ROT ? 0.f : (a[2] - a[0]) * (a[3] - a[1]);
-  for (int cb = rb; cb <= cb_last; ++cb) {
-    const int c0 = cb * 64;
-    const int nc = min(64, M - c0);
-    __syncthreads();
-    for (int t = threadIdx.x; t < nc * D; t += 64 * kSub) {
-      const int j = t / D, q = t - j * D;
-      float v = sb[(size_t)c0 * D + t];
-      if (apply_offsets && (ROT ? q < 2 : true)) v += clsf_of_pos[c0 + j] * scale;
-      cbox[t] = v;
-    }
-    __syncthreads();
-    // rows whose category ends before this block have an empty column range (jend <= jbeg) and write nothing, but stay in
-    // the loop: the shuffles and barriers below are executed by every lane
-    const bool active = row_ok && c0 < my_hi;
-    unsigned long long bits = 0ull;
-    const int jbeg = max(sub * kCols, row + 1 - c0), jend = active ? min(min(nc, (sub + 1) * kCols), my_hi - c0) : 0;
-    if (ROT) {
-      for (int j = jbeg; j < jend; ++j) {
-        const float iou = rotated_iou(a, cbox + j * 5);
-        if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
-      }
-    } else {
-      for (int j = jbeg; j < jend; ++j) {
-        const float* b = cbox + j * 4;
-        const float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
-        const float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
-        const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
-        const float inter = w * h;
-        const float area_b = (b[2] - b[0]) * (b[3] - b[1]);
-        const float ovr = inter / (area_a + area_b - inter);
-        if ((double)ovr > thr) bits |= 1ull << j;  // torchvision nms: strict
-      }
-    }
-#pragma unroll
-    for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
-    if (active && sub == 0) maskT[(size_t)(cb - rb) * M + row] = bits;
+  const int nc = min(64, M - c0);
+  for (int t = threadIdx.x; t < nc * D; t += 64 * kSub) {
+    const int j = t / D, q = t - j * D;
+    float v = sb[(size_t)c0 * D + t];
+    if (apply_offsets && (ROT ? q < 2 : true)) v += clsf_of_pos[c0 + j] * scale;
+    cbox[t] = v;
   }
+  __syncthreads();
+  // rows whose category ends before this block have an empty column range and write nothing, but every lane takes part in
+  // the shuffles below
+  const bool active = row_ok && c0 < my_hi;
+  unsigned long long bits = 0ull;
+  const int jbeg = max(sub * kCols, row + 1 - c0), jend = active ? min(min(nc, (sub + 1) * kCols), my_hi - c0) : 0;
+  if (ROT) {
+    for (int j = jbeg; j < jend; ++j) {
+      const float iou = rotated_iou(a, cbox + j * 5);
+      if ((double)iou >= thr) bits |= 1ull << j;  // nms_rotated_cpu.cpp:54
+    }
+  } else {
+    const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
+    for (int j = jbeg; j < jend; ++j) {
+      const float* b = cbox + j * 4;
+      const float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
+      const float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
+      const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+      const float inter = w * h;
+      const float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+      const float ovr = inter / (area_a + area_b - inter);
+      if ((double)ovr > thr) bits |= 1ull << j;  // torchvision nms: strict
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < kSub; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);  // the kSub lanes of a row are adjacent
+  if (active && sub == 0) maskT[(size_t)blockIdx.y * M + row] = bits;
 }
 
 constexpr int kScanThreads = 512;
@@ -429,9 +427,9 @@ __device__ __forceinline__ int block_excl_scan(int v, int* __restrict__ warp_tot
 
 // ---- kernel 3: greedy scan over the bitmask, one CTA per category segment (plain NMS = one segment), then -- in the CTA
 // that finishes last -- compaction of the kept boxes in global score order.
-// dynamic smem: removed[] (uint64), one word per 64-box block of the segment.  Per block b: (B) thread 0 resolves the
-// intra-block chain from removed[b] and the diagonal word of each row; (C) the warps OR the kept rows into the `removed`
-// words of the later blocks.  Everything the next block needs from global memory (its diagonal words, its rows of the later
+// dynamic smem: removed[] (uint64), one word per 64-box block of the segment.  Per block b: (B) warp 0 resolves the greedy
+// selection inside the block from removed[b] and the diagonal word of each row in a few parallel rounds; (C) the warps OR the
+// kept rows into the `removed` words of the later blocks.  Everything the next block needs from global memory (its diagonal words, its rows of the later
 // columns) is requested one full iteration ahead and parked in registers, so the serial chain never waits on L2.
 __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigned long long* __restrict__ maskT,
                                                                    const int* __restrict__ grank_of_pos,
@@ -489,44 +487,29 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
       const int lo = max(p0 - b * 64, 0), hi = min(p1 - b * 64, 64);  // rows [lo, hi) of this block belong to the segment
       const unsigned long long vmask =
           (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
-      // ---- step B: intra-block chain.  One thread, branch-free: per row the dependent path is
-      //      bit test -> mask -> and/or (about four ALU latencies); the diagonal words are pre-read from shared memory
-      //      sixteen rows at a time so that no load sits on the chain.
-      if (tid == 0) {
-        const unsigned long long rem = removed[b - b0];
-        unsigned rlo = (unsigned)rem, rhi = (unsigned)(rem >> 32), klo = 0u, khi = 0u;
-        const ulonglong2* dg = reinterpret_cast<const ulonglong2*>(s_diag[b & 1]);
-        const unsigned vlo = (unsigned)vmask, vhi = (unsigned)(vmask >> 32);
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          ulonglong2 d[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int i = blk * 16 + q;
-            const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
-            const unsigned m = 0u - ((~rlo & vlo) >> i & 1u);  // all-ones when row i is alive
-            klo |= m & (1u << i);
-            rlo |= m & (unsigned)dw;
-            rhi |= m & (unsigned)(dw >> 32);
-          }
+      // ---- step B: greedy selection inside the block, by warp 0 in parallel ROUNDS instead of a 64-step serial chain.
+      //      U = rows still undecided.  A row of U that no other row of U suppresses is kept (every earlier row that could
+      //      still suppress it is undecided too, and would show up in T); its own suppressions leave U.  The lowest row of U
+      //      always qualifies (the diagonal words only hold later columns), so a round decides at least one row -- in practice
+      //      most of them: the number of rounds is the longest suppression chain inside the block (a handful), each round two
+      //      warp-wide OR reductions.  Same result as the sequential greedy scan.
+      if (warp == 0) {
+        const ulonglong2 dd = reinterpret_cast<const ulonglong2*>(s_diag[b & 1])[lane];  // rows 2*lane, 2*lane + 1
+        unsigned long long U = vmask & ~removed[b - b0], K = 0ull;
+        while (U) {
+          const bool u0 = (U >> (2 * lane)) & 1ull, u1 = (U >> (2 * lane + 1)) & 1ull;
+          unsigned long long t = (u0 ? dd.x : 0ull) | (u1 ? dd.y : 0ull);
+          t = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(t >> 32)) << 32) |
+              __reduce_or_sync(0xffffffffu, (unsigned)t);
+          const unsigned long long Kr = U & ~t;
+          K |= Kr;
+          const bool k0b = (Kr >> (2 * lane)) & 1ull, k1b = (Kr >> (2 * lane + 1)) & 1ull;
+          unsigned long long rm = (k0b ? dd.x : 0ull) | (k1b ? dd.y : 0ull);
+          rm = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(rm >> 32)) << 32) |
+               __reduce_or_sync(0xffffffffu, (unsigned)rm);
+          U &= ~Kr & ~rm;
         }
-#pragma unroll
-        for (int blk = 2; blk < 4; ++blk) {
-          ulonglong2 d[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) d[q] = dg[blk * 8 + q];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int i = (blk - 2) * 16 + q;
-            const unsigned long long dw = (q & 1) ? d[q >> 1].y : d[q >> 1].x;
-            const unsigned m = 0u - ((~rhi & vhi) >> i & 1u);
-            khi |= m & (1u << i);
-            rhi |= m & (unsigned)(dw >> 32);
-          }
-        }
-        s_kept = ((unsigned long long)khi << 32) | klo;
+        if (lane == 0) s_kept = K;
       }
       __syncthreads();
       const unsigned long long kept = s_kept;
@@ -655,7 +638,7 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   if (workspace_bytes < w.total) return D2B_EWORKSPACE;
   const int m = (int)M, nb = (m + 63) / 64;
   const size_t smem = (size_t)(w.wcap + 1) * sizeof(unsigned long long);
-  if (smem > 200 * 1024) return D2B_EUNSUPPORTED;
+  if (smem > 200 * 1024 || w.wcap > 65535) return D2B_EUNSUPPORTED;
   D2B_CUDA(cudaMemsetAsync(w.ctrl, 0, w.zero_bytes, stream));
   const int apply_offsets = (idxs && !no_offset) ? 1 : 0;
   // 1. positions in the score order and in the category-major order, segments, coordinate range
@@ -671,10 +654,10 @@ D2B_API int d2b_nms(const float* boxes, const float* scores, const int64_t* idxs
   D2B_CHECK_LAUNCH();
   // 2. IoU bitmask inside the categories (coordinate offsets of the reference's batched-NMS trick applied in fp32)
   if (rotated)
-    nms_mask_kernel<true, 8><<<nb, 512, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
+    nms_mask_kernel<true, 8><<<dim3(nb, w.wcap), 512, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
                                                      w.wcap, iou_threshold, w.maskT);
   else
-    nms_mask_kernel<false, 4><<<nb, 256, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
+    nms_mask_kernel<false, 4><<<dim3(nb, w.wcap), 256, 0, stream>>>(w.sorted_boxes, w.seg_hi_of_pos, w.clsf_of_pos, w.ctrl, apply_offsets, m,
                                                       w.wcap, iou_threshold, w.maskT);
   D2B_CHECK_LAUNCH();
   // 3. per-segment greedy scans in parallel + compaction in global score order by the last CTA

@@ -1453,10 +1453,16 @@ D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, c
                                          int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
   Pyr P;
   if (!make_pyr(pyr, P) || N < 0 || C < 0) return D2B_EINVAL;
-  for (int l = 0; l < P.num_levels; ++l) {
-    if (!P.grad[l]) return D2B_EINVAL;
-    size_t bytes = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
-    if (bytes) D2B_CUDA(cudaMemsetAsync(P.grad[l], 0, bytes, (cudaStream_t)stream));
+  {
+    void* zp[D2B_MAX_LEVELS];
+    size_t zb[D2B_MAX_LEVELS];
+    for (int l = 0; l < P.num_levels; ++l) {
+      if (!P.grad[l]) return D2B_EINVAL;
+      zp[l] = P.grad[l];
+      zb[l] = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
+    }
+    int rc = d2b_zero_buffers(zp, zb, P.num_levels, (cudaStream_t)stream);  // all levels zero-filled by one launch
+    if (rc) return rc;
   }
   if (K == 0 || C == 0 || N == 0) return D2B_OK;
   if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
@@ -1484,10 +1490,16 @@ D2B_API int d2b_roi_pooler_backward(const d2b_pyramid* pyr, int N, int C, const 
                                     int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
   Pyr P;
   if (!make_pyr(pyr, P) || N < 0 || C < 0) return D2B_EINVAL;
-  for (int l = 0; l < P.num_levels; ++l) {
-    if (!P.grad[l]) return D2B_EINVAL;
-    size_t bytes = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
-    if (bytes) D2B_CUDA(cudaMemsetAsync(P.grad[l], 0, bytes, (cudaStream_t)stream));
+  {
+    void* zp[D2B_MAX_LEVELS];
+    size_t zb[D2B_MAX_LEVELS];
+    for (int l = 0; l < P.num_levels; ++l) {
+      if (!P.grad[l]) return D2B_EINVAL;
+      zp[l] = P.grad[l];
+      zb[l] = sizeof(float) * (size_t)N * C * P.H[l] * P.W[l];
+    }
+    int rc = d2b_zero_buffers(zp, zb, P.num_levels, (cudaStream_t)stream);  // all levels zero-filled by one launch
+    if (rc) return rc;
   }
   if (K == 0 || C == 0 || N == 0) return D2B_OK;
   if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
