@@ -24,9 +24,10 @@
 //   * precision 1 ("bf16x3"): operands are split x = hi + lo (two bf16) and hi*hi + hi*lo + lo*hi is accumulated in fp32 --
 //     fp32-class accuracy (<= 1e-4 rel) at a third of the bf16 tensor peak.  precision 2: plain bf16 operands.
 //
-// Warp roles (320 threads, one CTA per SM): warps 0-7 gather / scatter / epilogue, warp 8 TMA producer (one lane),
-// warp 9 MMA issuer (one lane) and TMEM owner.
+// Warp roles (576 threads, one CTA per SM): warps 0-15 gather / scatter / epilogue, warp 16 TMA producer (one lane),
+// warp 17 MMA issuer (one lane) and TMEM owner.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -35,12 +36,12 @@ using namespace d2b_tc;
 
 namespace {
 
-// 8 worker warps with 200 registers each rather than 16 with 100: the gather is bound by bytes in flight (latency x
-// bandwidth), and a lane that keeps 32 LDG.128 in flight (8 pixels x 4 corners) doubles the bytes in flight per SM.
-constexpr int kWorkerWarps = 8;
-constexpr int kWorkers = kWorkerWarps * 32;  // 256
+// 16 worker warps (112 registers each) measured faster than 8 warps with twice the loads in flight per lane (K1 res3 79 vs
+// 94 us, K2 132 vs 141 us): the gather / scatter loops are bound by instruction issue and need the warps, not deeper queues.
+constexpr int kWorkerWarps = 16;
+constexpr int kWorkers = kWorkerWarps * 32;  // 512
 constexpr int kThreads = kWorkers + 64;      // + producer warp + MMA warp
-constexpr int kRowsPerHalf = 128 / (2 * kWorkerWarps);  // pixel rows of a 128-row tile owned by one half-warp: 8
+constexpr int kRowsPerHalf = 128 / (2 * kWorkerWarps);  // pixel rows of a 128-row tile owned by one half-warp: 4
 constexpr int kTile = 16384;                 // [128 rows][128 B]
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kGcolPitch = 132;              // floats per pixel row of the drained gcol tile (128 + 4: conflict-free float4)
@@ -124,6 +125,24 @@ int largest_tile(int n) {  // largest of {256,...,16} dividing n
   return 0;
 }
 
+// Split `work` units of a CTA `base` times replicated over up to `max_split` parts: the number of parts that minimises
+// (waves over the 148 SMs) x (units per CTA + the CTA's fixed prologue / epilogue cost in units).  One CTA per SM is
+// resident, so 153 CTAs cost two full waves.
+int best_split(long long base, int work, int max_split, int overhead) {
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= max_split; ++s) {
+    const int per = d2b_cdiv(work, s);
+    const int parts = d2b_cdiv(work, per);
+    const long long cost = (long long)d2b_cdiv(base * parts, kNumSMs) * (per + overhead);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = parts;
+    }
+  }
+  return best;
+}
+
 int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -140,8 +159,7 @@ bool plan_k1(const TC& d, K1P& k) {
   }
   if (k.BN < 16) return false;
   const int base = d.N * d.tiles_img * (d.SG / k.gspan) * k.noct;
-  k.ksplit = 1;
-  if (base < 100) k.ksplit = std::min(d.KK, d2b_cdiv(kNumSMs, base));
+  k.ksplit = best_split(base, d.KK, d.KK, 1);
   k.nkp = d2b_cdiv(d.KK, k.ksplit);
   k.ksplit = d2b_cdiv(d.KK, k.nkp);
   k.red = k.ksplit > 1;
@@ -156,8 +174,7 @@ bool plan_k1(const TC& d, K1P& k) {
 bool plan_k2(const TC& d, K2P& k) {
   if (d.ops % 64) return false;
   const int base = d.N * d.tiles_img * d.SG;
-  k.msplit = 1;
-  if (base < 100) k.msplit = std::min(d.MC, d2b_cdiv(kNumSMs, base));
+  k.msplit = best_split(base, d.MC, d.MC, 1);
   k.mper = d2b_cdiv(d.MC, k.msplit);
   k.msplit = d2b_cdiv(d.MC, k.mper);
   const int nkp = std::min(d.KK, (2 * k.mper + d.cbs - 1) / d.cbs + 1);
@@ -172,7 +189,7 @@ bool plan_k3(const TC& d, K3P& k) {
   k.noct = d.ops / k.BN;
   const int units = d.MC * d.SG * k.noct;
   const int total = d.N * d.stages_img;
-  k.nsplit = std::max(1, std::min(total, d2b_cdiv(kNumSMs, units)));
+  k.nsplit = best_split(units, total, std::min(total, 4 * kNumSMs), 3);
   k.sper = d2b_cdiv(total, k.nsplit);
   k.nsplit = d2b_cdiv(total, k.sper);
   k.stage_bytes = 2 * kTile + 2 * k.BN * 128;
@@ -332,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
       uint8_t* a_hi = smem + s * k.stage_bytes;
       uint8_t* a_lo = a_hi + kTile;
       mbar_wait(&empty_bar[s], par ^ 1u);
-      {  // the half-warp's 8 pixel rows in ONE batch: 32 loads in flight per lane before the first use
+      {  // the half-warp's pixel rows in ONE batch: all their corner loads are in flight before the first use
         int4 tap[kRowsPerHalf];
         Taps4 c[kRowsPerHalf];
 #pragma unroll
@@ -549,13 +566,14 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
       const int nu = (2 * m + 1 < d.U) ? 2 : 1;
       mbar_wait(&acc_full[buf], (uint32_t)((ml >> 1) & 1));
       tc_fence_after();
-      // ---- drain: this warp's 32 TMEM lanes (pixels) x 64 of the 128 columns -> gcol[px][col]
-      if (cq * 64 < nu * 64) {
-        float* dst = gcol + (quad * 32 + lane) * kGcolPitch + cq * 64;
+      // ---- drain: this warp's 32 TMEM lanes (pixels) x its share of the 128 columns -> gcol[px][col]
+      constexpr int kDrainCols = 128 / (kWorkerWarps / 4);
+      if (cq * kDrainCols < nu * 64) {
+        float* dst = gcol + (quad * 32 + lane) * kGcolPitch + cq * kDrainCols;
 #pragma unroll
-        for (int h4 = 0; h4 < 4; ++h4) {
+        for (int h4 = 0; h4 < kDrainCols / 16; ++h4) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cq * 64 + h4 * 16), r);
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cq * kDrainCols + h4 * 16), r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -582,17 +600,19 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
         const int4* __restrict__ tp = taps + ((dg - dg0) * nkp + (kp - kp0)) * 128;
         const float* __restrict__ xc = ximg + cbase + q * 4;
 #pragma unroll
-        for (int it = 0; it < R / 4; ++it) {  // 4 pixel rows per batch: 16 loads in flight per lane, then 16 reductions
-          int4 tap[4];
-          Taps4 c[4];
+        constexpr int kB2 = 2;  // pixel rows per batch: 8 loads in flight per lane, then up to 8 reductions
 #pragma unroll
-          for (int e = 0; e < 4; ++e) tap[e] = tp[warp * 2 * R + (it * 4 + e) * 2 + half];
+        for (int it = 0; it < R / kB2; ++it) {
+          int4 tap[kB2];
+          Taps4 c[kB2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) load_corners(xc, d.Cin, d.W, tap[e].x, c[e]);
+          for (int e = 0; e < kB2; ++e) tap[e] = tp[warp * 2 * R + (it * kB2 + e) * 2 + half];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < kB2; ++e) load_corners(xc, d.Cin, d.W, tap[e].x, c[e]);
+#pragma unroll
+          for (int e = 0; e < kB2; ++e) {
             if ((tap[e].x & 15) == 0) continue;  // sample outside the image: no gradient anywhere
-            const int j = it * 4 + e;
+            const int j = it * kB2 + e;
             const int row = warp * 2 * R + j * 2 + half;
             const float4 g4 = *reinterpret_cast<const float4*>(gcol + row * kGcolPitch + ul * 64 + q * 4);
             const float lh = __int_as_float(tap[e].y), lw = __int_as_float(tap[e].z), mk = __int_as_float(tap[e].w);
@@ -697,8 +717,9 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
                                                                         const float* __restrict__ offset,
                                                                         const float* __restrict__ mask,
                                                                         const uint8_t* __restrict__ gt, const TC d,
-                                                                        const K3P k, const int split,
+                                                                        const K3P k, const int split_dbg,
                                                                         float* __restrict__ gw) {
+  const int split = split_dbg & 1, dbg = split_dbg >> 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   int4* tap_s = reinterpret_cast<int4*>(smem + k.S * k.stage_bytes);  // [16 warps][8]
@@ -739,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
     // lanes 0..15 build the taps of this warp's 8 pixels x 2 units; the loads of the NEXT stage's offsets / mask are issued
     // before this stage's gather and consumed after it, so that their latency is hidden behind the gather
     constexpr int PX = 64 / kWorkerWarps;  // pixels of a stage per warp: 8
-    const int tl_half = (lane >> 3) & 1, tl_j = lane & 7;
+    const int tl_half = (lane / PX) & 1, tl_j = lane % PX;
     const int tl_u = 2 * mb + tl_half;
     const bool tl_ok = lane < 2 * PX && tl_u < d.U;
     const int tl_kp = tl_ok ? tl_u / d.cbs : 0;
@@ -765,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
       TapRaw raw = {0.f, 0.f, 1.f};
       if (have_next) {
         stage_of(i + 1, bn, pbn);
-        if (tl_ok) raw = tap_loads(d, offset, mask, bn, tl_dg, tl_kp, pbn + warp * PX + tl_j);
+        if (tl_ok && !(dbg & 4)) raw = tap_loads(d, offset, mask, bn, tl_dg, tl_kp, pbn + warp * PX + tl_j);
       }
       const float* __restrict__ xc = xh + (size_t)b * d.H * d.W * d.Cin + cbase + q * 4;
       uint8_t* a_hi = smem + s * k.stage_bytes + half * 8192;
@@ -778,14 +799,14 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
 #pragma unroll
         for (int j = 0; j < PX; ++j) tap[j] = cur[j];
 #pragma unroll
-        for (int j = 0; j < PX; ++j) load_corners(xc, d.Cin, d.W, tap[j].x, c[j]);
+        for (int j = 0; j < PX; ++j) load_corners(xc, d.Cin, d.W, (dbg & 1) ? 0 : tap[j].x, c[j]);
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
           const uint32_t r = (uint32_t)(warp * PX + j);
           gather_store(c[j], tap[j], a_hi, a_lo, swz128(r, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
         }
       }
-      if (have_next && lane < 2 * PX)
+      if (have_next && lane < 2 * PX && !(dbg & 4))
         my_taps[((i + 1) & 1) * (2 * PX) + lane] =
             tl_ok ? tap_finish(d, raw, mask != nullptr, tl_kp, pbn + warp * PX + tl_j) : make_int4(0, 0, 0, 0);
       fence_proxy_async();
@@ -840,6 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
         for (int kk = 0; kk < 4; ++kk) {
           // A: 16 pixels (K) = two 8-row atoms 1024 B apart; the two 64-channel M blocks are 8192 B apart
           const uint32_t ao = (uint32_t)kk * 2048u, bo = (uint32_t)kk * 32u;
+          if (dbg & 2) continue;
           umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
           if (split) {
             umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_lo + bo, 0, 1024), idesc, 1u);
@@ -862,14 +884,10 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
 
 // ================================================================================================ operand pre-tiling
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-  float h[8], r[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-    r[i] = v[i] - h[i];
-  }
-  hi = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-  lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+  split2(v[0], v[1], hi.x, lo.x);
+  split2(v[2], v[3], hi.y, lo.y);
+  split2(v[4], v[5], hi.z, lo.z);
+  split2(v[6], v[7], hi.w, lo.w);
 }
 
 // weight element of (global output channel, global input channel, kernel point); 0 across original groups
@@ -1232,11 +1250,13 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     }
     const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;
     const int cols = pow2_cols(k3.BN);
+    const char* dbg_env = getenv("D2B_DCN_DEBUG");  // experiment switches (tools/dev_dcn.py); 0 in production
+    const int dbg3 = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid(d.MC, k3.nsplit, d.SG * k3.noct);
 #define D2B_LAUNCH_K3(COLS)                                                                                              \
   {                                                                                                                      \
     D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_tc_kernel<COLS>);                                                                  \
-    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, d, k3, split, grad_weight); \
+    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, d, k3, split | (dbg3 << 4), grad_weight); \
   }
     if (cols <= 32) D2B_LAUNCH_K3(32)
     else if (cols == 64) D2B_LAUNCH_K3(64)

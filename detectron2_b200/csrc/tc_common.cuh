@@ -29,7 +29,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
@@ -135,15 +135,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {  // a -> low h
   return *reinterpret_cast<uint32_t*>(&v);
 }
 // x = hi + lo with hi, lo bf16 (lo = rn(x - hi)): three bf16 MMAs hi*hi + hi*lo + lo*hi keep ~16 mantissa bits per product
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(a, b);                                   // one F2FP for both values
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16(a - ha, b - hb);
+}
 __device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
-  float h[4], r[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-    r[i] = v[i] - h[i];
-  }
-  hi = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-  lo = make_uint2(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]));
+  split2(v[0], v[1], hi.x, lo.x);
+  split2(v[2], v[3], hi.y, lo.y);
 }
 // Packed fp32 FMA (sm_100 FFMA2): two lanes of fp32 FMA in ONE issue slot -- the gather loops are issue-bound
 struct F2 {
