@@ -958,9 +958,12 @@ __device__ __forceinline__ float gout_elem(const float* __restrict__ gout, const
   return g;
 }
 
+// Also writes the K3 B tiles (oc-row layout, see dcn_gout_oc_tiles_kernel) of the same elements when dst_oc != nullptr, so
+// that a backward that needs both gradients reads grad_out once.
 __global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __restrict__ gout,
                                                                 const float* __restrict__ ysaved, const Epi ep, const TC d,
-                                                                uint8_t* __restrict__ dst) {
+                                                                uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_oc,
+                                                                int BN, int noct) {
   // grid (tiles, 4): a CTA converts 32 of the tile's 128 pixel rows -- 4x the CTAs of a tile-per-CTA layout, which matters for
   // the small maps (res5: 144 tiles on 148 SMs)
   __shared__ float t[64][33];
@@ -990,6 +993,24 @@ __global__ void __launch_bounds__(256) dcn_gout_px_tiles_kernel(const float* __r
     split8(v, hi, lo);
     *reinterpret_cast<uint4*>(base + swz128((uint32_t)(r0 + r), (uint32_t)c16)) = hi;
     *reinterpret_cast<uint4*>(base + kTile + swz128((uint32_t)(r0 + r), (uint32_t)c16)) = lo;
+  }
+  if (dst_oc) {  // rows = output channels, 64-pixel stages: this CTA's 32 pixels are chunks [c0, c0 + 4) of one stage
+    const int o = tid >> 2, ch = tid & 3;  // 64 channel rows x 4 chunks of 8 pixels
+    const int ocs = ks * 64 + o;           // channel inside the super-group
+    const int oct = ocs / BN, row = ocs - oct * BN;
+    const int pglob = pt * 128 + r0;       // first pixel of this CTA inside the image
+    const int ps = pglob >> 6, c16 = ((pglob & 63) >> 3) + ch;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[o][ch * 8 + i];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    if (ps < d.stages_img) {
+      const size_t tile_oc = (((size_t)b * d.stages_img + ps) * d.SG + sg) * noct + oct;
+      uint8_t* bo = dst_oc + tile_oc * (size_t)(2 * BN * 128);
+      *reinterpret_cast<uint4*>(bo + swz128((uint32_t)row, (uint32_t)c16)) = hi;
+      *reinterpret_cast<uint4*>(bo + BN * 128 + swz128((uint32_t)row, (uint32_t)c16)) = lo;
+    }
   }
 }
 
@@ -1215,14 +1236,20 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     int rc = d2b_zero_buffers(zp, zb, 4, stream);
     if (rc) return rc;
   }
+  uint8_t* gt_px = nullptr;
+  uint8_t* wt = nullptr;
   if (need_data) {
     if (!x_nhwc) ws += xbytes;
-    uint8_t* gt = ws;
+    gt_px = ws;
     ws += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);
-    uint8_t* wt = ws;
+    wt = ws;
     ws += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);
-    dcn_gout_px_tiles_kernel<<<dim3((unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 4), 256, 0, stream>>>(grad_out, y_saved,
-                                                                                                       ep, d, gt);
+  }
+  uint8_t* gt_oc = need_weight ? ws : nullptr;
+  if (need_data) {
+    // grad_out is read once: pixel-row tiles for K2 and (when the weight gradient is wanted too) channel-row tiles for K3
+    dcn_gout_px_tiles_kernel<<<dim3((unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 4), 256, 0, stream>>>(
+        grad_out, y_saved, ep, d, gt_px, gt_oc, k3.BN, k3.noct);
     D2B_CHECK_LAUNCH();
     {
       const long long total = (long long)d.SG * d.MC * d.nks * 128 * 8;
@@ -1232,7 +1259,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     const int smem_bytes = 2 * 4 * kTile + 128 * kGcolPitch * 4 + k2.tap_bytes + 1024 + 256;
     D2B_ALLOW_BIG_SMEM(dcn_bwd_data_tc_kernel);
     dim3 grid(d.N * d.tiles_img, d.SG, k2.msplit);
-    dcn_bwd_data_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, wt, d, k2, split, gxh, grad_offset,
+    dcn_bwd_data_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_px, wt, d, k2, split, gxh, grad_offset,
                                                                   mask ? grad_mask : nullptr);
     D2B_CHECK_LAUNCH();
     if (grad_x && !x_nhwc) {
@@ -1242,21 +1269,20 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     }
   }
   if (need_weight) {
-    uint8_t* gt = ws;
-    {
+    if (!need_data) {
       const long long total = (long long)d.N * d.stages_img * d.SG * k3.noct * k3.BN * 8;
-      dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, y_saved, ep, d, k3.BN, k3.noct, gt);
+      dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, y_saved, ep, d, k3.BN, k3.noct, gt_oc);
       D2B_CHECK_LAUNCH();
     }
     const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;
     const int cols = pow2_cols(k3.BN);
-    const char* dbg_env = getenv("D2B_DCN_DEBUG");  // experiment switches (tools/dev_dcn.py); 0 in production
+    const char* dbg_env = getenv("D2B_DCN_DEBUG");  // experiment switches (tools/dev_k3.py); 0 in production
     const int dbg3 = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid(d.MC, k3.nsplit, d.SG * k3.noct);
 #define D2B_LAUNCH_K3(COLS)                                                                                              \
   {                                                                                                                      \
     D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_tc_kernel<COLS>);                                                                  \
-    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt, d, k3, split | (dbg3 << 4), grad_weight); \
+    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_oc, d, k3, split | (dbg3 << 4), grad_weight); \
   }
     if (cols <= 32) D2B_LAUNCH_K3(32)
     else if (cols == 64) D2B_LAUNCH_K3(64)

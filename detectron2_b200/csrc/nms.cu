@@ -206,8 +206,9 @@ __device__ __forceinline__ float dec_f(unsigned u) {
 //   pos   = #{j : c_j < c_i} + #{j : c_j == c_i and j before i}        position in the category-major order
 // which is what two stable radix sorts would produce -- but in one launch, with the segment bounds of every position and
 // the segment list as by-products.  O(M^2 / 32) warp steps: 3 us at M = 8819, ~3 ms at M = 100 000.
-constexpr int kRankTile = 2048;
+constexpr int kRankTile = 1792;
 constexpr int kRankWarps = 8;
+constexpr int kRankHist = 4096;  // category ids in [-1, kRankHist) take the histogram path
 
 template <bool ROT>
 __global__ void __launch_bounds__(kRankWarps * 32) nms_rank_kernel(const float* __restrict__ boxes,
@@ -218,37 +219,110 @@ __global__ void __launch_bounds__(kRankWarps * 32) nms_rank_kernel(const float* 
                                                                    int* __restrict__ seg_hi_of_pos, float* __restrict__ clsf_of_pos,
                                                                    float* __restrict__ sorted_boxes, int* __restrict__ seg_start,
                                                                    int* __restrict__ seg_end, unsigned char* __restrict__ keepflag) {
-  __shared__ float s_score[kRankTile];
+  // tile of the streamed boxes: generic path {score, int64 category}; histogram path {64-bit order key, int32 category}
+  __shared__ unsigned long long s_key[kRankTile];
   __shared__ long long s_cls[kRankTile];
+  __shared__ int s_hist[kRankHist + 2];  // [c + 1] = number of boxes of category c, then exclusive prefix = #{smaller category}
+  __shared__ int s_wtot[kRankWarps];
   __shared__ float s_mx[kRankWarps], s_mn[kRankWarps];
   constexpr int D = ROT ? 5 : 4;
+  constexpr int kT = kRankWarps * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = (blockIdx.x * kRankWarps + warp) * 2, i1 = i0 + 1;
   const bool ok0 = i0 < M, ok1 = i1 < M;
   const float sa = ok0 ? scores[i0] : 0.f, sb = ok1 ? scores[i1] : 0.f;
   const long long ca = (ok0 && idxs) ? idxs[i0] : 0, cb = (ok1 && idxs) ? idxs[i1] : 0;
   int ga = 0, gb = 0, sma = 0, smb = 0, bea = 0, beb = 0, na = 0, nb = 0;  // grank, smaller-class, before-in-class, class size
-  for (int t0 = 0; t0 < M; t0 += kRankTile) {
-    const int tn = min(kRankTile, M - t0);
-    __syncthreads();
-    for (int j = tid; j < tn; j += kRankWarps * 32) {
-      s_score[j] = scores[t0 + j];
-      s_cls[j] = idxs ? idxs[t0 + j] : 0;
+  // ---- category histogram (every CTA builds its own: M small loads from L2): when all ids fit, the O(M^2) loop below only
+  //      has to count "before me in the score order" and "... and of my category" -- two compares per pair.
+  for (int c = tid; c < kRankHist + 2; c += kT) s_hist[c] = 0;
+  __syncthreads();
+  int small = 1;
+  if (idxs) {
+    for (int j = tid; j < M; j += kT) {
+      const long long c = idxs[j];
+      if (c < -1 || c >= kRankHist) small = 0;
+      else atomicAdd(&s_hist[(int)c + 1], 1);
     }
+  } else if (tid == 0) {
+    s_hist[1] = M;
+  }
+  small = __syncthreads_and(small);
+  if (small) {
+    // exclusive prefix over the bins: strip per thread + scan of the strip totals
+    constexpr int kStrip = (kRankHist + 2 + kT - 1) / kT;
+    const int c0 = tid * kStrip;
+    int loc[kStrip], sum = 0;
+#pragma unroll
+    for (int e = 0; e < kStrip; ++e) {
+      loc[e] = (c0 + e < kRankHist + 2) ? s_hist[c0 + e] : 0;
+      sum += loc[e];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
     __syncthreads();
-    for (int jl = lane; jl < tn; jl += 32) {
-      const float s = s_score[jl];
-      const long long c = s_cls[jl];
-      const int j = t0 + jl;
-      const bool fa = s > sa || (s == sa && j < i0), fb = s > sb || (s == sb && j < i1);
-      ga += fa;
-      gb += fb;
-      sma += c < ca;
-      smb += c < cb;
-      na += c == ca;
-      nb += c == cb;
-      bea += (c == ca) && fa;
-      beb += (c == cb) && fb;
+    int base = inc - sum;
+    for (int w = 0; w < warp; ++w) base += s_wtot[w];
+    // s_hist[c + 1] <- #{boxes of a smaller category}; the count itself is recovered as the difference to the next bin
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kStrip; ++e)
+      if (c0 + e < kRankHist + 2) {
+        s_hist[c0 + e] = base;
+        base += loc[e];
+      }
+    __syncthreads();
+    const unsigned long long ka = ((unsigned long long)(~enc_f(sa)) << 32) | (unsigned)i0;  // ascending key == score order
+    const unsigned long long kb = ((unsigned long long)(~enc_f(sb)) << 32) | (unsigned)i1;
+    const int ca32 = (int)ca, cb32 = (int)cb;
+    int* s_c32 = reinterpret_cast<int*>(s_cls);
+    for (int t0 = 0; t0 < M; t0 += kRankTile) {
+      const int tn = min(kRankTile, M - t0);
+      __syncthreads();
+      for (int j = tid; j < tn; j += kT) {
+        s_key[j] = ((unsigned long long)(~enc_f(scores[t0 + j])) << 32) | (unsigned)(t0 + j);
+        s_c32[j] = idxs ? (int)idxs[t0 + j] : 0;
+      }
+      __syncthreads();
+      for (int jl = lane; jl < tn; jl += 32) {
+        const unsigned long long kj = s_key[jl];
+        const int c = s_c32[jl];
+        const bool fa = kj < ka, fb = kj < kb;
+        ga += fa;
+        gb += fb;
+        bea += fa && (c == ca32);
+        beb += fb && (c == cb32);
+      }
+    }
+  } else {
+    float* s_score = reinterpret_cast<float*>(s_key);
+    for (int t0 = 0; t0 < M; t0 += kRankTile) {
+      const int tn = min(kRankTile, M - t0);
+      __syncthreads();
+      for (int j = tid; j < tn; j += kT) {
+        s_score[j] = scores[t0 + j];
+        s_cls[j] = idxs ? idxs[t0 + j] : 0;
+      }
+      __syncthreads();
+      for (int jl = lane; jl < tn; jl += 32) {
+        const float s = s_score[jl];
+        const long long c = s_cls[jl];
+        const int j = t0 + jl;
+        const bool fa = s > sa || (s == sa && j < i0), fb = s > sb || (s == sb && j < i1);
+        ga += fa;
+        gb += fb;
+        sma += c < ca;
+        smb += c < cb;
+        na += c == ca;
+        nb += c == cb;
+        bea += (c == ca) && fa;
+        beb += (c == cb) && fb;
+      }
     }
   }
 #pragma unroll
@@ -261,6 +335,10 @@ __global__ void __launch_bounds__(kRankWarps * 32) nms_rank_kernel(const float* 
     nb += __shfl_xor_sync(0xffffffffu, nb, o);
     bea += __shfl_xor_sync(0xffffffffu, bea, o);
     beb += __shfl_xor_sync(0xffffffffu, beb, o);
+  }
+  if (small) {  // category start / size from the prefix table
+    if (ok0) { sma = s_hist[(int)ca + 1]; na = s_hist[(int)ca + 2] - sma; }
+    if (ok1) { smb = s_hist[(int)cb + 1]; nb = s_hist[(int)cb + 2] - smb; }
   }
   float mx = -INFINITY, mn = INFINITY;
 #pragma unroll

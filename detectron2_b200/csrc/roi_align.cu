@@ -928,7 +928,7 @@ static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
 // (ROIAlignRotated_cuda.cu:311-318 / torchvision roi_align_backward) and one scalar red per pixel and channel in the NCHW
 // kernel above.  Measured ceiling of red.v4 on 256-byte runs: 5.9 TB/s (profiles/r2_microbench.txt).
 constexpr int kBwdBand = 64;     // footprint rows per pass
-constexpr int kBwdMaxFw = 320;   // footprint columns with a table; wider RoIs take the per-sample path below
+constexpr int kBwdMaxFw = 96;    // footprint columns with a table (FPN-assigned RoIs span < 60); wider RoIs take the per-sample path
 constexpr int kBwdThreads = 256;
 
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
@@ -969,8 +969,10 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   __shared__ float WyT[kBwdBand * kMaxP];      // [row of the band][ph]
   __shared__ float WxT[kBwdMaxFw * kMaxP];     // [column of the footprint][pw]
   __shared__ unsigned char ylo[kBwdBand], yhi[kBwdBand], xlo[kBwdMaxFw], xhi[kBwdMaxFw];  // non-zero bin range per row / column
+  // the common case -- at most two bins touch a pixel row / column (bins at least one pixel wide): {bin a, bin b, w a, w b}
+  __shared__ float4 colE[kBwdMaxFw], rowE[kBwdBand];
   __shared__ RoiGeom sg;
-  __shared__ int s_xmin, s_xmax, s_ymin, s_ymax;
+  __shared__ int s_xmin, s_xmax, s_ymin, s_ymax, s_wide;
 
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * kNhwcCh;
@@ -985,6 +987,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
     sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
     s_xmin = s_ymin = 1 << 30;
     s_xmax = s_ymax = -1;
+    s_wide = 0;
   }
   __syncthreads();
   const RoiGeom g = sg;
@@ -1044,12 +1047,24 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   }
   __syncthreads();
   for (int x = tid; x < fw; x += kBwdThreads) {
-    int lo = 255, hi = 0;
-    for (int pw = 0; pw < PW; ++pw)
-      if (WxT[x * kMaxP + pw] != 0.f) { lo = min(lo, pw); hi = max(hi, pw + 1); }
+    int lo = 255, hi = 0, cnt = 0, ia = 0, ib = 0;
+    float wa = 0.f, wb = 0.f;
+    for (int pw = 0; pw < PW; ++pw) {
+      const float w = WxT[x * kMaxP + pw];
+      if (w != 0.f) {
+        lo = min(lo, pw);
+        hi = max(hi, pw + 1);
+        if (cnt == 0) { ia = pw; wa = w; }
+        else if (cnt == 1) { ib = pw; wb = w; }
+        ++cnt;
+      }
+    }
     xlo[x] = (unsigned char)lo;
     xhi[x] = (unsigned char)hi;
+    colE[x] = make_float4(__int_as_float(ia), __int_as_float(ib), wa, wb);
+    if (cnt > 2) atomicOr(&s_wide, 1);
   }
+  float* __restrict__ Ts = gs + (size_t)bins * kNhwcCh + (size_t)warp * PW * kNhwcCh;  // this warp's row-collapsed gradients
   // ---- bands of footprint rows
   for (int yb = ymin; yb <= ymax; yb += kBwdBand) {
     const int nrow = min(kBwdBand, ymax - yb + 1);
@@ -1065,13 +1080,64 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
     }
     __syncthreads();
     for (int y = tid; y < nrow; y += kBwdThreads) {
-      int lo = 255, hi = 0;
-      for (int ph = 0; ph < PH; ++ph)
-        if (WyT[y * kMaxP + ph] != 0.f) { lo = min(lo, ph); hi = max(hi, ph + 1); }
+      int lo = 255, hi = 0, cnt = 0, ia = 0, ib = 0;
+      float wa = 0.f, wb = 0.f;
+      for (int ph = 0; ph < PH; ++ph) {
+        const float w = WyT[y * kMaxP + ph];
+        if (w != 0.f) {
+          lo = min(lo, ph);
+          hi = max(hi, ph + 1);
+          if (cnt == 0) { ia = ph; wa = w; }
+          else if (cnt == 1) { ib = ph; wb = w; }
+          ++cnt;
+        }
+      }
       ylo[y] = (unsigned char)lo;
       yhi[y] = (unsigned char)hi;
+      rowE[y] = make_float4(__int_as_float(ia), __int_as_float(ib), wa, wb);
+      if (cnt > 2) atomicOr(&s_wide, 1);
     }
     __syncthreads();
+    if (!s_wide) {
+      // separable two-step form: a warp owns a footprint row; T[pw] = wy_a g[ph_a][pw] + wy_b g[ph_b][pw] once per row
+      // (warp-private shared memory), then every pixel of the row is wx_a T[pw_a] + wx_b T[pw_b]: ~12 instructions / pixel
+      for (int yr = warp; yr < nrow; yr += kWarps) {
+        const float4 re = rowE[yr];
+        if (re.z == 0.f && re.w == 0.f) continue;  // warp-uniform
+        const int pa = __float_as_int(re.x), pb = __float_as_int(re.y);
+        const F2 wya = f2_pack(re.z, re.z), wyb = f2_pack(re.w, re.w);
+        __syncwarp();
+        for (int pw = 0; pw < PW; ++pw) {
+          const int ba = pa * PW + pw, bb = pb * PW + pw;
+          const float4 ga = *reinterpret_cast<const float4*>(gs + ba * kNhwcCh + (((lane ^ ba) & 31) << 2));
+          const float4 gb = *reinterpret_cast<const float4*>(gs + bb * kNhwcCh + (((lane ^ bb) & 31) << 2));
+          const F2 z = f2_pack(0.f, 0.f);
+          const F2 t01 = f2_fma(wyb, f2_pack(gb.x, gb.y), f2_fma(wya, f2_pack(ga.x, ga.y), z));
+          const F2 t23 = f2_fma(wyb, f2_pack(gb.z, gb.w), f2_fma(wya, f2_pack(ga.z, ga.w), z));
+          float4 tv;
+          f2_unpack(t01, tv.x, tv.y);
+          f2_unpack(t23, tv.z, tv.w);
+          *reinterpret_cast<float4*>(Ts + pw * kNhwcCh + lane * 4) = tv;
+        }
+        __syncwarp();
+        float* __restrict__ grow = gimg + (size_t)(yb + yr) * W * C + (size_t)xmin * C;
+        for (int xr = 0; xr < fw; ++xr) {
+          const float4 ce = colE[xr];
+          if (ce.z == 0.f && ce.w == 0.f) continue;
+          const float4 ta = *reinterpret_cast<const float4*>(Ts + __float_as_int(ce.x) * kNhwcCh + lane * 4);
+          const float4 tb = *reinterpret_cast<const float4*>(Ts + __float_as_int(ce.y) * kNhwcCh + lane * 4);
+          const F2 z = f2_pack(0.f, 0.f), wxa = f2_pack(ce.z, ce.z), wxb = f2_pack(ce.w, ce.w);
+          const F2 a01 = f2_fma(wxb, f2_pack(tb.x, tb.y), f2_fma(wxa, f2_pack(ta.x, ta.y), z));
+          const F2 a23 = f2_fma(wxb, f2_pack(tb.z, tb.w), f2_fma(wxa, f2_pack(ta.z, ta.w), z));
+          float4 acc;
+          f2_unpack(a01, acc.x, acc.y);
+          f2_unpack(a23, acc.z, acc.w);
+          if (lane_live) red_add_v4(grow + (size_t)xr * C, acc);
+        }
+      }
+      continue;
+    }
+    // general form (bins narrower than a pixel: more than two bins per row / column)
     for (int yr = 0; yr < nrow; ++yr) {
       const int pa = ylo[yr], pb = yhi[yr];
       if (pa >= pb) continue;
@@ -1104,8 +1170,9 @@ static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   for (int l = 0; l < P.num_levels; ++l)
     if ((reinterpret_cast<uintptr_t>(P.grad[l]) & 15) != 0) return D2B_EINVAL;
   (void)N;
-  const size_t smem = sizeof(float) * kNhwcCh * (size_t)PH * PW;
-  if (smem > 160 * 1024) return D2B_EUNSUPPORTED;
+  // gradient tile [bins][128] + per-warp row-collapsed tile [8 warps][PW][128]
+  const size_t smem = sizeof(float) * kNhwcCh * ((size_t)PH * PW + (size_t)(kBwdThreads / 32) * PW);
+  if (smem > 180 * 1024) return D2B_EUNSUPPORTED;
   D2B_ALLOW_BIG_SMEM(roi_align_bwd_nhwc_kernel);
   dim3 grid(K, d2b_cdiv(C, kNhwcCh));
   roi_align_bwd_nhwc_kernel<<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, gout);
