@@ -206,12 +206,18 @@ class TrainRunner:
                                                224.0, channels_last)
 
     def dconv_fwd(self, d, si, li, prec=-1):
-        return self.ops.deform_conv_op(d["dc_x"][si], d["dc_off"][si], None, d["dc_w"][si][li], None, [1, 1], [1, 1], [1, 1], 1, 1,
-                                       prec)
+        """(y, x_saved, cols): the training forward keeps the channels-last copy of x it ran on and its sampled columns."""
+        return self.ops.deform_conv_train_op(d["dc_x"][si], d["dc_off"][si], None, d["dc_w"][si][li], None, [1, 1], [1, 1],
+                                             [1, 1], 1, 1, prec)
 
-    def dconv_bwd(self, d, si, li, prec=-1):
-        return self.ops.deform_conv_backward_op(d["dc_x"][si], d["dc_off"][si], None, d["dc_w"][si][li], d["dc_go"][si],
-                                                [1, 1], [1, 1], [1, 1], 1, 1, False, True, True, prec)
+    def dconv_bwd(self, d, si, li, saved=None, prec=-1):
+        """All gradients; `saved` = dconv_fwd's result (what autograd keeps between the two calls)."""
+        x, cols = d["dc_x"][si], None
+        if saved is not None:
+            x = saved[1] if saved[1].numel() else x
+            cols = saved[2] if saved[2].numel() else None
+        return self.ops.deform_conv_backward_op(x, d["dc_off"][si], None, d["dc_w"][si][li], d["dc_go"][si],
+                                                [1, 1], [1, 1], [1, 1], 1, 1, False, True, True, prec, cols)
 
     def step(self, d):
         ops = self.ops
@@ -228,7 +234,8 @@ class TrainRunner:
         outs["dc"] = []
         for si, (_, _, _, layers) in enumerate(DCONV_STAGES):
             for li in range(layers):
-                outs["dc"].append((self.dconv_fwd(d, si, li), self.dconv_bwd(d, si, li)))
+                saved = self.dconv_fwd(d, si, li)
+                outs["dc"].append((saved[0], self.dconv_bwd(d, si, li, saved)))
         return outs
 
     KERNELS_PER_STEP = (2 * 8            # NMS: iota, coord_range, class_of_rank, segments, gather, mask, scan, compact (CUB sorts are library code)
@@ -309,8 +316,8 @@ def validate_step(runner, d_host, d_dev, outs):
     k = 0
     for si, (c, h, w, layers) in enumerate(DCONV_STAGES):
         y, (gx, goff, _, gw, _) = outs["dc"][k]
-        y0 = runner.dconv_fwd(d_dev, si, 0, 0)
-        g0 = runner.dconv_bwd(d_dev, si, 0, 0)
+        y0 = runner.dconv_fwd(d_dev, si, 0, 0)[0]
+        g0 = runner.dconv_bwd(d_dev, si, 0, None, 0)
         for name, a, b in (("y", y, y0), ("gx", gx, g0[0]), ("goff", goff, g0[1]), ("gw", gw, g0[3])):
             err = (a - b).abs().max().item()
             assert err <= 1e-4 * b.abs().max().item() + 1e-6, ("dconv", si, name, err)
@@ -613,9 +620,12 @@ def main():
         "mask_pool_bwd": lambda b: runner.pool_bwd(devin[b], "mask", rois_mask[b], True),
         "grads_to_nchw": lambda b: runner.ops._from_nhwc(gcl[b], IMGS_PER_GPU, C, dev),
     }
+    saved = [[[runner.dconv_fwd(d, si, li) for li in range(layers)] for si, (_, _, _, layers) in enumerate(DCONV_STAGES)]
+             for d in devin]
     for si, (c, h, w, layers) in enumerate(DCONV_STAGES):
         stages["dconv_c%d_fwd_x%d" % (c, layers)] = lambda b, si=si, layers=layers: [runner.dconv_fwd(devin[b], si, li) for li in range(layers)]
-        stages["dconv_c%d_bwd_x%d" % (c, layers)] = lambda b, si=si, layers=layers: [runner.dconv_bwd(devin[b], si, li) for li in range(layers)]
+        stages["dconv_c%d_bwd_x%d" % (c, layers)] = lambda b, si=si, layers=layers: [
+            runner.dconv_bwd(devin[b], si, li, saved[b][si][li]) for li in range(layers)]
     stage_ms = {}
     for name, fn in stages.items():
         sg = [graph_of(lambda b=b: fn(b), side) for b in range(NBUF)]

@@ -23,7 +23,7 @@ class DcnParams(C.Structure):
 
 
 MAX_LEVELS = 8
-ABI_VERSION = 2  # include/d2b200.h D2B_ABI_VERSION
+ABI_VERSION = 3  # include/d2b200.h D2B_ABI_VERSION
 DCN_X_NHWC = 1   # D2B_DCN_X_NHWC
 
 
@@ -69,13 +69,15 @@ def _declare(lib):
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),
         "d2b_deform_conv_tc_shape_supported": (i, [C.POINTER(DcnParams), i]),
         "d2b_deform_conv_forward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i]),
-        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, vp, sz, vp]),
+        "d2b_deform_conv_cols_bytes": (sz, [C.POINTER(DcnParams), i]),
+        "d2b_deform_conv_forward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, vp, vp, sz, vp]),
         "d2b_deform_conv_backward_workspace_bytes": (sz, [C.POINTER(DcnParams), i, i, i, i]),
-        "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, f32p, f32p,
+        "d2b_deform_conv_backward": (i, [f32p, f32p, f32p, f32p, f32p, C.POINTER(DcnParams), i, i, vp, f32p, f32p, f32p,
                                          f32p, f32p, vp, sz, vp]),
-        "d2b_deform_conv_fused_forward": (i, [f32p, f32p, f32p, f32p, f32p, i, C.POINTER(DcnParams), i, i, f32p, vp, sz, vp]),
-        "d2b_deform_conv_fused_backward": (i, [f32p, f32p, f32p, f32p, i, f32p, f32p, C.POINTER(DcnParams), i, i, f32p, f32p,
-                                               f32p, vp, sz, vp]),
+        "d2b_deform_conv_fused_forward": (i, [f32p, f32p, f32p, f32p, f32p, i, C.POINTER(DcnParams), i, i, f32p, vp, vp, sz,
+                                              vp]),
+        "d2b_deform_conv_fused_backward": (i, [f32p, f32p, f32p, f32p, i, f32p, f32p, C.POINTER(DcnParams), i, i, vp, f32p,
+                                               f32p, f32p, vp, sz, vp]),
         "d2b_paste_masks": (i, [f32p, f32p, i, i, i, i, f, u8p, vp]),
     }
     for name, (res, args) in sig.items():

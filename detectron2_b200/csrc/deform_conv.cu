@@ -375,15 +375,16 @@ __global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float* __restr
 int d2b_deform_conv_tc_supported(const d2b_dcn_params* p);
 int d2b_deform_conv_tc_bwd_supported(const d2b_dcn_params* p);
 size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc);
+size_t d2b_deform_conv_tc_cols_bytes(const d2b_dcn_params* p, int precision);
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
                                const float* scale, const float* shift, int relu, const d2b_dcn_params* p, int precision,
-                               int tcflags, float* out, void* workspace, size_t workspace_bytes, void* stream);
+                               int tcflags, float* out, void* cols, void* workspace, size_t workspace_bytes, void* stream);
 size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int need_data, int need_weight);
 int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
                                 const float* grad_out, const float* scale, const float* y_saved, int relu,
-                                const d2b_dcn_params* p, int precision, int tcflags, float* grad_x, float* grad_offset,
-                                float* grad_mask, float* grad_weight, void* workspace, size_t workspace_bytes,
-                                void* stream);
+                                const d2b_dcn_params* p, int precision, int tcflags, const void* cols, float* grad_x,
+                                float* grad_offset, float* grad_mask, float* grad_weight, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 // precision: 0 = fp32 FFMA, 1 = bf16x3 on tcgen05, 2 = bf16 on tcgen05, -1 = auto (1 when the tensor-core kernels take
 // the shape, else 0 -- both are fp32-class, so "auto" never lowers accuracy)
@@ -397,9 +398,18 @@ D2B_API size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, 
   return d2b_deform_conv_tc_fwd_workspace(p, (flags & D2B_DCN_X_NHWC) ? 1 : 0);
 }
 
+// Saved columns (training): the tensor-core forward can keep the sampled columns it builds -- bf16 hi [| lo] tiles in the
+// tensor core's operand layout -- and the backward's weight-gradient kernel then streams them back instead of sampling x a
+// second time.  0 when the shape / precision has no tensor-core path (pass cols = NULL then).
+D2B_API size_t d2b_deform_conv_cols_bytes(const d2b_dcn_params* p, int precision) {
+  if (precision == -1) precision = (d2b_deform_conv_tc_supported(p) && d2b_deform_conv_tc_bwd_supported(p)) ? 1 : 0;
+  if (precision == 0 || !d2b_deform_conv_tc_bwd_supported(p)) return 0;
+  return d2b_deform_conv_tc_cols_bytes(p, precision);
+}
+
 D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask, const float* weight,
                                     const float* bias, const d2b_dcn_params* p, int precision, int flags, float* out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* cols, void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
   if (d.N == 0) return D2B_OK;
@@ -408,8 +418,9 @@ D2B_API int d2b_deform_conv_forward(const float* x, const float* offset, const f
   if (precision == -1) precision = d2b_deform_conv_tc_supported(p) ? 1 : 0;
   if (precision != 0)  // no silent precision / path change: an unsupported shape is reported, not rerouted
     return d2b_deform_conv_forward_tc(x, offset, mask, weight, nullptr, bias, 0, p, precision,
-                                      (flags & D2B_DCN_X_NHWC) ? 1 : 0, out, workspace, workspace_bytes, stream);
+                                      (flags & D2B_DCN_X_NHWC) ? 1 : 0, out, cols, workspace, workspace_bytes, stream);
   if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;  // the FFMA parity path reads NCHW planes
+  if (cols) return D2B_EINVAL;                          // ... and never materialises columns
   dim3 grid(d2b_cdiv(d.HoWo, BN), d2b_cdiv(d.opg, BM), d.N * d.G);
   dcn_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, offset, mask, weight, bias, d, out);
   D2B_CHECK_LAUNCH();
@@ -425,14 +436,16 @@ D2B_API size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p,
 
 D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const float* mask, const float* weight,
                                      const float* grad_out, const d2b_dcn_params* p, int precision, int flags,
-                                     float* grad_x, float* grad_offset, float* grad_mask, float* grad_weight,
-                                     float* grad_bias, void* workspace, size_t workspace_bytes, void* stream_) {
+                                     const void* cols, float* grad_x, float* grad_offset, float* grad_mask,
+                                     float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
   if (precision < -1 || precision > 2) return D2B_EINVAL;
   if (precision == -1) precision = d2b_deform_conv_tc_bwd_supported(p) ? 1 : 0;
   if (d.N > 0 && (!x || !offset || !weight || !grad_out)) return D2B_EINVAL;
+  if (cols && precision == 0) return D2B_EINVAL;
   if (grad_bias) {
     if (d.N == 0) {
       D2B_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d.Cout * 4, stream));
@@ -443,7 +456,7 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
   }
   if (precision != 0)
     return d2b_deform_conv_backward_tc(x, offset, mask, weight, grad_out, nullptr, nullptr, 0, p, precision,
-                                       (flags & D2B_DCN_X_NHWC) ? 1 : 0, grad_x, grad_offset, grad_mask, grad_weight,
+                                       (flags & D2B_DCN_X_NHWC) ? 1 : 0, cols, grad_x, grad_offset, grad_mask, grad_weight,
                                        workspace, workspace_bytes, stream_);
   if (flags & D2B_DCN_X_NHWC) return D2B_EUNSUPPORTED;
   const size_t nx = (size_t)d.N * d.Cin * d.H * d.W, noff = (size_t)d.N * d.DG * 2 * d.KK * d.HoWo;
@@ -490,27 +503,28 @@ D2B_API int d2b_deform_conv_backward(const float* x, const float* offset, const 
 //   scale = NULL and shift = bias -- happens in the TMEM epilogue.  Tensor-core precisions only.
 D2B_API int d2b_deform_conv_fused_forward(const float* x, const float* offset_mask, const float* weight, const float* scale,
                                           const float* shift, int relu, const d2b_dcn_params* p, int precision, int flags,
-                                          float* out, void* workspace, size_t workspace_bytes, void* stream) {
+                                          float* out, void* cols, void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
   if (d.N == 0) return D2B_OK;
   if (!x || !offset_mask || !weight || !out || precision == 0 || precision < -1 || precision > 2) return D2B_EINVAL;
   if (precision == -1) precision = 1;
   return d2b_deform_conv_forward_tc(x, offset_mask, nullptr, weight, scale, shift, relu, p, precision,
-                                    ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, out, workspace, workspace_bytes, stream);
+                                    ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, out, cols, workspace, workspace_bytes, stream);
 }
 
 // grad_out is the gradient of y; y itself (saved by the caller) gates the ReLU.  grad_offset_mask [N, 3*DG*kh*kw, Ho, Wo].
 D2B_API int d2b_deform_conv_fused_backward(const float* x, const float* offset_mask, const float* weight, const float* scale,
                                            int relu, const float* y, const float* grad_out, const d2b_dcn_params* p,
-                                           int precision, int flags, float* grad_x, float* grad_offset_mask,
-                                           float* grad_weight, void* workspace, size_t workspace_bytes, void* stream) {
+                                           int precision, int flags, const void* cols, float* grad_x,
+                                           float* grad_offset_mask, float* grad_weight, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
   Dims d;
   if (!make_dims(p, d)) return D2B_EINVAL;
   if (precision == 0 || precision < -1 || precision > 2) return D2B_EINVAL;
   if (precision == -1) precision = 1;
   if (d.N > 0 && (!x || !offset_mask || !weight || !grad_out)) return D2B_EINVAL;
   return d2b_deform_conv_backward_tc(x, offset_mask, nullptr, weight, grad_out, scale, y, relu, p, precision,
-                                     ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, grad_x, grad_offset_mask, nullptr, grad_weight,
-                                     workspace, workspace_bytes, stream);
+                                     ((flags & D2B_DCN_X_NHWC) ? 1 : 0) | 2, cols, grad_x, grad_offset_mask, nullptr,
+                                     grad_weight, workspace, workspace_bytes, stream);
 }

@@ -251,15 +251,16 @@ struct Taps4 {
   float4 v0, v1, v2, v3;
 };
 
-// the four corner pixels (4 channels each) of one tap entry; corners outside the image read as 0
-__device__ __forceinline__ void load_corners(const float* __restrict__ xc, int Cin, int W, int code, Taps4& t) {
-  const int pos0 = (code >> 4) - W - 1;
-  const float* __restrict__ p = xc + (long long)pos0 * Cin;
+// the four corner pixels (4 channels each) of one tap entry; corners outside the image read as 0.
+// `xcb` is the channel pointer biased by -(W + 1) pixels so that the tap's (pos0 + W + 1) indexes it directly; all offsets
+// are 32-bit element counts (H * W * Cin < 2^30 is part of the shape gate), `rs` = W * Cin.
+__device__ __forceinline__ void load_corners(const float* __restrict__ xcb, uint32_t Cin, uint32_t rs, int code, Taps4& t) {
+  const float* __restrict__ p = xcb + (uint32_t)(code >> 4) * Cin;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   t.v0 = (code & 1) ? __ldg(reinterpret_cast<const float4*>(p)) : z;
   t.v1 = (code & 2) ? __ldg(reinterpret_cast<const float4*>(p + Cin)) : z;
-  t.v2 = (code & 4) ? __ldg(reinterpret_cast<const float4*>(p + (size_t)W * Cin)) : z;
-  t.v3 = (code & 8) ? __ldg(reinterpret_cast<const float4*>(p + (size_t)(W + 1) * Cin)) : z;
+  t.v2 = (code & 4) ? __ldg(reinterpret_cast<const float4*>(p + rs)) : z;
+  t.v3 = (code & 8) ? __ldg(reinterpret_cast<const float4*>(p + (rs + Cin))) : z;
 }
 
 __device__ __forceinline__ void interp4(const Taps4& t, float w0, float w1, float w2, float w3, float (&v)[4]) {
@@ -289,15 +290,20 @@ __device__ __forceinline__ void gather_store(const Taps4& t, int4 tap, uint8_t* 
 }
 
 // ================================================================================================ K1: forward
-// grid (N * tiles_img, spans * oc tiles, k splits)
+// grid (N * tiles_img, spans * oc tiles, k splits).  One more warp than K2 / K3: the SAVER, which (when the caller keeps the
+// sampled columns for the weight gradient) copies every finished A stage -- already bf16 hi | lo in the tensor core's
+// swizzled tile layout -- to global memory with one bulk store, so that the backward streams the tiles back instead of
+// sampling x a second time (dcn_bwd_weight_cols_kernel).  Column tile of (image tile, super-group, unit): 16 KB hi [+ 16 KB lo].
+constexpr int kThreadsK1 = kThreads + 32;
 template <int kTmemCols>
-__global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __restrict__ xh,
-                                                                 const float* __restrict__ offset,
-                                                                 const float* __restrict__ mask,
-                                                                 const uint8_t* __restrict__ wt, const Epi ep, const TC d,
-                                                                 const K1P k, const int split, float* __restrict__ out) {
+__global__ void __launch_bounds__(kThreadsK1, 1) dcn_fwd_tc_kernel(const float* __restrict__ xh,
+                                                                   const float* __restrict__ offset,
+                                                                   const float* __restrict__ mask,
+                                                                   const uint8_t* __restrict__ wt, const Epi ep, const TC d,
+                                                                   const K1P k, const int split, float* __restrict__ out,
+                                                                   uint8_t* __restrict__ cols) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset form keeps the shared address space
   int4* taps = reinterpret_cast<int4*>(smem + k.S * k.stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(taps) + k.tap_bytes);
   uint64_t* full_bar = bars;
@@ -312,11 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
   const int kp0 = blockIdx.z * k.nkp, nkp = min(d.KK, kp0 + k.nkp) - kp0;
   const int nt = k.gspan * nkp * d.cbs;
   const int dg0 = (sg0 * d.cps) / d.cpdg;
+  const bool saving = cols != nullptr && oct == 0;  // CTAs of the other output-channel tiles build the same columns
 
   if (tid == 0) {
     for (int s = 0; s < k.S; ++s) {
       mbar_init(&full_bar[s], kWorkerWarps + 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], saving ? 2 : 1);  // the tensor core is done with the stage [+ the saver has copied it out]
     }
     mbar_init(accum_bar, 1);
     mbar_init_fence();
@@ -338,7 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
   if (warp < kWorkerWarps) {
     // =============================================================== GATHER: A tile [128 px][64 k'] K-major, hi + lo
     const int half = lane >> 4, q = lane & 15;
-    const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin;
+    const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin - (size_t)(d.W + 1) * d.Cin;  // biased: load_corners
+    const uint32_t ucin = (uint32_t)d.Cin, urs = (uint32_t)(d.W * d.Cin);
     int sgl = 0, kpl = 0, cb = 0;
     for (int t = 0; t < nt; ++t) {
       const int s = t % k.S;
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
 #pragma unroll
         for (int j = 0; j < kRowsPerHalf; ++j) tap[j] = tp[warp * 2 * kRowsPerHalf + j * 2 + half];
 #pragma unroll
-        for (int j = 0; j < kRowsPerHalf; ++j) load_corners(xc, d.Cin, d.W, tap[j].x, c[j]);
+        for (int j = 0; j < kRowsPerHalf; ++j) load_corners(xc, ucin, urs, tap[j].x, c[j]);
 #pragma unroll
         for (int j = 0; j < kRowsPerHalf; ++j) {
           const uint32_t r = (uint32_t)(warp * 2 * kRowsPerHalf + j * 2 + half);
@@ -418,6 +426,27 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_fwd_tc_kernel(const float* __
         }
       }
     }
+  } else if (warp == kWorkerWarps + 2) {
+    // =============================================================== SAVER: finished A stages -> column tiles in global memory
+    if (saving && lane == 0) {
+      const uint32_t tile_bytes = (uint32_t)(split ? 2 : 1) * (uint32_t)kTile;
+      int sgl = 0, kpl = 0, cb = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int s = t % k.S;
+        const uint32_t par = (uint32_t)((t / k.S) & 1);
+        mbar_wait(&full_bar[s], par);  // the workers' writes are fenced to the async proxy before they arrive
+        const size_t tile = ((size_t)blockIdx.x * d.SG + (sg0 + sgl)) * d.U + (size_t)(kp0 + kpl) * d.cbs + cb;
+        bulk_s2g(cols + tile * tile_bytes, smem + s * k.stage_bytes, tile_bytes);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(&empty_bar[s]);
+        if (++cb == d.cbs) {
+          cb = 0;
+          if (++kpl == nkp) { kpl = 0; ++sgl; }
+        }
+      }
+      bulk_wait0();
+    }
   } else {
     // =============================================================== MMA issuer
     const uint32_t idesc = umma_idesc(k.BN, false, false);
@@ -471,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
                                                                       float* __restrict__ gxh, float* __restrict__ goff,
                                                                       float* __restrict__ gmask) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset form keeps the shared address space
   constexpr int kStage = 4 * kTile;  // A hi | A lo | B hi | B lo
   float* gcol = reinterpret_cast<float*>(smem + 2 * kStage);
   int4* taps = reinterpret_cast<int4*>(smem + 2 * kStage + 128 * kGcolPitch * 4);
@@ -516,35 +545,53 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
   if (warp < kWorkerWarps) {
     const int half = lane >> 4, q = lane & 15;
     const int quad = warp & 3, cq = warp >> 2;
-    const float* __restrict__ ximg = xh + (size_t)b * d.H * d.W * d.Cin;
-    float* __restrict__ gimg = gxh ? gxh + (size_t)b * d.H * d.W * d.Cin : nullptr;
+    // both image pointers are biased by -(W + 1) pixels (see load_corners)
+    const size_t img_off = (size_t)b * d.H * d.W * d.Cin - (size_t)(d.W + 1) * d.Cin;
+    const float* __restrict__ ximg = xh + img_off;
+    float* __restrict__ gimg = gxh ? gxh + img_off : nullptr;
+    const uint32_t ucin = (uint32_t)d.Cin, urs = (uint32_t)(d.W * d.Cin);
     constexpr int R = kRowsPerHalf;  // pixel rows of the tile owned by this half-warp (fixed for the whole kernel)
-    float sh[R], sw[R], sm[R];       // running sums over channels of the current (deformable group, kernel point)
+    float sh[R], sw[R], sm[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) sh[j] = sw[j] = sm[j] = 0.f;
     int cur_kp = -1, cur_dg = -1;
 
     auto flush = [&]() {
       if (cur_kp < 0) return;
+      // 12 partial sums (4 rows x {d/dh, d/dw, d/dmask}) per lane, to be summed over the 16 lanes of the half-warp.
+      // Recursive halving: at each step a lane keeps one half of its values and hands the other half to its partner,
+      // so 6 + 3 + 2 + 1 shuffles replace 12 butterflies of 4; lane q ends up owning value (row = q >> 2, which = q & 3).
+      static_assert(R == 4, "the reduction below is written for 4 rows per half-warp");
+      float v12[12];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-#pragma unroll
-        for (int o = 8; o; o >>= 1) {
-          sh[j] += __shfl_xor_sync(0xffffffffu, sh[j], o);
-          sw[j] += __shfl_xor_sync(0xffffffffu, sw[j], o);
-          sm[j] += __shfl_xor_sync(0xffffffffu, sm[j], o);
-        }
+        v12[3 * j] = sh[j];
+        v12[3 * j + 1] = sw[j];
+        v12[3 * j + 2] = sm[j];
       }
-      // 3 * R values per half-warp, written by its 16 lanes
-      for (int o = q; o < 3 * R; o += 16) {
-        const int j = o / 3, which = o - j * 3;
-        float v = 0.f;
+      const bool b8 = q & 8, b4 = q & 4, b2 = q & 2, b1 = q & 1;
+      float v6[6], v3[3];
 #pragma unroll
-        for (int jj = 0; jj < R; ++jj)
-          if (jj == j) v = which == 0 ? sh[jj] : (which == 1 ? sw[jj] : sm[jj]);
+      for (int i = 0; i < 6; ++i) {
+        const float keep = b8 ? v12[i + 6] : v12[i], send = b8 ? v12[i] : v12[i + 6];
+        v6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float keep = b4 ? v6[i + 3] : v6[i], send = b4 ? v6[i] : v6[i + 3];
+        v3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      // {v3[0], v3[1]} | {v3[2], -}
+      const float k0 = b2 ? v3[2] : v3[0], s0 = b2 ? v3[0] : v3[2];
+      const float k1 = b2 ? 0.f : v3[1], s1 = b2 ? v3[1] : 0.f;
+      const float u0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+      const float u1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+      float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, b1 ? u0 : u1, 1);
+      {
+        const int j = q >> 2, which = q & 3;
         const int row = warp * 2 * R + j * 2 + half;
         const int p = p0 + row;
-        if (p < d.HoWo) {
+        if (which < 3 && p < d.HoWo) {
           if (which < 2) {
             if (goff) red_add(goff + (size_t)b * d.off_bs + ((size_t)cur_dg * 2 * d.KK + 2 * cur_kp + which) * d.HoWo + p, v);
           } else if (gmask) {
@@ -599,8 +646,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
         }
         const int4* __restrict__ tp = taps + ((dg - dg0) * nkp + (kp - kp0)) * 128;
         const float* __restrict__ xc = ximg + cbase + q * 4;
-#pragma unroll
-        constexpr int kB2 = 2;  // pixel rows per batch: 8 loads in flight per lane, then up to 8 reductions
+        float* __restrict__ gc = gimg + cbase + q * 4;
+        constexpr int kB2 = 2;  // pixel rows per batch: 4 * kB2 loads in flight per lane, then up to 4 * kB2 reductions
 #pragma unroll
         for (int it = 0; it < R / kB2; ++it) {
           int4 tap[kB2];
@@ -608,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
 #pragma unroll
           for (int e = 0; e < kB2; ++e) tap[e] = tp[warp * 2 * R + (it * kB2 + e) * 2 + half];
 #pragma unroll
-          for (int e = 0; e < kB2; ++e) load_corners(xc, d.Cin, d.W, tap[e].x, c[e]);
+          for (int e = 0; e < kB2; ++e) load_corners(xc, ucin, urs, tap[e].x, c[e]);
 #pragma unroll
           for (int e = 0; e < kB2; ++e) {
             if ((tap[e].x & 15) == 0) continue;  // sample outside the image: no gradient anywhere
@@ -618,29 +665,43 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
             const float lh = __int_as_float(tap[e].y), lw = __int_as_float(tap[e].z), mk = __int_as_float(tap[e].w);
             const float hh = 1.f - lh, hw = 1.f - lw;
             const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
-            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-            const float a0[4] = {c[e].v0.x, c[e].v0.y, c[e].v0.z, c[e].v0.w}, a1[4] = {c[e].v1.x, c[e].v1.y, c[e].v1.z, c[e].v1.w};
-            const float a2[4] = {c[e].v2.x, c[e].v2.y, c[e].v2.z, c[e].v2.w}, a3[4] = {c[e].v3.x, c[e].v3.y, c[e].v3.z, c[e].v3.w};
-            float gm[4];
-            float ah = 0.f, aw = 0.f, am = 0.f;
+            const F2 LH = f2_pack(lh, lh), LW = f2_pack(lw, lw), HH = f2_pack(hh, hh), HW = f2_pack(hw, hw);
+            const F2 W0 = f2_pack(w0, w0), W1 = f2_pack(w1, w1), W2 = f2_pack(w2, w2), W3 = f2_pack(w3, w3);
+            const F2 MK = f2_pack(mk, mk);
+            // two channels per instruction (packed fp32): pair 0 = channels 0,1; pair 1 = channels 2,3
+            const F2 G[2] = {f2_pack(g4.x, g4.y), f2_pack(g4.z, g4.w)};
+            const F2 A0[2] = {f2_pack(c[e].v0.x, c[e].v0.y), f2_pack(c[e].v0.z, c[e].v0.w)};
+            const F2 A1[2] = {f2_pack(c[e].v1.x, c[e].v1.y), f2_pack(c[e].v1.z, c[e].v1.w)};
+            const F2 A2[2] = {f2_pack(c[e].v2.x, c[e].v2.y), f2_pack(c[e].v2.z, c[e].v2.w)};
+            const F2 A3[2] = {f2_pack(c[e].v3.x, c[e].v3.y), f2_pack(c[e].v3.z, c[e].v3.w)};
+            F2 GM[2];
+            F2 th2 = f2_pack(0.f, 0.f), tw2 = th2, tm2 = th2;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              gm[i] = g[i] * mk;
+            for (int i = 0; i < 2; ++i) {
+              GM[i] = f2_mul(G[i], MK);
               // d val / d h = (1-lw)(v2-v0) + lw (v3-v1);  d val / d w = (1-lh)(v1-v0) + lh (v3-v2)
-              ah = fmaf(gm[i], fmaf(lw, a3[i] - a1[i], hw * (a2[i] - a0[i])), ah);
-              aw = fmaf(gm[i], fmaf(lh, a3[i] - a2[i], hh * (a1[i] - a0[i])), aw);
-              am = fmaf(g[i], fmaf(w3, a3[i], fmaf(w2, a2[i], fmaf(w1, a1[i], w0 * a0[i]))), am);
+              const F2 dh = f2_fma(LW, f2_sub(A3[i], A1[i]), f2_mul(HW, f2_sub(A2[i], A0[i])));
+              const F2 dw = f2_fma(LH, f2_sub(A3[i], A2[i]), f2_mul(HH, f2_sub(A1[i], A0[i])));
+              const F2 val = f2_fma(W3, A3[i], f2_fma(W2, A2[i], f2_fma(W1, A1[i], f2_mul(W0, A0[i]))));
+              th2 = f2_fma(GM[i], dh, th2);
+              tw2 = f2_fma(GM[i], dw, tw2);
+              tm2 = f2_fma(G[i], val, tm2);
             }
-            sh[j] += ah;
-            sw[j] += aw;
-            sm[j] += am;
+            {
+              float e0, e1;
+              f2_unpack(th2, e0, e1);
+              sh[j] += e0 + e1;
+              f2_unpack(tw2, e0, e1);
+              sw[j] += e0 + e1;
+              f2_unpack(tm2, e0, e1);
+              sm[j] += e0 + e1;
+            }
             if (gimg) {
-              const int pos0 = (tap[e].x >> 4) - d.W - 1;
-              float* gp = gimg + (long long)pos0 * d.Cin + cbase + q * 4;
-              if (tap[e].x & 1) red_add_v4(gp, gm[0] * w0, gm[1] * w0, gm[2] * w0, gm[3] * w0);
-              if (tap[e].x & 2) red_add_v4(gp + d.Cin, gm[0] * w1, gm[1] * w1, gm[2] * w1, gm[3] * w1);
-              if (tap[e].x & 4) red_add_v4(gp + (size_t)d.W * d.Cin, gm[0] * w2, gm[1] * w2, gm[2] * w2, gm[3] * w2);
-              if (tap[e].x & 8) red_add_v4(gp + (size_t)(d.W + 1) * d.Cin, gm[0] * w3, gm[1] * w3, gm[2] * w3, gm[3] * w3);
+              float* gp = gc + (uint32_t)(tap[e].x >> 4) * ucin;
+              red_add_v4_if(tap[e].x & 1, gp, f2_mul(GM[0], W0), f2_mul(GM[1], W0));
+              red_add_v4_if(tap[e].x & 2, gp + ucin, f2_mul(GM[0], W1), f2_mul(GM[1], W1));
+              red_add_v4_if(tap[e].x & 4, gp + urs, f2_mul(GM[0], W2), f2_mul(GM[1], W2));
+              red_add_v4_if(tap[e].x & 8, gp + (urs + ucin), f2_mul(GM[0], W3), f2_mul(GM[1], W3));
             }
           }
         }
@@ -717,11 +778,10 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
                                                                         const float* __restrict__ offset,
                                                                         const float* __restrict__ mask,
                                                                         const uint8_t* __restrict__ gt, const TC d,
-                                                                        const K3P k, const int split_dbg,
+                                                                        const K3P k, const int split,
                                                                         float* __restrict__ gw) {
-  const int split = split_dbg & 1, dbg = split_dbg >> 4;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset form keeps the shared address space
   int4* tap_s = reinterpret_cast<int4*>(smem + k.S * k.stage_bytes);  // [16 warps][8]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tap_s) + 4096);
   uint64_t* full_bar = bars;
@@ -786,9 +846,10 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
       TapRaw raw = {0.f, 0.f, 1.f};
       if (have_next) {
         stage_of(i + 1, bn, pbn);
-        if (tl_ok && !(dbg & 4)) raw = tap_loads(d, offset, mask, bn, tl_dg, tl_kp, pbn + warp * PX + tl_j);
+        if (tl_ok) raw = tap_loads(d, offset, mask, bn, tl_dg, tl_kp, pbn + warp * PX + tl_j);
       }
-      const float* __restrict__ xc = xh + (size_t)b * d.H * d.W * d.Cin + cbase + q * 4;
+      const float* __restrict__ xc = xh + ((size_t)b * d.H * d.W - (size_t)(d.W + 1)) * d.Cin + cbase + q * 4;  // biased
+      const uint32_t ucin = (uint32_t)d.Cin, urs = (uint32_t)(d.W * d.Cin);
       uint8_t* a_hi = smem + s * k.stage_bytes + half * 8192;
       uint8_t* a_lo = a_hi + kTile;
       const int4* cur = my_taps + (i & 1) * (2 * PX) + half * PX;
@@ -799,14 +860,14 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
 #pragma unroll
         for (int j = 0; j < PX; ++j) tap[j] = cur[j];
 #pragma unroll
-        for (int j = 0; j < PX; ++j) load_corners(xc, d.Cin, d.W, (dbg & 1) ? 0 : tap[j].x, c[j]);
+        for (int j = 0; j < PX; ++j) load_corners(xc, ucin, urs, tap[j].x, c[j]);
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
           const uint32_t r = (uint32_t)(warp * PX + j);
           gather_store(c[j], tap[j], a_hi, a_lo, swz128(r, (uint32_t)(q >> 1)) + (uint32_t)(q & 1) * 8u, split != 0);
         }
       }
-      if (have_next && lane < 2 * PX && !(dbg & 4))
+      if (have_next && lane < 2 * PX)
         my_taps[((i + 1) & 1) * (2 * PX) + lane] =
             tl_ok ? tap_finish(d, raw, mask != nullptr, tl_kp, pbn + warp * PX + tl_j) : make_int4(0, 0, 0, 0);
       fence_proxy_async();
@@ -861,7 +922,132 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
         for (int kk = 0; kk < 4; ++kk) {
           // A: 16 pixels (K) = two 8-row atoms 1024 B apart; the two 64-channel M blocks are 8192 B apart
           const uint32_t ao = (uint32_t)kk * 2048u, bo = (uint32_t)kk * 32u;
-          if (dbg & 2) continue;
+          umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          if (split) {
+            umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_lo + bo, 0, 1024), idesc, 1u);
+            umma_bf16(tmem_base, umma_desc(a_lo + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == ns - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkerWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ================================================================================================ K3c: backward weight from saved columns
+// Same grid, tiles and epilogue as K3, but the A operand is streamed back from the column tiles the forward saved
+// (dcn_fwd_tc_kernel's saver warp) instead of being sampled from x again: a pure TMA -> tcgen05 pipeline.  A 64-pixel stage of
+// a unit is one contiguous 8 KB half of its [128 px][64 ch] tile (the 128-byte swizzle repeats every 8 rows).
+template <int kTmemCols>
+__global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_cols_kernel(const uint8_t* __restrict__ cols,
+                                                                          const uint8_t* __restrict__ gt, const TC d,
+                                                                          const K3P k, const int S, const int split,
+                                                                          float* __restrict__ gw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * k.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + S;
+  uint64_t* accum_bar = bars + 2 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.x;
+  const int sg = blockIdx.z / k.noct, oct = blockIdx.z - sg * k.noct;
+  const int total = d.N * d.stages_img;
+  const int gs0 = blockIdx.y * k.sper, gs1 = min(total, gs0 + k.sper), ns = gs1 - gs0;
+  const int nu = (2 * mb + 1 < d.U) ? 2 : 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_init_fence();
+  }
+  if (warp == kWorkerWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (nu == 1 && tid < kWorkers) {  // odd unit count: the second 64 rows of A are never loaded; keep them finite
+    for (int s = 0; s < S; ++s)
+      for (int i = tid; i < 2 * 512; i += kWorkers) {
+        const int part = i >> 9, w = i & 511;
+        reinterpret_cast<uint4*>(smem + s * k.stage_bytes + part * kTile + 8192)[w] = make_uint4(0, 0, 0, 0);
+      }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWorkerWarps) {
+    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> red.add into gW
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int quad = warp & 3, cgrp = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int eu = 2 * mb + (row >> 6);
+    const bool row_ok = eu < d.U;
+    const int ekp = row_ok ? eu / d.cbs : 0;
+    const int ec = sg * d.cps + (row_ok ? eu - ekp * d.cbs : 0) * 64 + (row & 63);  // global input channel
+    const int egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
+    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += kWorkerWarps / 4) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int oc = sg * d.ops + oct * k.BN + c16 * 16 + i;
+          if (oc / d.opg == egrp) red_add(gw + ((size_t)oc * d.cpg + ecin) * d.KK + ekp, __uint_as_float(r[i]));
+        }
+      }
+    }
+  } else if (warp == kWorkerWarps) {
+    // =============================================================== TMA producer: column halves + grad_out tile per stage
+    if (lane == 0) {
+      const uint32_t parts = split ? 2u : 1u;
+      const uint32_t tile_bytes = parts * (uint32_t)kTile;
+      const uint32_t gbytes = parts * (uint32_t)k.BN * 128u;
+      for (int i = 0; i < ns; ++i) {
+        const int s = i % S;
+        const uint32_t par = (uint32_t)((i / S) & 1);
+        const int gs = gs0 + i;
+        const int b = gs / d.stages_img, st = gs - b * d.stages_img;
+        mbar_wait(&empty_bar[s], par ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)nu * parts * 8192u + gbytes);
+        uint8_t* stage = smem + s * k.stage_bytes;
+        const uint8_t* src =
+            cols + ((((size_t)b * d.tiles_img + (st >> 1)) * d.SG + sg) * d.U + 2 * mb) * tile_bytes + (size_t)(st & 1) * 8192;
+        for (int ul = 0; ul < nu; ++ul)
+          for (uint32_t part = 0; part < parts; ++part)
+            bulk_g2s(stage + part * kTile + ul * 8192, src + (size_t)ul * tile_bytes + (size_t)part * kTile, 8192u, &full_bar[s]);
+        const size_t tile = ((size_t)gs * d.SG + sg) * k.noct + oct;
+        bulk_g2s(stage + 2 * kTile, gt + tile * (size_t)(2 * k.BN * 128), gbytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer (as K3)
+    const uint32_t idesc = umma_idesc(k.BN, true, false);
+    for (int i = 0; i < ns; ++i) {
+      const int s = i % S;
+      const uint32_t par = (uint32_t)((i / S) & 1);
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * k.stage_bytes), a_lo = a_hi + kTile;
+        const uint32_t b_hi = a_hi + 2 * kTile, b_lo = b_hi + (uint32_t)k.BN * 128u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ao = (uint32_t)kk * 2048u, bo = (uint32_t)kk * 32u;
           umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_hi + bo, 0, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
           if (split) {
             umma_bf16(tmem_base, umma_desc(a_hi + ao, 8192, 1024), umma_desc(b_lo + bo, 0, 1024), idesc, 1u);
@@ -1110,10 +1296,19 @@ size_t d2b_deform_conv_tc_fwd_workspace(const d2b_dcn_params* p, int x_nhwc) {
   return b;
 }
 
+// bytes of the column tiles one forward call saves for the backward (0: shape not taken by the tensor-core kernels)
+size_t d2b_deform_conv_tc_cols_bytes(const d2b_dcn_params* p, int precision) {
+  TC d;
+  K1P k;
+  if (precision == 0 || !make_tc(p, d) || !plan_k1(d, k)) return 0;
+  return (size_t)d.N * d.tiles_img * d.SG * d.U * (size_t)(precision == 1 ? 2 : 1) * kTile;
+}
+
 // tcflags: bit 0 = x is NHWC, bit 1 = `offset` is the fused [N, 3*DG*KK, Ho, Wo] offset + mask-logit tensor (mask must be null)
+// cols: optional, d2b_deform_conv_tc_cols_bytes() bytes, 16-byte aligned: receives the sampled columns (see the saver warp)
 int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float* mask, const float* weight,
                                const float* scale, const float* shift, int relu, const d2b_dcn_params* p, int precision,
-                               int tcflags, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+                               int tcflags, float* out, void* cols, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int x_nhwc = tcflags & 1;
   TC d;
@@ -1125,7 +1320,9 @@ int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float*
     mask = use_fused_offset_mask(d, offset);
   }
   if (!workspace || workspace_bytes < d2b_deform_conv_tc_fwd_workspace(p, x_nhwc)) return D2B_EWORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15))) return D2B_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15)) ||
+      (reinterpret_cast<uintptr_t>(cols) & 15))
+    return D2B_EINVAL;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   uint8_t* wt = ws;
   ws += align256((size_t)d.SG * k.noct * d.U * 2 * k.BN * 128);
@@ -1143,18 +1340,19 @@ int d2b_deform_conv_forward_tc(const float* x, const float* offset, const float*
   }
   if (k.red) D2B_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)d.N * d.Cout * d.HoWo, stream));
   const int smem_bytes = k.S * k.stage_bytes + k.tap_bytes + 1024 + 256;
-  const int cols = pow2_cols(k.gspan * k.BN);
+  const int tcols = pow2_cols(k.gspan * k.BN);
   const int split = precision == 1 ? 1 : 0;
   const Epi ep = {scale, shift, relu};
   dim3 grid(d.N * d.tiles_img, (d.SG / k.gspan) * k.noct, k.ksplit);
 #define D2B_LAUNCH_K1(COLS)                                                                                            \
   {                                                                                                                    \
     D2B_ALLOW_BIG_SMEM(dcn_fwd_tc_kernel<COLS>);                                                                       \
-    dcn_fwd_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, wt, ep, d, k, split, out);       \
+    dcn_fwd_tc_kernel<COLS><<<grid, kThreadsK1, smem_bytes, stream>>>(xh, offset, mask, wt, ep, d, k, split, out,      \
+                                                                      reinterpret_cast<uint8_t*>(cols));               \
   }
-  if (cols <= 32) D2B_LAUNCH_K1(32)
-  else if (cols == 64) D2B_LAUNCH_K1(64)
-  else if (cols == 128) D2B_LAUNCH_K1(128)
+  if (tcols <= 32) D2B_LAUNCH_K1(32)
+  else if (tcols == 64) D2B_LAUNCH_K1(64)
+  else if (tcols == 128) D2B_LAUNCH_K1(128)
   else D2B_LAUNCH_K1(256)
 #undef D2B_LAUNCH_K1
   D2B_CHECK_LAUNCH();
@@ -1188,9 +1386,9 @@ size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int
 // the sigmoid) and grad_mask must be null.  scale / y_saved / relu: transpose of the forward's epilogue.
 int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float* mask, const float* weight,
                                 const float* grad_out, const float* scale, const float* y_saved, int relu,
-                                const d2b_dcn_params* p, int precision, int tcflags, float* grad_x, float* grad_offset,
-                                float* grad_mask, float* grad_weight, void* workspace, size_t workspace_bytes,
-                                void* stream_) {
+                                const d2b_dcn_params* p, int precision, int tcflags, const void* cols, float* grad_x,
+                                float* grad_offset, float* grad_mask, float* grad_weight, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int x_nhwc = tcflags & 1;
   TC d;
@@ -1215,7 +1413,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
   }
   if (!workspace || workspace_bytes < d2b_deform_conv_tc_bwd_workspace(p, x_nhwc, need_data, need_weight)) return D2B_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (x_nhwc && (reinterpret_cast<uintptr_t>(x) & 15)) ||
-      (x_nhwc && grad_x && (reinterpret_cast<uintptr_t>(grad_x) & 15)))
+      (x_nhwc && grad_x && (reinterpret_cast<uintptr_t>(grad_x) & 15)) || (reinterpret_cast<uintptr_t>(cols) & 15))
     return D2B_EINVAL;
   const int split = precision == 1 ? 1 : 0;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -1274,21 +1472,35 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
       dcn_gout_oc_tiles_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(grad_out, y_saved, ep, d, k3.BN, k3.noct, gt_oc);
       D2B_CHECK_LAUNCH();
     }
-    const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;
-    const int cols = pow2_cols(k3.BN);
-    const char* dbg_env = getenv("D2B_DCN_DEBUG");  // experiment switches (tools/dev_k3.py); 0 in production
-    const int dbg3 = dbg_env ? atoi(dbg_env) : 0;
+    const int tcols = pow2_cols(k3.BN);
     dim3 grid(d.MC, k3.nsplit, d.SG * k3.noct);
+    if (cols) {  // the forward kept its sampled columns: stream them back (no second pass over x)
+      const int S = std::min(6, (kMaxSmem - 2048) / k3.stage_bytes);
+      const int smem_bytes = S * k3.stage_bytes + 1024 + 256;
+      const uint8_t* cl = reinterpret_cast<const uint8_t*>(cols);
+#define D2B_LAUNCH_K3C(COLS)                                                                                             \
+  {                                                                                                                      \
+    D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_cols_kernel<COLS>);                                                                \
+    dcn_bwd_weight_cols_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(cl, gt_oc, d, k3, S, split, grad_weight);   \
+  }
+      if (tcols <= 32) D2B_LAUNCH_K3C(32)
+      else if (tcols == 64) D2B_LAUNCH_K3C(64)
+      else if (tcols == 128) D2B_LAUNCH_K3C(128)
+      else D2B_LAUNCH_K3C(256)
+#undef D2B_LAUNCH_K3C
+    } else {
+      const int smem_bytes = k3.S * k3.stage_bytes + 4096 + 1024 + 256;
 #define D2B_LAUNCH_K3(COLS)                                                                                              \
   {                                                                                                                      \
     D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_tc_kernel<COLS>);                                                                  \
-    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_oc, d, k3, split | (dbg3 << 4), grad_weight); \
+    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_oc, d, k3, split, grad_weight); \
   }
-    if (cols <= 32) D2B_LAUNCH_K3(32)
-    else if (cols == 64) D2B_LAUNCH_K3(64)
-    else if (cols == 128) D2B_LAUNCH_K3(128)
-    else D2B_LAUNCH_K3(256)
+      if (tcols <= 32) D2B_LAUNCH_K3(32)
+      else if (tcols == 64) D2B_LAUNCH_K3(64)
+      else if (tcols == 128) D2B_LAUNCH_K3(128)
+      else D2B_LAUNCH_K3(256)
 #undef D2B_LAUNCH_K3
+    }
     D2B_CHECK_LAUNCH();
   }
   return D2B_OK;

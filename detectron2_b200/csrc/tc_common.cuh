@@ -67,6 +67,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// shared -> global, tracked by the thread's bulk async-group (commit, then wait for the reads of the source to finish
+// before the shared-memory tile is reused)
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ TMEM
 template <int kCols>
@@ -158,6 +167,37 @@ __device__ __forceinline__ F2 f2_fma(F2 w, F2 v, F2 c) {
   F2 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(w.v), "l"(v.v), "l"(c.v));
   return d;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) {
+  F2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ void red_add_v4(float* p, F2 ab, F2 cd) {
+  float a, b, c, d;
+  f2_unpack(ab, a, b);
+  f2_unpack(cd, c, d);
+  red_add_v4(p, a, b, c, d);
+}
+// predicated form: one instruction slot, no branch around it
+__device__ __forceinline__ void red_add_v4_if(int pred, float* p, F2 ab, F2 cd) {
+  float a, b, c, d;
+  f2_unpack(ab, a, b);
+  f2_unpack(cd, c, d);
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+      "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred)
+      : "memory");
 }
 
 // byte offset of the 16-byte chunk `c16` of row `r` inside a 128-byte-swizzled tile of 128-byte rows

@@ -24,8 +24,8 @@ def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1
         raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
     if not input.is_cuda:
         raise NotImplementedError("Deformable Conv is not supported on CPUs!")
-    return ops.deform_conv_op(input, offset, None, weight, None, list(_pair(stride)), list(_pair(padding)),
-                              list(_pair(dilation)), groups, deformable_groups, DEFAULT_PRECISION)
+    return ops.deform_conv(input, offset, None, weight, None, list(_pair(stride)), list(_pair(padding)),
+                           list(_pair(dilation)), groups, deformable_groups, DEFAULT_PRECISION)
 
 
 def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
@@ -33,8 +33,8 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
     """DCNv2 (`_ModulatedDeformConv.apply`)."""
     if not input.is_cuda:
         raise NotImplementedError("Deformable Conv is not supported on CPUs!")
-    return ops.deform_conv_op(input, offset, mask, weight, bias, list(_pair(stride)), list(_pair(padding)),
-                              list(_pair(dilation)), groups, deformable_groups, DEFAULT_PRECISION)
+    return ops.deform_conv(input, offset, mask, weight, bias, list(_pair(stride)), list(_pair(padding)),
+                           list(_pair(dilation)), groups, deformable_groups, DEFAULT_PRECISION)
 
 
 def _empty_output(x, weight, padding, dilation, kernel_size, stride):

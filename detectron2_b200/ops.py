@@ -527,7 +527,7 @@ def deform_conv_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Te
     ws = _ws(ws_bytes, x.device)
     with torch.cuda.device(x.device):
         check(_C.lib().d2b_deform_conv_forward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision, flags,
-                                               ptr(out), ptr(ws), ws_bytes, stream_ptr(x.device)),
+                                               ptr(out), None, ptr(ws), ws_bytes, stream_ptr(x.device)),
               "deform_conv_forward")
     return out.to(x.dtype)
 
@@ -541,8 +541,11 @@ def _(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformab
 def deform_conv_backward_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, grad_out: Tensor,
                             stride: List[int], padding: List[int], dilation: List[int], groups: int,
                             deformable_groups: int, with_bias: bool, need_data: bool,
-                            need_weight: bool, precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _C.require_cuda(x, offset, mask, weight, grad_out)
+                            need_weight: bool, precision: int,
+                            cols: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """All gradients of deform_conv.  `cols`: the column tiles saved by deform_conv_train (same shapes / precision); the
+    weight gradient then streams them back instead of sampling x again.  grad_x has x's memory format."""
+    _C.require_cuda(x, offset, mask, weight, grad_out, cols)
     of, mf, wf, gf = _f32c(offset), _f32c(mask), _f32c(weight), _f32c(grad_out)
     p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
     xf, flags = _dcn_x(x, p, precision, True)
@@ -557,16 +560,19 @@ def deform_conv_backward_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], w
     ws_bytes = _C.lib().d2b_deform_conv_backward_workspace_bytes(C.byref(p), precision, flags, int(need_data),
                                                                  int(need_weight))
     ws = _ws(ws_bytes, dev)
+    if cols is not None and cols.numel() != _C.lib().d2b_deform_conv_cols_bytes(C.byref(p), precision):
+        raise RuntimeError("deform_conv_backward: `cols` does not belong to this shape / precision")
     with torch.cuda.device(dev):
         check(_C.lib().d2b_deform_conv_backward(ptr(xf), ptr(of), ptr(mf), ptr(wf), ptr(gf), C.byref(p), precision, flags,
-                                                P(gx), P(go), P(gm), P(gw), P(gb), ptr(ws), ws_bytes, stream_ptr(dev)),
+                                                ptr(cols), P(gx), P(go), P(gm), P(gw), P(gb), ptr(ws), ws_bytes,
+                                                stream_ptr(dev)),
               "deform_conv_backward")
     return gx, go, gm, gw, gb
 
 
 @deform_conv_backward_op.register_fake
 def _(x, offset, mask, weight, grad_out, stride, padding, dilation, groups, deformable_groups, with_bias, need_data,
-      need_weight, precision):
+      need_weight, precision, cols=None):
     e = lambda: x.new_empty((0,))  # noqa: E731
     return (torch.empty_like(x) if need_data else e(), torch.empty_like(offset) if need_data else e(),
             torch.empty_like(mask) if (need_data and mask is not None) else e(),
@@ -597,6 +603,96 @@ def _dcn_bwd(ctx, grad):
 deform_conv_op.register_autograd(_dcn_bwd, setup_context=_dcn_setup)
 
 
+# ----------------------------------------------------------------------------------- training forward: keeps what the backward needs
+def _dcn_train_layout(x: Tensor, p, precision: int):
+    """(x for the kernel, flags, saved channels-last copy or None, cols or None).  When the tensor-core kernels take the
+    shape in both directions, x is laid out channels-last ONCE (our layout kernel) and that copy serves the forward and both
+    gradient kernels; the forward also keeps its sampled columns for the weight gradient."""
+    xf = x.to(dtype=torch.float32)
+    lib = _C.lib()
+    if precision != 0 and lib.d2b_deform_conv_tc_shape_supported(C.byref(p), 0) and \
+            lib.d2b_deform_conv_tc_shape_supported(C.byref(p), 1) and xf.numel():
+        if _is_channels_last(xf) and xf.data_ptr() % 16 == 0:
+            xs = None
+            xk = xf
+        else:
+            xs = pyramid_to_channels_last([xf.detach().contiguous()])[0]
+            xk = xs
+        if _is_channels_last(xk) and xk.data_ptr() % 16 == 0:
+            nb = lib.d2b_deform_conv_cols_bytes(C.byref(p), precision)
+            cols = torch.empty((nb,), dtype=torch.uint8, device=x.device) if nb else None
+            return xk, _C.DCN_X_NHWC, xs, cols
+    xk, flags = _dcn_x(x, p, precision, False)
+    return xk, flags, None, None
+
+
+@torch.library.custom_op("d2b200::deform_conv_train", mutates_args=(), device_types="cuda")
+def deform_conv_train_op(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
+                         stride: List[int], padding: List[int], dilation: List[int], groups: int, deformable_groups: int,
+                         precision: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """deform_conv for a step that will be differentiated: (out, x_saved, cols).  x_saved is the channels-last fp32 copy of x
+    the kernels ran on (empty when x itself was usable), cols the saved column tiles (empty when the shape has no
+    tensor-core path); both go to deform_conv_backward."""
+    _C.require_cuda(x, offset, mask, weight, bias)
+    _dcn_check(x, offset, mask, weight, stride, padding, dilation, groups, deformable_groups)
+    of, mf, wf, bf = _f32c(offset), _f32c(mask), _f32c(weight), _f32c(bias)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    xk, flags, xs, cols = _dcn_train_layout(x, p, precision)
+    out = torch.empty(dcn_output_shape(xk, wf, stride, padding, dilation), dtype=torch.float32, device=x.device)
+    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), precision, flags)
+    ws = _ws(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        check(_C.lib().d2b_deform_conv_forward(ptr(xk), ptr(of), ptr(mf), ptr(wf), ptr(bf), C.byref(p), precision, flags,
+                                               ptr(out), ptr(cols), ptr(ws), ws_bytes, stream_ptr(x.device)),
+              "deform_conv_forward")
+    e = lambda dt: torch.empty((0,), dtype=dt, device=x.device)  # noqa: E731
+    return out.to(x.dtype), xs if xs is not None else e(torch.float32), cols if cols is not None else e(torch.uint8)
+
+
+@deform_conv_train_op.register_fake
+def _(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups, precision):
+    return (x.new_empty(dcn_output_shape(x, weight, stride, padding, dilation)), x.new_empty((0,), dtype=torch.float32),
+            x.new_empty((0,), dtype=torch.uint8))
+
+
+def _dcnt_setup(ctx, inputs, output):
+    x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, precision = inputs
+    _, xs, cols = output
+    ctx.save_for_backward(x if xs.numel() == 0 else xs, offset, mask, weight, cols)
+    ctx.args = (stride, padding, dilation, groups, dg, bias is not None, precision, x.dtype)
+    ctx.has_mask = mask is not None
+
+
+def _dcnt_bwd(ctx, grad, _gxs, _gcols):
+    x, offset, mask, weight, cols = ctx.saved_tensors
+    stride, padding, dilation, groups, dg, with_bias, precision, xdtype = ctx.args
+    need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ctx.has_mask and ctx.needs_input_grad[2])
+    need_weight = ctx.needs_input_grad[3] or (with_bias and ctx.needs_input_grad[4])
+    gx, go, gm, gw, gb = deform_conv_backward_op(x, offset, mask, weight, grad, stride, padding, dilation, groups, dg,
+                                                 with_bias, need_data, need_weight, precision,
+                                                 cols if cols.numel() else None)
+    return (gx.to(xdtype) if need_data else None, go.to(offset.dtype) if need_data else None,
+            gm.to(mask.dtype) if (need_data and ctx.has_mask) else None,
+            gw.to(weight.dtype) if need_weight else None, gb if (with_bias and need_weight) else None,
+            None, None, None, None, None, None)
+
+
+deform_conv_train_op.register_autograd(_dcnt_bwd, setup_context=_dcnt_setup)
+
+
+def deform_conv(x: Tensor, offset: Tensor, mask: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
+                stride: List[int], padding: List[int], dilation: List[int], groups: int, deformable_groups: int,
+                precision: int) -> Tensor:
+    """The entry the layers call: the training op (which keeps the channels-last copy of x and the sampled columns for the
+    backward) when a gradient can flow, the plain forward otherwise."""
+    if torch.is_grad_enabled() and (x.requires_grad or offset.requires_grad or weight.requires_grad
+                                    or (mask is not None and mask.requires_grad)
+                                    or (bias is not None and bias.requires_grad)):
+        return deform_conv_train_op(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups,
+                                    precision)[0]
+    return deform_conv_op(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups, precision)
+
+
 # ----------------------------------------------------------------------------------- DeformBottleneckBlock conv2, fused
 @torch.library.custom_op("d2b200::deform_conv_fused", mutates_args=(), device_types="cuda")
 def deform_conv_fused_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
@@ -624,7 +720,8 @@ def deform_conv_fused_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: 
     ws = _ws(ws_bytes, x.device)
     with torch.cuda.device(x.device):
         check(_C.lib().d2b_deform_conv_fused_forward(ptr(xf), ptr(om), ptr(wf), ptr(sc), ptr(sh), int(relu), C.byref(p),
-                                                     precision, flags, ptr(out), ptr(ws), ws_bytes, stream_ptr(x.device)),
+                                                     precision, flags, ptr(out), None, ptr(ws), ws_bytes,
+                                                     stream_ptr(x.device)),
               "deform_conv_fused_forward")
     return out.to(x.dtype)
 
@@ -650,8 +747,8 @@ def deform_conv_fused_backward_op(x: Tensor, offset_mask: Tensor, weight: Tensor
     ws = _ws(ws_bytes, x.device)
     with torch.cuda.device(x.device):
         check(_C.lib().d2b_deform_conv_fused_backward(ptr(xf), ptr(om), ptr(wf), ptr(sc), int(relu), ptr(yf), ptr(gf),
-                                                      C.byref(p), precision, flags, ptr(gx), ptr(gom), ptr(gw), ptr(ws),
-                                                      ws_bytes, stream_ptr(x.device)), "deform_conv_fused_backward")
+                                                      C.byref(p), precision, flags, None, ptr(gx), ptr(gom), ptr(gw),
+                                                      ptr(ws), ws_bytes, stream_ptr(x.device)), "deform_conv_fused_backward")
     return gx, gom, gw
 
 

@@ -31,7 +31,7 @@ extern "C" {
 #define D2B_EWORKSPACE (-2)  /* workspace too small */
 #define D2B_EUNSUPPORTED (-3)
 
-#define D2B_ABI_VERSION 2
+#define D2B_ABI_VERSION 3
 int d2b_abi_version(void);
 /* compile-time facts, replaces detectron2._C.get_cuda_version / has_cuda (csrc/vision.cpp:23-49,86-88) */
 int d2b_cuda_version(void);
@@ -215,19 +215,25 @@ typedef struct {
 #define D2B_DCN_X_NHWC 1
 int d2b_deform_conv_tc_shape_supported(const d2b_dcn_params* p, int backward);
 size_t d2b_deform_conv_forward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags);
+/* Saved columns (training).  `cols` (optional, d2b_deform_conv_cols_bytes() bytes, 16-byte aligned, tensor-core precisions
+ * only) receives the sampled columns the forward builds anyway -- bf16 hi [| lo] tiles in the tensor core's operand layout;
+ * handed to the backward, the weight-gradient kernel streams them back instead of sampling x a second time (the reference
+ * re-runs deformable_im2col in deform_conv_backward_parameters, deform_conv_cuda.cu:586-610).  The buffer is opaque and only
+ * valid for the same params / precision.  d2b_deform_conv_cols_bytes returns 0 when the shape has no tensor-core path. */
+size_t d2b_deform_conv_cols_bytes(const d2b_dcn_params* p, int precision);
 int d2b_deform_conv_forward(const float* x, const float* offset, const float* mask,
                             const float* weight, const float* bias, const d2b_dcn_params* p,
-                            int precision, int flags, float* out, void* workspace, size_t workspace_bytes,
-                            void* stream);
+                            int precision, int flags, float* out, void* cols, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* Backward.  Any of the grad outputs may be NULL to skip it.  Outputs are fully written (zero-filled inside, then
  * accumulated); need_data = any of grad_x / grad_offset / grad_mask, need_weight = grad_weight. */
 size_t d2b_deform_conv_backward_workspace_bytes(const d2b_dcn_params* p, int precision, int flags, int need_data,
                                                 int need_weight);
 int d2b_deform_conv_backward(const float* x, const float* offset, const float* mask,
                              const float* weight, const float* grad_out, const d2b_dcn_params* p,
-                             int precision, int flags, float* grad_x, float* grad_offset, float* grad_mask,
-                             float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             int precision, int flags, const void* cols, float* grad_x, float* grad_offset,
+                             float* grad_mask, float* grad_weight, float* grad_bias, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* conv2 of a DeformBottleneckBlock fused (detectron2/modeling/backbone/resnet.py:305-318): `offset_mask`
  * [N, 3*DG*kh*kw, Ho, Wo] is the raw conv2_offset output (chunk / cat / sigmoid of :307-311 applied while the sampling taps
@@ -237,11 +243,11 @@ int d2b_deform_conv_backward(const float* x, const float* offset, const float* m
  * the fused offset_mask tensor (mask part through the sigmoid). */
 int d2b_deform_conv_fused_forward(const float* x, const float* offset_mask, const float* weight, const float* scale,
                                   const float* shift, int relu, const d2b_dcn_params* p, int precision, int flags,
-                                  float* out, void* workspace, size_t workspace_bytes, void* stream);
+                                  float* out, void* cols, void* workspace, size_t workspace_bytes, void* stream);
 int d2b_deform_conv_fused_backward(const float* x, const float* offset_mask, const float* weight, const float* scale,
                                    int relu, const float* y, const float* grad_out, const d2b_dcn_params* p,
-                                   int precision, int flags, float* grad_x, float* grad_offset_mask, float* grad_weight,
-                                   void* workspace, size_t workspace_bytes, void* stream);
+                                   int precision, int flags, const void* cols, float* grad_x, float* grad_offset_mask,
+                                   float* grad_weight, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- paste_masks_in_image ---------------------------------------------------------------
  * Replaces detectron2/layers/mask_ops.py:74-147 (GPU branch: every pixel of the image for every mask).

@@ -774,6 +774,52 @@ def test_deform_conv_tensor_core_backward_vs_oracle(cin, cout, h, w, grp, dg, mo
             assert err <= tol * scale + 1e-5, (name, cl, err, scale)
         if cl:
             assert gs[0].is_contiguous(memory_format=torch.channels_last)
+    # training pair: the forward keeps a channels-last copy of x and its sampled columns; the weight gradient that streams
+    # the columns back must match the oracle like the re-sampling kernel does
+    bias = torch.randn(cout, generator=g) if mod else None
+    y, xs, cols = ops.deform_conv_train_op(dev(x), dev(off), dev(mask), dev(wt), dev(bias), [stride, stride], [p, p], [1, 1],
+                                           grp, dg, prec)
+    yref = orc.deform_conv_forward(x, off, mask, wt, bias, stride, p, 1, grp, dg)
+    assert (y.cpu() - yref).abs().max().item() <= (1e-4 if prec == 1 else 2e-2) * yref.abs().max().item()
+    assert xs.numel() == x.numel() and xs.is_contiguous(memory_format=torch.channels_last)
+    assert cols.numel() == _C.lib().d2b_deform_conv_cols_bytes(C.byref(prm), prec) > 0
+    gs = ops.deform_conv_backward_op(xs, dev(off), dev(mask), dev(wt), dev(go), [stride, stride], [p, p], [1, 1], grp, dg,
+                                     mod, True, True, prec, cols)
+    for name, a, r in zip(["gx", "goff", "gmask", "gw", "gb"], gs, gref):
+        if r is None or a.numel() == 0:
+            continue
+        scale = r.abs().max().item() + 1e-6
+        err = (a.cpu() - r).abs().max().item()
+        assert err <= tol * scale + 1e-5, ("saved columns", name, err, scale)
+    with pytest.raises(RuntimeError):
+        ops.deform_conv_backward_op(xs, dev(off), dev(mask), dev(wt), dev(go), [stride, stride], [p, p], [1, 1], grp, dg,
+                                    mod, True, True, prec, cols[:-16])
+
+
+@pytest.mark.parametrize("cin,grp,h,w,mod", [(128, 1, 25, 42, False), (512, 1, 7, 9, True), (512, 32, 13, 17, False),
+                                             (64, 1, 12, 20, True), (48, 1, 8, 8, False)])
+def test_deform_conv_layer_autograd_saved_columns(L, cin, grp, h, w, mod):
+    # layers.deform_conv / modulated_deform_conv under autograd run the training op (saved channels-last x + columns); all
+    # gradients against the oracle.  512 ch: two output-channel tiles (only one saves), 7x9: k-split forward, 48 ch: FFMA path.
+    g = torch.Generator().manual_seed(cin + h)
+    n = 2
+    x = torch.randn(n, cin, h, w, generator=g)
+    off = torch.randn(n, 18, h, w, generator=g) * 2
+    mask = torch.sigmoid(torch.randn(n, 9, h, w, generator=g)) if mod else None
+    wt = torch.randn(cin, cin // grp, 3, 3, generator=g) * (1.0 / math.sqrt(cin // grp * 9))
+    go = torch.randn(n, cin, h, w, generator=g)
+    gref = orc.deform_conv_backward(x, off, mask, wt, go, 1, 1, 1, grp, 1, False)
+    xd, od, wd = [t.to(DEV).requires_grad_(True) for t in (x, off, wt)]
+    md = mask.to(DEV).requires_grad_(True) if mod else None
+    y = L.modulated_deform_conv(xd, od, md, wd, None, 1, 1, 1, grp, 1) if mod else L.deform_conv(xd, od, wd, 1, 1, 1, grp, 1)
+    y.backward(go.to(DEV))
+    got = [xd.grad, od.grad, md.grad if mod else None, wd.grad]
+    for name, a, r in zip(["gx", "goff", "gmask", "gw"], got, gref):
+        if r is None:
+            continue
+        scale = r.abs().max().item() + 1e-6
+        err = (a.cpu() - r).abs().max().item()
+        assert err <= 1e-4 * scale + 1e-5, (name, err, scale)
 
 
 @pytest.mark.parametrize("c,co,h,w,grp,dg,stride,use_scale,relu", [(64, 64, 12, 20, 1, 1, 1, True, True),

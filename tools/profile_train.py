@@ -35,8 +35,7 @@ def main():
             r.pool_bwd(d, "mask", rm, True)
         if "dconv" in what:
             for si in range(3):
-                r.dconv_fwd(d, si, 0)
-                r.dconv_bwd(d, si, 0)
+                r.dconv_bwd(d, si, 0, r.dconv_fwd(d, si, 0))
         torch.cuda.synchronize()
     print("done")
 
