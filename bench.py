@@ -238,10 +238,12 @@ class TrainRunner:
                 outs["dc"].append((saved[0], self.dconv_bwd(d, si, li, saved)))
         return outs
 
-    KERNELS_PER_STEP = (2 * 8            # NMS: iota, coord_range, class_of_rank, segments, gather, mask, scan, compact (CUB sorts are library code)
+    # our own kernels per step (torch's add / cat / fill / memset launches not counted; tools/kernel_times.py lists them all)
+    KERNELS_PER_STEP = (2 * 3            # NMS: rank, mask, scan (+ compaction in the last CTA)
                         + 1 + 2          # pyramid layout change, channels-last pooler forward per head
-                        + 2 + 1          # channels-last pooler backward per head, gradient layout change back to NCHW
-                        + 13 * (3 + 7))  # deform conv: fwd (layout, weight tiles, K1); bwd (layout, 2 x gout tiles, W^T tiles, K2, layout back, K3)
+                        + 2 * 2 + 1      # per head: zero fill + channels-last pooler backward; gradient layout change back to NCHW
+                        + 13 * (3 + 6))  # deform conv fwd: layout, weight tiles, K1 (saves x channels-last + its columns);
+    #                                      bwd: zero fill, grad_out tiles, W^T tiles, K2, K3 from the saved columns, weight-gradient re-layout
 
     def step_autograd(self, d):
         """Public API + torch.autograd: what a training loop runs.  Returns a small result vector (checksums)."""
@@ -737,11 +739,13 @@ def main():
         "validation": validation,
         "l2": "two input sets rotate (2 x 183 MB of feature maps) and every step writes 183 MB of gradients: > 126 MB L2",
         "roofline": {"kernel": "deform-conv backward, R50 res3 layer (2 x 128 x 100 x 168): dcn_bwd_data_tc_kernel + "
-                               "dcn_bwd_weight_tc_kernel (+ their operand pre-tiling / layout launches)",
+                               "dcn_bwd_weight_cols_kernel (+ their operand pre-tiling / zero-fill / re-layout launches)",
                      "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                      "peak_source": src + ", sustained bf16", "algorithmic_flops": flops_bwd, "avg_launch_ms": bwd_ms,
-                     "note": "bf16x3 issues 3 MMAs per algorithmic product (fp32-class accuracy); the kernels are bound by the L2 "
-                             "gather / red.v4 scatter around the contraction, see DESIGN.md section 4",
+                     "note": "bf16x3 issues 3 MMAs per algorithmic product (fp32-class accuracy); the data-gradient kernel is bound "
+                             "by the L2 vector reductions of its scatter (4 corners x 16 B per 4 channels and kernel point: %.0f MB "
+                             "per launch against the 5.9 TB/s red.v4 ceiling of profiles/r2_microbench.txt), see DESIGN.md section 4"
+                             % (IMGS_PER_GPU * h * w * 9 * c * 16 / 1e6),
                      "algorithmic_bytes": dconv_bwd_algorithmic_bytes(c, h, w, IMGS_PER_GPU),
                      "achieved_hbm_gbs": gbs(dconv_bwd_algorithmic_bytes(c, h, w, IMGS_PER_GPU), bwd_ms),
                      "traffic": None},

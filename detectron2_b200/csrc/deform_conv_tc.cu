@@ -770,6 +770,71 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_data_tc_kernel(const floa
   }
 }
 
+// ================================================================================================ weight-gradient epilogue
+// The accumulator tile of a K3 CTA is [128 k' rows][BN oc]; in the weight tensor [Cout][Cin/G][KK] one unit's 64 rows are
+// 36 bytes apart (one kernel point of 64 channels), so writing it directly costs one 32-byte sector atomic per ELEMENT and
+// per pixel split.  Instead every CTA adds its tile with 16-byte vector reductions (64-byte row segments) into the zero-filled
+// staging matrix `part` [SG][MC*128][ops], and a small second kernel moves it into the weight tensor's layout.
+__device__ __forceinline__ void gw_tile_store(uint32_t tmem_base, int quad, int cgrp, int lane, int BN,
+                                              float* __restrict__ tile, int pitch) {
+  float* __restrict__ prow = tile + (size_t)(quad * 32 + lane) * pitch;
+  for (int c16 = cgrp; c16 * 16 < BN; c16 += kWorkerWarps / 4) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      red_add_v4(prow + c16 * 16 + i * 4, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+  }
+}
+
+// one thread per (super-group, unit row, oc of the super-group); oc fastest: the reads of `part` are coalesced
+__global__ void dcn_gw_reduce_kernel(const float* __restrict__ part, const TC d, float* __restrict__ gw) {
+  const long long total = (long long)d.SG * d.U * 64 * d.ops;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ocl = (int)(idx % d.ops);
+  const long long r = idx / d.ops;
+  const int rowu = (int)(r % ((long long)d.U * 64)), sg = (int)(r / ((long long)d.U * 64));
+  const int u = rowu >> 6, ch = rowu & 63;
+  const int kp = u / d.cbs, cb = u - kp * d.cbs;
+  const int ec = sg * d.cps + cb * 64 + ch, egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
+  const int oc = sg * d.ops + ocl;
+  if (oc / d.opg != egrp) return;  // block-diagonal padding of a packed super-group
+  gw[((size_t)oc * d.cpg + ecin) * d.KK + kp] = __ldg(part + ((size_t)sg * d.MC * 128 + rowu) * d.ops + ocl);
+}
+
+// The same sum with coalesced writes for small kernels (KK <= 9): one block owns (super-group, 16 channels, 16 output
+// channels), stages the KK x 16 x 16 sums in shared memory and writes, per output channel, the run of 16 * KK floats that the
+// block's channels occupy in the weight tensor.
+constexpr int kRedOc = 16, kRedCh = 16;
+__global__ void __launch_bounds__(256) dcn_gw_reduce_tile_kernel(const float* __restrict__ part, const TC d,
+                                                                  float* __restrict__ gw) {
+  __shared__ float tile[9 * kRedCh][kRedOc + 1];
+  const int per_sg = d.cps / kRedCh;
+  const int sg = blockIdx.x / per_sg, c0 = (blockIdx.x - sg * per_sg) * kRedCh;  // first channel inside the super-group
+  const int cb = c0 >> 6, ch0 = c0 & 63;
+  const int ocl0 = blockIdx.y * kRedOc;
+  const int tid = threadIdx.x;
+  {
+    const int j = tid & (kRedOc - 1), r0 = tid / kRedOc;  // 16 rows per pass
+    for (int row = r0; row < d.KK * kRedCh; row += 256 / kRedOc) {
+      const int kp = row / kRedCh, ch = row - kp * kRedCh;
+      tile[row][j] = __ldg(part + ((size_t)sg * d.MC * 128 + (size_t)(kp * d.cbs + cb) * 64 + ch0 + ch) * d.ops + ocl0 + j);
+    }
+  }
+  __syncthreads();
+  const int ec0 = sg * d.cps + c0;
+  for (int i = tid; i < kRedOc * kRedCh * d.KK; i += 256) {
+    const int j = i / (kRedCh * d.KK), e = i - j * (kRedCh * d.KK);
+    const int ch = e / d.KK, kp = e - ch * d.KK;
+    const int oc = sg * d.ops + ocl0 + j, grp = oc / d.opg;
+    const int ec = ec0 + ch;
+    if (ec / d.cpg == grp) gw[((size_t)oc * d.cpg + (ec - grp * d.cpg)) * d.KK + kp] = tile[kp * kRedCh + ch][j];
+  }
+}
+
 // ================================================================================================ K3: backward weight
 // grid (M blocks = pairs of units, pixel splits, SG * oc tiles).  D[128 k'][BN oc] += col^T[128 k'][64 px] . gout[64 px][BN oc]
 // per 64-pixel stage; the gathered tile is written [unit half][pixel][64 ch] = MN-major for the tensor core.
@@ -874,28 +939,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
     }
-    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> red.add into gW
+    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> this split's partial tile
     mbar_wait(accum_bar, 0u);
     tc_fence_after();
     const int quad = warp & 3, cgrp = warp >> 2;
-    const int row = quad * 32 + lane;
-    const int eu = 2 * mb + (row >> 6);
-    const bool row_ok = eu < d.U;
-    const int ekp = row_ok ? eu / d.cbs : 0;
-    const int ec = sg * d.cps + (row_ok ? eu - ekp * d.cbs : 0) * 64 + (row & 63);  // global input channel
-    const int egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
-    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += kWorkerWarps / 4) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int oc = sg * d.ops + oct * k.BN + c16 * 16 + i;
-          if (oc / d.opg == egrp) red_add(gw + ((size_t)oc * d.cpg + ecin) * d.KK + ekp, __uint_as_float(r[i]));
-        }
-      }
-    }
+    gw_tile_store(tmem_base, quad, cgrp, lane, k.BN,
+                  gw + ((size_t)sg * d.MC * 128 + (size_t)mb * 128) * d.ops + (size_t)oct * k.BN,
+                  d.ops);
   } else if (warp == kWorkerWarps) {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(split ? 2 : 1) * (uint32_t)k.BN * 128u;
@@ -946,6 +996,9 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_tc_kernel(const fl
 // Same grid, tiles and epilogue as K3, but the A operand is streamed back from the column tiles the forward saved
 // (dcn_fwd_tc_kernel's saver warp) instead of being sampled from x again: a pure TMA -> tcgen05 pipeline.  A 64-pixel stage of
 // a unit is one contiguous 8 KB half of its [128 px][64 ch] tile (the 128-byte swizzle repeats every 8 rows).
+// (Measured: multicasting the shared grad_out tile over clusters of 2 along the macro-chunk axis changes nothing -- the kernel
+// is bound by the three tcgen05 passes of the bf16x3 split and the column stream, not by L2 reads -- and clusters of 3 / 6 do
+// not fit the one-wave grid, 135 / 132 resident CTAs; the kernel therefore runs without clusters.)
 template <int kTmemCols>
 __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_cols_kernel(const uint8_t* __restrict__ cols,
                                                                           const uint8_t* __restrict__ gt, const TC d,
@@ -989,28 +1042,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_bwd_weight_cols_kernel(const 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kWorkerWarps) {
-    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> red.add into gW
+    // =============================================================== EPILOGUE: TMEM [k' row][oc col] -> this split's partial tile
     mbar_wait(accum_bar, 0u);
     tc_fence_after();
     const int quad = warp & 3, cgrp = warp >> 2;
-    const int row = quad * 32 + lane;
-    const int eu = 2 * mb + (row >> 6);
-    const bool row_ok = eu < d.U;
-    const int ekp = row_ok ? eu / d.cbs : 0;
-    const int ec = sg * d.cps + (row_ok ? eu - ekp * d.cbs : 0) * 64 + (row & 63);  // global input channel
-    const int egrp = ec / d.cpg, ecin = ec - egrp * d.cpg;
-    for (int c16 = cgrp; c16 * 16 < k.BN; c16 += kWorkerWarps / 4) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c16 * 16), r);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int oc = sg * d.ops + oct * k.BN + c16 * 16 + i;
-          if (oc / d.opg == egrp) red_add(gw + ((size_t)oc * d.cpg + ecin) * d.KK + ekp, __uint_as_float(r[i]));
-        }
-      }
-    }
+    gw_tile_store(tmem_base, quad, cgrp, lane, k.BN,
+                  gw + ((size_t)sg * d.MC * 128 + (size_t)mb * 128) * d.ops + (size_t)oct * k.BN,
+                  d.ops);
   } else if (warp == kWorkerWarps) {
     // =============================================================== TMA producer: column halves + grad_out tile per stage
     if (lane == 0) {
@@ -1377,7 +1415,10 @@ size_t d2b_deform_conv_tc_bwd_workspace(const d2b_dcn_params* p, int x_nhwc, int
     b += align256((size_t)d.N * d.tiles_img * d.SG * d.nks * 2 * kTile);  // gout, pixel-row tiles
     b += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);               // W^T tiles
   }
-  if (need_weight) b += align256((size_t)d.N * d.stages_img * d.SG * k3.noct * 2 * k3.BN * 128);  // gout, oc-row tiles
+  if (need_weight) {
+    b += align256((size_t)d.N * d.stages_img * d.SG * k3.noct * 2 * k3.BN * 128);  // gout, oc-row tiles
+    b += align256(sizeof(float) * (size_t)d.SG * d.MC * 128 * d.ops);  // weight gradient in the accumulator tiles' layout
+  }
   return b;
 }
 
@@ -1428,12 +1469,6 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
   }
   float* gxh = nullptr;
   if (need_data && grad_x) gxh = x_nhwc ? grad_x : reinterpret_cast<float*>(ws);
-  {  // every accumulated output of the call zero-filled by one launch (grad_mask of the fused layout lives inside grad_offset)
-    void* zp[4] = {grad_offset, fused_om ? nullptr : grad_mask, grad_weight, gxh};
-    size_t zb[4] = {noff * 4, nm * 4, nw * 4, nx * 4};
-    int rc = d2b_zero_buffers(zp, zb, 4, stream);
-    if (rc) return rc;
-  }
   uint8_t* gt_px = nullptr;
   uint8_t* wt = nullptr;
   if (need_data) {
@@ -1444,6 +1479,18 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
     ws += align256((size_t)d.SG * d.MC * d.nks * 2 * kTile);
   }
   uint8_t* gt_oc = need_weight ? ws : nullptr;
+  float* gw_part = nullptr;
+  if (need_weight) {
+    ws += align256((size_t)d.N * d.stages_img * d.SG * k3.noct * 2 * k3.BN * 128);
+    gw_part = reinterpret_cast<float*>(ws);
+  }
+  {  // every accumulated output of the call zero-filled by one launch (grad_mask of the fused layout lives inside grad_offset;
+    // grad_weight is accumulated in the staging matrix and then written element by element)
+    void* zp[4] = {grad_offset, fused_om ? nullptr : grad_mask, gxh, gw_part};
+    size_t zb[4] = {noff * 4, nm * 4, nx * 4, sizeof(float) * (size_t)d.SG * d.MC * 128 * d.ops};
+    int rc = d2b_zero_buffers(zp, zb, 4, stream);
+    if (rc) return rc;
+  }
   if (need_data) {
     // grad_out is read once: pixel-row tiles for K2 and (when the weight gradient is wanted too) channel-row tiles for K3
     dcn_gout_px_tiles_kernel<<<dim3((unsigned)((size_t)d.N * d.tiles_img * d.SG * d.nks), 4), 256, 0, stream>>>(
@@ -1481,7 +1528,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
 #define D2B_LAUNCH_K3C(COLS)                                                                                             \
   {                                                                                                                      \
     D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_cols_kernel<COLS>);                                                                \
-    dcn_bwd_weight_cols_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(cl, gt_oc, d, k3, S, split, grad_weight);   \
+    dcn_bwd_weight_cols_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(cl, gt_oc, d, k3, S, split, gw_part);       \
   }
       if (tcols <= 32) D2B_LAUNCH_K3C(32)
       else if (tcols == 64) D2B_LAUNCH_K3C(64)
@@ -1493,7 +1540,7 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
 #define D2B_LAUNCH_K3(COLS)                                                                                              \
   {                                                                                                                      \
     D2B_ALLOW_BIG_SMEM(dcn_bwd_weight_tc_kernel<COLS>);                                                                  \
-    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_oc, d, k3, split, grad_weight); \
+    dcn_bwd_weight_tc_kernel<COLS><<<grid, kThreads, smem_bytes, stream>>>(xh, offset, mask, gt_oc, d, k3, split, gw_part); \
   }
       if (tcols <= 32) D2B_LAUNCH_K3(32)
       else if (tcols == 64) D2B_LAUNCH_K3(64)
@@ -1502,6 +1549,15 @@ int d2b_deform_conv_backward_tc(const float* x, const float* offset, const float
 #undef D2B_LAUNCH_K3
     }
     D2B_CHECK_LAUNCH();
+    {
+      if (d.KK <= 9) {  // d.ops is a multiple of 16 (shape gate)
+        dcn_gw_reduce_tile_kernel<<<dim3(d.SG * (d.cps / kRedCh), d.ops / kRedOc), 256, 0, stream>>>(gw_part, d, grad_weight);
+      } else {
+        const long long total = (long long)d.SG * d.U * 64 * d.ops;
+        dcn_gw_reduce_kernel<<<d2b_cdiv(total, 256), 256, 0, stream>>>(gw_part, d, grad_weight);
+      }
+      D2B_CHECK_LAUNCH();
+    }
   }
   return D2B_OK;
 }

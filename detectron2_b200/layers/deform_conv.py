@@ -152,6 +152,6 @@ class DeformBottleneckConv2(nn.Module):
         self.norm_shift.copy_(bias - running_mean * scale)
 
     def forward(self, x, offset_mask):
-        return ops.deform_conv_fused_op(x, offset_mask, self.weight, self.norm_scale, self.norm_shift, self.relu,
-                                        list(self.stride), list(self.padding), list(self.dilation), self.groups,
-                                        self.deformable_groups, DEFAULT_PRECISION if DEFAULT_PRECISION != 0 else 1)
+        return ops.deform_conv_fused(x, offset_mask, self.weight, self.norm_scale, self.norm_shift, self.relu,
+                                     list(self.stride), list(self.padding), list(self.dilation), self.groups,
+                                     self.deformable_groups, DEFAULT_PRECISION if DEFAULT_PRECISION != 0 else 1)

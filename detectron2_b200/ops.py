@@ -735,8 +735,8 @@ def _(x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, gro
 def deform_conv_fused_backward_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor], relu: bool,
                                   y: Tensor, grad_out: Tensor, stride: List[int], padding: List[int],
                                   dilation: List[int], groups: int, deformable_groups: int,
-                                  precision: int) -> Tuple[Tensor, Tensor, Tensor]:
-    _C.require_cuda(x, offset_mask, weight, scale, y, grad_out)
+                                  precision: int, cols: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    _C.require_cuda(x, offset_mask, weight, scale, y, grad_out, cols)
     om, wf, sc, yf, gf = _f32c(offset_mask), _f32c(weight), _f32c(scale), _f32c(y), _f32c(grad_out)
     p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
     if not _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(p), 1):
@@ -745,15 +745,18 @@ def deform_conv_fused_backward_op(x: Tensor, offset_mask: Tensor, weight: Tensor
     gx, gom, gw = torch.empty_like(xf), torch.empty_like(om), torch.empty_like(wf)
     ws_bytes = _C.lib().d2b_deform_conv_backward_workspace_bytes(C.byref(p), 1, flags, 1, 1)
     ws = _ws(ws_bytes, x.device)
+    if cols is not None and cols.numel() != _C.lib().d2b_deform_conv_cols_bytes(C.byref(p), precision):
+        raise RuntimeError("deform_conv_fused_backward: `cols` does not belong to this shape / precision")
     with torch.cuda.device(x.device):
         check(_C.lib().d2b_deform_conv_fused_backward(ptr(xf), ptr(om), ptr(wf), ptr(sc), int(relu), ptr(yf), ptr(gf),
-                                                      C.byref(p), precision, flags, None, ptr(gx), ptr(gom), ptr(gw),
+                                                      C.byref(p), precision, flags, ptr(cols), ptr(gx), ptr(gom), ptr(gw),
                                                       ptr(ws), ws_bytes, stream_ptr(x.device)), "deform_conv_fused_backward")
     return gx, gom, gw
 
 
 @deform_conv_fused_backward_op.register_fake
-def _(x, offset_mask, weight, scale, relu, y, grad_out, stride, padding, dilation, groups, deformable_groups, precision):
+def _(x, offset_mask, weight, scale, relu, y, grad_out, stride, padding, dilation, groups, deformable_groups, precision,
+      cols=None):
     return torch.empty_like(x), torch.empty_like(offset_mask), torch.empty_like(weight)
 
 
@@ -774,6 +777,72 @@ def _dcnf_bwd(ctx, grad):
 
 
 deform_conv_fused_op.register_autograd(_dcnf_bwd, setup_context=_dcnf_setup)
+
+
+@torch.library.custom_op("d2b200::deform_conv_fused_train", mutates_args=(), device_types="cuda")
+def deform_conv_fused_train_op(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor],
+                               shift: Optional[Tensor], relu: bool, stride: List[int], padding: List[int],
+                               dilation: List[int], groups: int, deformable_groups: int,
+                               precision: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """deform_conv_fused for a step that will be differentiated: (y, x_saved, cols) like deform_conv_train."""
+    _C.require_cuda(x, offset_mask, weight, scale, shift)
+    kh, kw = weight.shape[2:]
+    n, cout, ho, wo = dcn_output_shape(x, weight, stride, padding, dilation)
+    if tuple(offset_mask.shape) != (n, 3 * deformable_groups * kh * kw, ho, wo):
+        raise RuntimeError("invalid shape of offset_mask: got %s, expected %s" %
+                           (tuple(offset_mask.shape), (n, 3 * deformable_groups * kh * kw, ho, wo)))
+    om, wf, sc, sh = _f32c(offset_mask), _f32c(weight), _f32c(scale), _f32c(shift)
+    p = _dcn_params(x, wf, stride, padding, dilation, groups, deformable_groups)
+    if precision == 0 or not _C.lib().d2b_deform_conv_tc_shape_supported(C.byref(p), 0):
+        raise RuntimeError("deform_conv_fused: the tensor-core kernels do not take this shape / precision")
+    prec = 1 if precision == -1 else precision
+    xk, flags, xs, cols = _dcn_train_layout(x, p, prec)
+    out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+    ws_bytes = _C.lib().d2b_deform_conv_forward_workspace_bytes(C.byref(p), 1, flags)
+    ws = _ws(ws_bytes, x.device)
+    with torch.cuda.device(x.device):
+        check(_C.lib().d2b_deform_conv_fused_forward(ptr(xk), ptr(om), ptr(wf), ptr(sc), ptr(sh), int(relu), C.byref(p),
+                                                     prec, flags, ptr(out), ptr(cols), ptr(ws), ws_bytes,
+                                                     stream_ptr(x.device)),
+              "deform_conv_fused_forward")
+    e = lambda dt: torch.empty((0,), dtype=dt, device=x.device)  # noqa: E731
+    return out.to(x.dtype), xs if xs is not None else e(torch.float32), cols if cols is not None else e(torch.uint8)
+
+
+@deform_conv_fused_train_op.register_fake
+def _(x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups, deformable_groups, precision):
+    return (x.new_empty(dcn_output_shape(x, weight, stride, padding, dilation)), x.new_empty((0,), dtype=torch.float32),
+            x.new_empty((0,), dtype=torch.uint8))
+
+
+def _dcnft_setup(ctx, inputs, output):
+    x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups, dg, precision = inputs
+    y, xs, cols = output
+    ctx.save_for_backward(x if xs.numel() == 0 else xs, offset_mask, weight, scale, y, cols)
+    ctx.args = (relu, stride, padding, dilation, groups, dg, 1 if precision == -1 else precision, x.dtype)
+
+
+def _dcnft_bwd(ctx, grad, _gxs, _gcols):
+    x, offset_mask, weight, scale, y, cols = ctx.saved_tensors
+    relu, stride, padding, dilation, groups, dg, precision, xdtype = ctx.args
+    gx, gom, gw = deform_conv_fused_backward_op(x, offset_mask, weight, scale, relu, y, grad, stride, padding, dilation,
+                                                groups, dg, precision, cols if cols.numel() else None)
+    return (gx.to(xdtype), gom.to(offset_mask.dtype), gw.to(weight.dtype), None, None, None, None, None, None, None, None,
+            None)
+
+
+deform_conv_fused_train_op.register_autograd(_dcnft_bwd, setup_context=_dcnft_setup)
+
+
+def deform_conv_fused(x: Tensor, offset_mask: Tensor, weight: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+                      relu: bool, stride: List[int], padding: List[int], dilation: List[int], groups: int,
+                      deformable_groups: int, precision: int) -> Tensor:
+    """The entry DeformBottleneckConv2 calls: the training op when a gradient can flow, the plain forward otherwise."""
+    if torch.is_grad_enabled() and (x.requires_grad or offset_mask.requires_grad or weight.requires_grad):
+        return deform_conv_fused_train_op(x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups,
+                                          deformable_groups, precision)[0]
+    return deform_conv_fused_op(x, offset_mask, weight, scale, shift, relu, stride, padding, dilation, groups,
+                                deformable_groups, precision)
 
 
 # =================================================================================== paste masks

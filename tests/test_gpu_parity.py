@@ -873,6 +873,14 @@ def test_deform_bottleneck_conv2_fused_vs_unfused(L, c, co, h, w, grp, dg, strid
         if use_scale:
             mod.norm_scale.copy_(scale)
     assert torch.allclose(mod(x.to(DEV), om.to(DEV)), y.detach(), rtol=1e-5, atol=1e-5)
+    # the module under autograd runs the training op (saved channels-last x + columns): same gradients
+    xm, omm = x.to(DEV).requires_grad_(True), om.to(DEV).requires_grad_(True)
+    ym = mod(xm, omm)
+    assert torch.allclose(ym.detach(), y.detach(), rtol=1e-5, atol=1e-5)
+    ym.backward(go.to(DEV))
+    for name, t, r in (("gx", xm.grad, xu.grad), ("gom", omm.grad, omu.grad), ("gw", mod.weight.grad, wu.grad)):
+        e = (t - r).abs().max().item()
+        assert e <= 2e-4 * r.abs().max().item() + 1e-5, ("module", name, e)
 
 
 def test_deform_conv_tensor_core_unsupported_shape_is_loud():

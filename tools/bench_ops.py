@@ -214,6 +214,12 @@ def main():
             rc = refgpu.get("deform_conv fwd C=%d %dx%d g=%d" % (cin, hh, ww, grp))
             add("deform_conv fwd C=%d %dx%d g=%d (%s)" % (cin, hh, ww, grp, tag), t, tr,
                 "%.2f TFLOP/s; reference csrc CUDA: %s us" % (flops / t / 1e6, ("%.1f" % rc) if rc else "n/a"))
+        try:  # the training forward: also lays x out channels-last once and keeps its sampled columns for the backward
+            t = timeit(lambda: _ops.deform_conv_train_op(xx, off, None, wt, None, [1, 1], [1, 1], [1, 1], grp, 1, 1), rep=10, warm=2)
+            add("deform_conv fwd C=%d %dx%d g=%d (bf16x3 tcgen05, training: saves columns)" % (cin, hh, ww, grp), t, tr,
+                "%.2f TFLOP/s" % (flops / t / 1e6))
+        except RuntimeError:
+            pass
         xg, og, wg = xx.clone().requires_grad_(True), off.clone().requires_grad_(True), wt.clone().requires_grad_(True)
         y = L.deform_conv(xg, og, wg, 1, 1, 1, grp, 1)
         go = torch.randn_like(y)
