@@ -23,7 +23,8 @@ class DcnParams(C.Structure):
 
 
 MAX_LEVELS = 8
-ABI_VERSION = 3  # include/d2b200.h D2B_ABI_VERSION
+MAX_IMAGES = 64  # D2B_MAX_IMAGES
+ABI_VERSION = 4  # include/d2b200.h D2B_ABI_VERSION
 DCN_X_NHWC = 1   # D2B_DCN_X_NHWC
 
 
@@ -31,12 +32,18 @@ class Pyramid(C.Structure):
     _fields_ = [("num_levels", C.c_int), ("feat", C.c_void_p * MAX_LEVELS), ("grad", C.c_void_p * MAX_LEVELS),
                 ("H", C.c_int * MAX_LEVELS), ("W", C.c_int * MAX_LEVELS), ("scale", C.c_float * MAX_LEVELS),
                 ("min_level", C.c_int), ("max_level", C.c_int), ("canonical_level", C.c_int),
-                ("canonical_box_size", C.c_float)]
+                ("canonical_box_size", C.c_float), ("level_rois", C.c_void_p)]
 
 
 class RpnLevels(C.Structure):
     _fields_ = [("num_levels", C.c_int), ("proposals", C.c_void_p * MAX_LEVELS), ("topk_idx", C.c_void_p * MAX_LEVELS),
                 ("topk_scores", C.c_void_p * MAX_LEVELS), ("A", C.c_int * MAX_LEVELS), ("k", C.c_int * MAX_LEVELS)]
+
+
+class DenseLevels(C.Structure):
+    _fields_ = [("num_levels", C.c_int), ("anchors", C.c_void_p * MAX_LEVELS), ("deltas", C.c_void_p * MAX_LEVELS),
+                ("topk_idx", C.c_void_p * MAX_LEVELS), ("topk_scores", C.c_void_p * MAX_LEVELS),
+                ("R", C.c_int * MAX_LEVELS), ("k", C.c_int * MAX_LEVELS)]
 
 
 def _declare(lib):
@@ -64,6 +71,10 @@ def _declare(lib):
         "d2b_nms": (i, [f32p, f32p, i64p, i64, d, i, i64, i64p, i64p, vp, sz, vp]),
         "d2b_rpn_prepare": (i, [C.POINTER(RpnLevels), i, f32p, f, i, f32p, f32p, f32p, f32p, i64p, vp, vp]),
         "d2b_rpn_select": (i, [i64p, i64p, i, i, i, f32p, f32p, i64p, f32p, f32p, i64p, i64p, vp]),
+        "d2b_frcnn_prepare": (i, [f32p, f32p, C.POINTER(C.c_int), i, i, i, f32p, f, i, f32p, f32p, f32p, f32p, i64p, i64p,
+                                  i64p, i64p, vp]),
+        "d2b_dense_prepare": (i, [C.POINTER(DenseLevels), i, i, C.POINTER(C.c_float), f, f32p, f32p, f32p, f32p, i64p, i64p,
+                                  vp]),
         "d2b_mask_loss_forward": (i, [f32p, i, i, i, u8p, i, i, i, f32p, i64p, i64p, f32p, u8p, vp]),
         "d2b_mask_loss_backward": (i, [f32p, i, i, i, u8p, i64p, f32p, f32p, vp]),
         "d2b_box_iou_rotated": (i, [f32p, i64, f32p, i64, f32p, vp]),

@@ -199,6 +199,260 @@ D2B_API int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, 
   return D2B_OK;
 }
 
+// ================================================================================================ Fast R-CNN / dense-head candidates
+// The candidate stages of the two inference post-processors that sit on the same NMS, as fixed-capacity
+// kernels with one CTA per image; d2b_rpn_select above then hands every image its first `topk` survivors.
+//
+//   d2b_frcnn_prepare   fast_rcnn_inference_single_image (detectron2/modeling/roi_heads/fast_rcnn.py:117-173) up to the NMS:
+//                       rows with a non-finite box or score are dropped (:137-140), the (row, class) pairs with
+//                       score > score_thresh (:150-154) are written IN ROW-MAJOR ORDER (the order `nonzero()` gives the
+//                       reference; it decides ties inside NMS) by an ordered block compaction -- no nonzero(), no sync --
+//                       with their box clipped to the image (:146-147) and torchvision's batched-NMS coordinate offsets.
+//   d2b_dense_prepare   DenseDetector._decode_per_level_predictions (meta_arch/dense_detector.py:186-235) after the per-level
+//                       top-k: Box2BoxTransform.apply_deltas (box_regression.py:78-116, same fp32 expression order) on the
+//                       selected (anchor, class) pairs only, class ids, coordinate offsets.
+namespace {
+
+struct FrcnnImages {
+  int N;
+  int row_start[D2B_MAX_IMAGES + 1];
+};
+
+__device__ __forceinline__ float block_max(float v, float* s_red, float* s_out) {
+  const int tid = threadIdx.x;
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // s_red reuse
+  if ((tid & 31) == 0) s_red[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    v = s_red[tid];
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (tid == 0) *s_out = v;
+  }
+  __syncthreads();
+  return *s_out;
+}
+
+__global__ void __launch_bounds__(kThreads) frcnn_prepare_kernel(const FrcnnImages I, const float* __restrict__ boxes,
+                                                                 const float* __restrict__ scores, int K, int kreg,
+                                                                 const float* __restrict__ image_hw, float score_thresh, int cap,
+                                                                 float* __restrict__ cand_boxes, float* __restrict__ nms_boxes,
+                                                                 float* __restrict__ nms_scores, float* __restrict__ raw_scores,
+                                                                 long long* __restrict__ cand_flat, long long* __restrict__ cat_ids,
+                                                                 long long* __restrict__ n_cand, long long* __restrict__ row_map) {
+  __shared__ int warp_tot[32];
+  __shared__ float s_red[32];
+  __shared__ float s_max;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int rs = I.row_start[n], R = I.row_start[n + 1] - rs;
+  const float ih = image_hw[2 * n], iw = image_hw[2 * n + 1];
+  const size_t obase = (size_t)n * cap;
+  int have = 0, have_rows = 0;
+  float mx = -INFINITY;
+  for (int r0 = 0; r0 < R; r0 += kThreads) {
+    const int r = r0 + tid;
+    int cnt = 0, valid = 0;
+    const float* __restrict__ srow = scores + (size_t)(rs + (r < R ? r : 0)) * (K + 1);
+    const float* __restrict__ brow = boxes + (size_t)(rs + (r < R ? r : 0)) * kreg * 4;
+    if (r < R) {
+      valid = 1;
+      for (int c = 0; c <= K; ++c) valid &= finitef(srow[c]) ? 1 : 0;
+      for (int c = 0; c < kreg * 4; ++c) valid &= finitef(brow[c]) ? 1 : 0;
+      if (valid)
+        for (int c = 0; c < K; ++c) cnt += srow[c] > score_thresh ? 1 : 0;
+    }
+    int total, total_rows;
+    const int off = have + block_scan(cnt, warp_tot, total);
+    const int vrank = have_rows + block_scan(valid, warp_tot, total_rows);
+    if (r < R) row_map[rs + r] = valid ? vrank : -1;  // index of the row among the valid rows (:138-140)
+    if (cnt) {
+      int pos = off;
+      for (int c = 0; c < K && pos < cap; ++c) {
+        const float sc = srow[c];
+        if (!(sc > score_thresh)) continue;
+        const float* __restrict__ b = brow + (kreg == 1 ? 0 : c * 4);
+        // Boxes.clip: clamp(min=0, max=w / h)
+        const float x1 = fminf(fmaxf(b[0], 0.f), iw), y1 = fminf(fmaxf(b[1], 0.f), ih);
+        const float x2 = fminf(fmaxf(b[2], 0.f), iw), y2 = fminf(fmaxf(b[3], 0.f), ih);
+        *reinterpret_cast<float4*>(cand_boxes + (obase + pos) * 4) = make_float4(x1, y1, x2, y2);
+        raw_scores[obase + pos] = sc;
+        nms_scores[obase + pos] = sc;
+        cand_flat[obase + pos] = (long long)r * K + c;
+        cat_ids[obase + pos] = (long long)n * (K + 1) + c;
+        mx = fmaxf(mx, fmaxf(fmaxf(x1, y1), fmaxf(x2, y2)));
+        ++pos;
+      }
+    }
+    have += total;
+    have_rows += total_rows;
+  }
+  if (tid == 0) n_cand[n] = have;  // > cap: the list was truncated, the caller redoes the image
+  const int live = min(have, cap);
+  mx = block_max(mx, s_red, &s_max);
+  const float scale = (live > 0 ? mx : 0.f) + 1.0f;  // torchvision _batched_nms_coordinate_trick: idxs * (boxes.max() + 1)
+  __threadfence_block();
+  for (int t = tid; t < cap; t += kThreads) {
+    const size_t o = obase + t;
+    if (t < live) {
+      float4 b = *reinterpret_cast<const float4*>(cand_boxes + o * 4);
+      const float offv = (float)(cat_ids[o] - (long long)n * (K + 1)) * scale;
+      b.x += offv;
+      b.y += offv;
+      b.z += offv;
+      b.w += offv;
+      *reinterpret_cast<float4*>(nms_boxes + o * 4) = b;
+    } else {  // dead slot: ignored by the NMS kernels
+      *reinterpret_cast<float4*>(cand_boxes + o * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(nms_boxes + o * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      raw_scores[o] = 0.f;
+      nms_scores[o] = -INFINITY;
+      cand_flat[o] = 0;
+      cat_ids[o] = -1;
+    }
+  }
+}
+
+struct DenseLevels {
+  int L;
+  const float* anchors[D2B_MAX_LEVELS];      // [R_l, 4]
+  const float* deltas[D2B_MAX_LEVELS];       // [N, R_l, 4]
+  const int64_t* topk_idx[D2B_MAX_LEVELS];   // [N, k_l]  flat (anchor * K + class)
+  const float* topk_scores[D2B_MAX_LEVELS];  // [N, k_l]  -inf = dead slot
+  int R[D2B_MAX_LEVELS], k[D2B_MAX_LEVELS], t0[D2B_MAX_LEVELS + 1];
+};
+
+__global__ void __launch_bounds__(kThreads) dense_prepare_kernel(const DenseLevels P, int T, int K, float wx, float wy, float ww,
+                                                                 float wh, float scale_clamp, float* __restrict__ flat_boxes,
+                                                                 float* __restrict__ nms_boxes, float* __restrict__ nms_scores,
+                                                                 float* __restrict__ raw_scores, long long* __restrict__ classes,
+                                                                 long long* __restrict__ cat_ids) {
+  __shared__ float s_red[32];
+  __shared__ int s_redi[32];
+  __shared__ float s_max;
+  __shared__ int s_live;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float mx = -INFINITY;
+  int nlive = 0;
+  for (int t = tid; t < T; t += kThreads) {
+    int l = 0;
+    while (l + 1 < P.L && t >= P.t0[l + 1]) ++l;
+    const int j = t - P.t0[l];
+    const long long f = P.topk_idx[l][(size_t)n * P.k[l] + j];
+    const float s = P.topk_scores[l][(size_t)n * P.k[l] + j];
+    const bool live = s > -INFINITY;
+    const long long a = f / K;
+    const long long cls = f - a * K;
+    const float4 an = *reinterpret_cast<const float4*>(P.anchors[l] + (size_t)a * 4);
+    const float4 d = *reinterpret_cast<const float4*>(P.deltas[l] + ((size_t)n * P.R[l] + a) * 4);
+    // Box2BoxTransform.apply_deltas, op for op (this file is compiled with -fmad=false)
+    const float widths = an.z - an.x, heights = an.w - an.y;
+    const float ctr_x = an.x + 0.5f * widths, ctr_y = an.y + 0.5f * heights;
+    const float dx = d.x / wx, dy = d.y / wy;
+    float dw = d.z / ww, dh = d.w / wh;
+    dw = dw > scale_clamp ? scale_clamp : dw;  // torch.clamp(max=): NaN stays NaN
+    dh = dh > scale_clamp ? scale_clamp : dh;
+    const float pcx = dx * widths + ctr_x, pcy = dy * heights + ctr_y;
+    const float pw = expf(dw) * widths, ph = expf(dh) * heights;
+    const float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
+    const size_t o = (size_t)n * T + t;
+    *reinterpret_cast<float4*>(flat_boxes + o * 4) = make_float4(x1, y1, x2, y2);
+    raw_scores[o] = s;
+    nms_scores[o] = live ? s : -INFINITY;
+    classes[o] = cls;
+    cat_ids[o] = live ? (long long)n * (K + 1) + cls : -1LL;
+    if (live) {
+      mx = fmaxf(mx, fmaxf(fmaxf(x1, y1), fmaxf(x2, y2)));
+      ++nlive;
+    }
+  }
+  for (int o = 16; o; o >>= 1) nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+  if ((tid & 31) == 0) s_redi[tid >> 5] = nlive;
+  mx = block_max(mx, s_red, &s_max);
+  if (tid < 32) {
+    int v = s_redi[tid];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tid == 0) s_live = v;
+  }
+  __syncthreads();
+  // torchvision/ops/boxes.py batched_nms: coordinate trick while the image has at most 100 000 box elements on CUDA
+  const bool trick = (long long)s_live * 4 <= 100000;
+  const float scale = (s_live > 0 ? mx : 0.f) + 1.0f;
+  for (int t = tid; t < T; t += kThreads) {
+    const size_t o = (size_t)n * T + t;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cat_ids[o] >= 0) {
+      b = *reinterpret_cast<const float4*>(flat_boxes + o * 4);
+      if (trick) {
+        const float offv = (float)classes[o] * scale;
+        b.x += offv;
+        b.y += offv;
+        b.z += offv;
+        b.w += offv;
+      }
+    }
+    *reinterpret_cast<float4*>(nms_boxes + o * 4) = b;
+  }
+}
+
+}  // namespace
+
+D2B_API int d2b_frcnn_prepare(const float* boxes, const float* scores, const int* row_start, int N, int num_classes, int kreg,
+                              const float* image_hw, float score_thresh, int cap, float* cand_boxes, float* nms_boxes,
+                              float* nms_scores, float* raw_scores, int64_t* cand_flat, int64_t* cat_ids, int64_t* n_cand,
+                              int64_t* row_map, void* stream) {
+  if (N < 0 || N > D2B_MAX_IMAGES || num_classes <= 0 || (kreg != 1 && kreg != num_classes) || cap < 0 || !row_start)
+    return D2B_EINVAL;
+  if (N == 0) return D2B_OK;
+  FrcnnImages I = {};
+  I.N = N;
+  for (int i = 0; i <= N; ++i) {
+    I.row_start[i] = row_start[i];
+    if (i && row_start[i] < row_start[i - 1]) return D2B_EINVAL;
+  }
+  if (!image_hw || !n_cand) return D2B_EINVAL;
+  if (row_start[N] > row_start[0] && (!boxes || !scores || !row_map)) return D2B_EINVAL;
+  if (cap > 0 && (!cand_boxes || !nms_boxes || !nms_scores || !raw_scores || !cand_flat || !cat_ids)) return D2B_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(cand_boxes) & 15) != 0 || (reinterpret_cast<uintptr_t>(nms_boxes) & 15) != 0) return D2B_EINVAL;
+  frcnn_prepare_kernel<<<N, kThreads, 0, (cudaStream_t)stream>>>(I, boxes, scores, num_classes, kreg, image_hw, score_thresh, cap,
+                                                                 cand_boxes, nms_boxes, nms_scores, raw_scores,
+                                                                 (long long*)cand_flat, (long long*)cat_ids, (long long*)n_cand,
+                                                                 (long long*)row_map);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
+D2B_API int d2b_dense_prepare(const d2b_dense_levels* lv, int N, int num_classes, const float* weights, float scale_clamp,
+                              float* flat_boxes, float* nms_boxes, float* nms_scores, float* raw_scores, int64_t* classes,
+                              int64_t* cat_ids, void* stream) {
+  if (!lv || lv->num_levels < 1 || lv->num_levels > D2B_MAX_LEVELS || N < 0 || num_classes <= 0 || !weights) return D2B_EINVAL;
+  if (N == 0) return D2B_OK;
+  DenseLevels P = {};
+  P.L = lv->num_levels;
+  int T = 0;
+  for (int l = 0; l < P.L; ++l) {
+    if (lv->R[l] < 0 || lv->k[l] < 0) return D2B_EINVAL;
+    if (lv->k[l] > 0 && (!lv->anchors[l] || !lv->deltas[l] || !lv->topk_idx[l] || !lv->topk_scores[l])) return D2B_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(lv->anchors[l]) & 15) != 0 || (reinterpret_cast<uintptr_t>(lv->deltas[l]) & 15) != 0)
+      return D2B_EINVAL;
+    P.anchors[l] = lv->anchors[l];
+    P.deltas[l] = lv->deltas[l];
+    P.topk_idx[l] = lv->topk_idx[l];
+    P.topk_scores[l] = lv->topk_scores[l];
+    P.R[l] = lv->R[l];
+    P.k[l] = lv->k[l];
+    P.t0[l] = T;
+    T += lv->k[l];
+  }
+  P.t0[P.L] = T;
+  if (T == 0) return D2B_OK;
+  if (!flat_boxes || !nms_boxes || !nms_scores || !raw_scores || !classes || !cat_ids) return D2B_EINVAL;
+  dense_prepare_kernel<<<N, kThreads, 0, (cudaStream_t)stream>>>(P, T, num_classes, weights[0], weights[1], weights[2], weights[3],
+                                                                 scale_clamp, flat_boxes, nms_boxes, nms_scores, raw_scores,
+                                                                 (long long*)classes, (long long*)cat_ids);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
+
 // ================================================================================================ mask targets + loss
 // Mask-head training target and loss in one pass:
 //   BitMasks.crop_and_resize (detectron2/structures/masks.py:193-224): RoIAlign(S x S, scale 1, sampling_ratio 0, aligned)

@@ -15,6 +15,7 @@
 //     rotated RoI is not a product grid), threads mapped to (channel, bin);
 //   * rotated backward: thread per (channel, bin), red.global.add per tap.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -40,6 +41,7 @@ struct Pyr {
   float scale[D2B_MAX_LEVELS];
   int min_level, max_level, canonical_level;
   float canonical_box_size;
+  const float* level_rois;  // [K,5] boxes the FPN level is computed from; null = the sampling rois themselves
 };
 
 // FPN level of a box: detectron2/modeling/poolers.py:54-62 (assign_boxes_to_levels), fp32 like torch:
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, co
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * c_per_cta;
   const int cn = min(c_per_cta, C - c0);
-  const int lvl = ROT ? 0 : pick_level(P, rois + (size_t)k * 5);
+  const int lvl = ROT ? 0 : pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
   float* __restrict__ gin = P.grad[lvl];
   const int H = P.H[lvl], W = P.W[lvl];
   const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), P.scale[lvl], PH, PW, sr, aligned);
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
 
   const int k = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
   const float* __restrict__ in = BWD ? nullptr : P.feat[lvl];
   float* __restrict__ gin = BWD ? P.grad[lvl] : nullptr;
   const int H = P.H[lvl], W = P.W[lvl];
@@ -781,21 +783,103 @@ __device__ __forceinline__ void nhwc_bin(const char* __restrict__ base, const CT
   f2_unpack(a23, acc.z, acc.w);
 }
 
+// Column-shared form of the bin loop (the fast path).  A warp owns a UNIT = 7 consecutive bins of one bin row and walks the
+// footprint columns of those bins ONCE, left to right: a column is "owned" by the first bin that touches it and feeds that
+// bin (weight wa) and, when the next bin's sample window reaches it too, the next bin (weight wb); two rotating accumulators
+// (current bin, next bin) are enough because no column may touch three bins (checked when the table is built; such RoIs --
+// bins narrower than a pixel -- take the per-bin loop above).  Per owned column the warp loads the RY tap rows of its bin row
+// (RY * XC independent 512-byte requests in flight), collapses them with the row weights and adds the result to the two
+// accumulators: RY loads per column instead of RY per (bin, column) pair -- the per-bin loop re-reads the columns that
+// neighbouring bins share and pads every bin's lists to whole chunks, 930 k against 453 k requests for the 1 024 RoIs of the
+// bench.  Entries: {byte offset of the column, wa, wb, last-column-of-its-bin flag}; every bin has at least one entry.
+constexpr int kColCap = 192;  // column entries per RoI (footprint width + pooled width + chunk padding)
+
+__device__ __forceinline__ void nhwc_emit(float* __restrict__ o, int chunk_pad, F2 c01, F2 c23, float inv, bool first) {
+  float a, b, c, d;
+  f2_unpack(c01, a, b);
+  f2_unpack(c23, c, d);
+  // later row chunks of a tall bin row accumulate (the cells of a unit belong to one warp); predicated reads, one code path
+  o[0] = fmaf(a, inv, first ? 0.f : o[0]);
+  o[32 * chunk_pad] = fmaf(b, inv, first ? 0.f : o[32 * chunk_pad]);
+  o[64 * chunk_pad] = fmaf(c, inv, first ? 0.f : o[64 * chunk_pad]);
+  o[96 * chunk_pad] = fmaf(d, inv, first ? 0.f : o[96 * chunk_pad]);
+}
+
+template <int RY, int XC>
+__device__ __forceinline__ void nhwc_unit(const char* __restrict__ base, const CTap* __restrict__ yt0, int ny, int nch,
+                                          const float4* __restrict__ colE, int cb, int ce, int skip, float* __restrict__ o,
+                                          int chunk_pad, float inv) {
+  for (int ch = 0; ch < nch; ++ch) {
+    unsigned ro[RY];
+    float wy[RY];
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const int e = ch * RY + j;
+      const CTap t = yt0[(e < ny ? e : 0) * kMaxP];
+      ro[j] = (unsigned)t.idx;
+      wy[j] = e < ny ? t.w : 0.f;
+    }
+    const F2 z = f2_pack(0.f, 0.f);
+    F2 c01 = z, c23 = z, n01 = z, n23 = z;
+    int b = -skip;  // bin of the unit the current accumulator belongs to (-1: the carry-in bin left of the unit)
+    for (int s = cb; s < ce; s += XC) {
+      float4 en[XC];
+      float4 v[XC][RY];
+#pragma unroll
+      for (int x = 0; x < XC; ++x) {
+        en[x] = colE[s + x];  // entries past ce exist (next bins or table padding): valid offsets, weights masked below
+        const char* __restrict__ cp = base + (size_t)(unsigned)__float_as_int(en[x].x);
+#pragma unroll
+        for (int j = 0; j < RY; ++j) v[x][j] = __ldg(reinterpret_cast<const float4*>(cp + ro[j]));
+      }
+#pragma unroll
+      for (int x = 0; x < XC; ++x) {
+        const bool live = XC == 1 || s + x < ce;  // warp-uniform
+        F2 t01 = z, t23 = z;
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const F2 w = f2_pack(wy[j], wy[j]);
+          t01 = f2_fma(w, f2_pack(v[x][j].x, v[x][j].y), t01);
+          t23 = f2_fma(w, f2_pack(v[x][j].z, v[x][j].w), t23);
+        }
+        const float wa = live ? en[x].y : 0.f, wb = live ? en[x].z : 0.f;
+        const F2 a2 = f2_pack(wa, wa), b2 = f2_pack(wb, wb);
+        c01 = f2_fma(a2, t01, c01);
+        c23 = f2_fma(a2, t23, c23);
+        n01 = f2_fma(b2, t01, n01);
+        n23 = f2_fma(b2, t23, n23);
+        if (live && __float_as_int(en[x].w) != 0) {  // last owned column of its bin: the bin is complete
+          if (b >= 0) nhwc_emit(o + b, chunk_pad, c01, c23, inv, ch == 0);
+          c01 = n01;
+          c23 = n23;
+          n01 = z;
+          n23 = z;
+          ++b;
+        }
+      }
+    }
+  }
+}
+
 // 4 CTAs x 7 warps per SM at 72 registers: measured faster than 3 CTAs at 80 (95 vs 97 us on the box-head call)
-__global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
+template <bool WIDE>
+__global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
                                                              int PW, int sr, int aligned, int chunk, int chunk_pad,
-                                                             float* __restrict__ out) {
+                                                             int allow_shared, float* __restrict__ out) {
   extern __shared__ __align__(16) float otile[];  // [4 (channel of the quad)][32 (lane)][chunk_pad]
   __shared__ CTap ytab[kMaxE * kMaxP];            // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];            // [tap][pw]
   __shared__ int yn[kMaxP], xn[kMaxP];
-  __shared__ int s_overflow, s_tapov;
+  __shared__ int ynr[kMaxP], xnr[kMaxP];   // list lengths before padding (the column-shared path uses the lists as built)
+  __shared__ float4 colE[kColCap];         // owned-column entries, bin after bin
+  __shared__ int cbeg[kMaxP + 1];          // first entry of every bin
+  __shared__ int s_overflow, s_tapov, s_colok, s_nymax;
   __shared__ RoiGeom sg;  // read from shared memory where needed: keeps the tap loop's register budget small
 
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * kNhwcCh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
   const int H = P.H[lvl], W = P.W[lvl];
   const int bins = PH * PW;
   const int C4 = C >> 2;
@@ -805,6 +889,8 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   if (tid == 0) {
     s_overflow = (PH > kMaxP || PW > kMaxP) ? 1 : 0;  // written here only; tap-list overflow goes to s_tapov (atomic)
     s_tapov = 0;
+    s_colok = 0;
+    s_nymax = 0;
     sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
   }
   __syncthreads();
@@ -822,25 +908,89 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
         add_tap(list, kMaxP, n, t.hi, t.wh, ov);
       }
       for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= W * C4 * 16;  // row offset in bytes
+      ynr[tid] = n;
+      atomicMax(&s_nymax, n);
       if (n > 0)  // pad to a whole number of row pairs: zero-weight taps on a valid row
         for (; n & 1; ++n) list[n * kMaxP] = CTap{list[0].idx, 0.f};
       yn[tid] = n;
       if (ov) atomicOr(&s_tapov, 1);
-    } else if (tid >= 32 && tid < 32 + PW) {
-      const int pw = tid - 32;
+    } else if (warp == 1) {  // the whole warp: lanes >= PW only take part in the shuffles
+      const int pw = lane;
+      const bool act = pw < PW;
       const RoiGeom g = sg;
       CTap* list = xtab + pw;
       int n = 0, ov = 0;
-      for (int ix = 0; ix < g.gw; ++ix) {
-        Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
-        add_tap(list, kMaxP, n, t.lo, t.wl, ov);
-        add_tap(list, kMaxP, n, t.hi, t.wh, ov);
+      if (act) {
+        for (int ix = 0; ix < g.gw; ++ix) {
+          Tap1 t = make_tap1(g.start_w + (float)pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.gw, W);
+          add_tap(list, kMaxP, n, t.lo, t.wl, ov);
+          add_tap(list, kMaxP, n, t.hi, t.wh, ov);
+        }
+        for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4 * 16;  // column offset in bytes
+        xnr[pw] = n;
+        if (ov) atomicOr(&s_tapov, 1);
       }
-      for (int e = 0; e < n; ++e) list[e * kMaxP].idx *= C4 * 16;  // column offset in bytes
-      if (n > 0)  // pad to a multiple of the x-tap chunk (4, or 8 for long lists): zero-weight taps on a valid column
-        for (const int m = n <= 4 ? 3 : 7; n & m; ++n) list[n * kMaxP] = CTap{list[0].idx, 0.f};
-      xn[pw] = n;
-      if (ov) atomicOr(&s_tapov, 1);
+      __syncwarp();
+      // ---- owned-column entries of the column-shared path (nhwc_unit): a column belongs to the first bin that touches it
+      const int n1 = act && pw >= 1 ? xnr[pw - 1] : 0, n2 = act && pw >= 2 ? xnr[pw - 2] : 0;
+      const int n3 = act && pw + 1 < PW ? xnr[pw + 1] : 0;
+      int own = 0, bad = ov;
+      unsigned ownmask = 0;  // lists hold <= kMaxE = 32 entries
+      for (int e = 0; e < n; ++e) {
+        const int c = list[e * kMaxP].idx;
+        bool in1 = false, in2 = false;
+        for (int q = 0; q < n1; ++q) in1 |= xtab[q * kMaxP + pw - 1].idx == c;
+        for (int q = 0; q < n2; ++q) in2 |= xtab[q * kMaxP + pw - 2].idx == c;
+        if (in1 && in2) bad = 1;  // three bins on one column: bins narrower than a pixel
+        if (!in1) {
+          ++own;
+          ownmask |= 1u << e;
+        }
+      }
+      const int cnt = act ? max(own, 1) : 0;  // a bin without an owned column still gets one (zero-weight) entry
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int beg = incl - cnt;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total + 4 > kColCap) bad = 1;
+      // worth it only when neighbouring bins really share columns / the per-bin lists carry padding: the column walk keeps
+      // fewer loads in flight than the per-bin loop (measured: fixed sampling_ratio on large boxes is faster per bin)
+      int padded = act ? (n == 0 ? 0 : (n <= 4 ? 4 : (n + 7) & ~7)) : 0;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) padded += __shfl_xor_sync(0xffffffffu, padded, d);
+      if (total * 5 > padded * 4) bad = 1;
+      bad = __any_sync(0xffffffffu, bad);
+      if (!bad) {
+        if (act) {
+          cbeg[pw] = beg;
+          int i = beg;
+          for (int e = 0; e < n; ++e)
+            if (ownmask >> e & 1u) {
+              const CTap t = list[e * kMaxP];
+              float wb = 0.f;
+              for (int q = 0; q < n3; ++q)
+                if (xtab[q * kMaxP + pw + 1].idx == t.idx) wb = xtab[q * kMaxP + pw + 1].w;
+              ++i;
+              colE[i - 1] = make_float4(__int_as_float(t.idx), t.w, wb, __int_as_float(i == beg + own ? 1 : 0));
+            }
+          if (own == 0) colE[beg] = make_float4(__int_as_float(0), 0.f, 0.f, __int_as_float(1));
+        }
+        if (lane < 4) colE[total + lane] = make_float4(__int_as_float(0), 0.f, 0.f, __int_as_float(0));
+        if (lane == 0) {
+          cbeg[PW] = total;
+          s_colok = 1;
+        }
+      }
+      __syncwarp();
+      if (act) {
+        if (n > 0)  // pad to a multiple of the x-tap chunk (4, or 8 for long lists): zero-weight taps on a valid column
+          for (const int m = n <= 4 ? 3 : 7; n & m; ++n) list[n * kMaxP] = CTap{list[0].idx, 0.f};
+        xn[pw] = n;
+      }
     }
   }
   __syncthreads();
@@ -849,6 +999,34 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   {
     const int bin0 = blockIdx.z * chunk;  // one output chunk per CTA
     const int nb = min(chunk, bins - bin0);
+    // column-shared path: pooled widths that split into units of 7 bins (7x7 box head, 14x14 mask head), chunks of whole units
+    const bool shared_cols = allow_shared && !onfly && s_colok && s_nymax <= 6 && PW % 7 == 0 && chunk % 7 == 0;
+    if (shared_cols) {
+      const float inv_count = sg.inv_count;
+      for (int u = warp; u * 7 < nb; u += nwarps) {
+        const int fb = bin0 + u * 7;
+        const int ph = fb / PW, pw0 = fb - ph * PW;
+        const int ny = ynr[ph];
+        float* __restrict__ o = otile + lane * chunk_pad + u * 7;
+        if (ny == 0) {  // bin row outside the map
+#pragma unroll
+          for (int b = 0; b < 7; ++b) o[b] = o[b + 32 * chunk_pad] = o[b + 64 * chunk_pad] = o[b + 96 * chunk_pad] = 0.f;
+          continue;
+        }
+        const int skip = pw0 > 0 ? 1 : 0;  // columns owned by the bin left of the unit may reach into its first bin
+        const int cb = cbeg[pw0 - skip], ce = cbeg[pw0 + 7];
+        const int nch = (ny + 5) / 6, ry = (ny + nch - 1) / nch;  // tap rows in chunks of <= 6
+        const CTap* __restrict__ yt0 = ytab + ph;
+        switch (ry) {
+          case 1: nhwc_unit<1, 4>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 2: nhwc_unit<2, WIDE ? 4 : 3>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 3: nhwc_unit<3, 2>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 4: nhwc_unit<4, WIDE ? 2 : 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 5: nhwc_unit<5, 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          default: nhwc_unit<6, 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+        }
+      }
+    } else
     for (int bl = warp; bl < nb; bl += nwarps) {
       const int bin = bin0 + bl;
       const int ph = bin / PW, pw = bin - ph * PW;
@@ -914,7 +1092,14 @@ static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   const size_t smem = sizeof(float) * 128 * (size_t)chunk_pad;
   if (nchunks > 65535) return D2B_EUNSUPPORTED;
   dim3 grid(K, slabs, nchunks);
-  roi_align_nhwc_kernel<<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, out);
+  // tuning knob (measurement only): 0 = column-shared path, 4 CTAs / SM (default); 1 = column-shared, 3 CTAs / SM with wider
+  // load batches; 2 = per-bin loop only
+  static const int mode = [] { const char* e = getenv("D2B_NHWC_MODE"); return e ? atoi(e) : 0; }();
+  if (mode == 1)
+    roi_align_nhwc_kernel<true><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, 1, out);
+  else
+    roi_align_nhwc_kernel<false><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad,
+                                                                        mode == 2 ? 0 : 1, out);
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
@@ -978,7 +1163,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int c0 = blockIdx.y * kNhwcCh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kBwdThreads / 32;
-  const int lvl = pick_level(P, rois + (size_t)k * 5);
+  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
   const int H = P.H[lvl], W = P.W[lvl];
   const int bins = PH * PW;
   const int ncta = min(kNhwcCh, C - c0);
@@ -1421,6 +1606,7 @@ static bool make_pyr(const d2b_pyramid* pyr, Pyr& P) {
   P.max_level = pyr->max_level;
   P.canonical_level = pyr->canonical_level;
   P.canonical_box_size = pyr->canonical_box_size;
+  P.level_rois = pyr->level_rois;
   if (P.num_levels > 1 && P.max_level - P.min_level + 1 != P.num_levels) return false;
   return true;
 }

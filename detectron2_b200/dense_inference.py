@@ -16,6 +16,8 @@ pipeline and there is a single host synchronisation (the read of the per-image o
     candidates, as `torchvision.ops.boxes.batched_nms` does on CUDA), dead slots parked in a dummy category;
   * the first `max_detections_per_image` survivors of every image are extracted from the score-ordered keep list on the
     device.
+On CUDA the decode, class ids, offsets (`d2b_dense_prepare`) and the final selection (`d2b_rpn_select`) are one kernel each
+for all levels and images; the torch-op form below is the host-logic restatement used for CPU tensors.
 """
 import math
 from typing import List, Sequence, Tuple
@@ -57,6 +59,70 @@ def apply_deltas(deltas: torch.Tensor, boxes: torch.Tensor, weights: Sequence[fl
     return torch.stack((x1, y1, x2, y2), dim=-1).reshape(deltas.shape)
 
 
+def dense_detector_inference_fixed(anchors: List[torch.Tensor], pred_scores: List[torch.Tensor],
+                                   pred_deltas: List[torch.Tensor], num_images: int, score_thresh: float,
+                                   topk_candidates: int, nms_thresh: float, max_detections_per_image: int,
+                                   box2box_weights: Sequence[float] = (1.0, 1.0, 1.0, 1.0),
+                                   scale_clamp: float = _DEFAULT_SCALE_CLAMP):
+    """Sync-free, fixed-capacity form (CUDA tensors only): (boxes [N, D, 4], scores [N, D], classes [N, D], counts [N]) with
+    D = max_detections_per_image, rows beyond counts[i] zero.  Launch sequence: per level one `where` + batched `topk`
+    (library), then d2b_dense_prepare (decode + class ids + NMS offsets of ALL levels and images), memset + 3 NMS kernels,
+    d2b_rpn_select, one gather.  Static shapes: capturable in a CUDA graph."""
+    import ctypes as C
+
+    from . import _C
+    from ._C import check, ptr, stream_ptr
+
+    n = int(num_images)
+    device = pred_scores[0].device
+    _C.require_cuda(*anchors, *pred_scores, *pred_deltas)
+    L = len(anchors)
+    if L > _C.MAX_LEVELS:
+        raise RuntimeError("dense_detector_inference: at most %d feature levels" % _C.MAX_LEVELS)
+    ncls = pred_scores[0].shape[2]
+    lv = _C.DenseLevels()
+    lv.num_levels = L
+    keepalive = []
+    t = 0
+    for l, (a_l, s_l, d_l) in enumerate(zip(anchors, pred_scores, pred_deltas)):
+        _, r, k_cls = s_l.shape
+        flat = s_l.reshape(n, r * k_cls)
+        k = min(int(topk_candidates), r * k_cls)
+        # score threshold + top-k (dense_detector.py:211-224): failing entries can never be selected ahead of passing ones
+        masked = torch.where(flat > score_thresh, flat.float(), torch.full_like(flat, float("-inf"), dtype=torch.float32))
+        top_s, top_i = masked.topk(k, dim=1)
+        a_c, d_c = a_l.float().contiguous(), d_l.float().contiguous()
+        keepalive += [top_s, top_i, a_c, d_c]
+        lv.anchors[l], lv.deltas[l], lv.topk_idx[l], lv.topk_scores[l] = a_c.data_ptr(), d_c.data_ptr(), top_i.data_ptr(), top_s.data_ptr()
+        lv.R[l], lv.k[l] = r, k
+        t += k
+    m = n * t
+    topk = int(max_detections_per_image) if max_detections_per_image >= 0 else t
+    f32 = dict(dtype=torch.float32, device=device)
+    i64 = dict(dtype=torch.int64, device=device)
+    flat_boxes, nms_boxes = torch.empty((m, 4), **f32), torch.empty((m, 4), **f32)
+    nms_scores, raw_scores = torch.empty((m,), **f32), torch.empty((m,), **f32)
+    classes, cat_ids = torch.empty((m,), **i64), torch.empty((m,), **i64)
+    out_boxes = torch.zeros((n, topk, 4), **f32)
+    out_scores = torch.zeros((n, topk), **f32)
+    out_index = torch.zeros((n, topk), **i64)
+    counts = torch.zeros((n,), **i64)
+    w = (C.c_float * 4)(*[float(x) for x in box2box_weights])
+    with torch.cuda.device(device):
+        check(_C.lib().d2b_dense_prepare(C.byref(lv), n, ncls, w, float(scale_clamp), ptr(flat_boxes), ptr(nms_boxes),
+                                         ptr(nms_scores), ptr(raw_scores), ptr(classes), ptr(cat_ids), stream_ptr(device)),
+              "dense_prepare")
+        if m and topk:
+            keep, num_keep = ops.nms_fixed(nms_boxes, nms_scores, cat_ids, float(nms_thresh), False, apply_offsets=False,
+                                           max_segment=max(t, 1))
+            check(_C.lib().d2b_rpn_select(ptr(keep), ptr(num_keep), n, t, topk, ptr(flat_boxes), ptr(raw_scores), ptr(cat_ids),
+                                          ptr(out_boxes), ptr(out_scores), ptr(out_index), ptr(counts), stream_ptr(device)),
+                  "det_select")
+    out_classes = classes[out_index.reshape(-1)].reshape(n, topk) if m else out_index
+    del keepalive
+    return out_boxes, out_scores, out_classes, counts
+
+
 def dense_detector_inference(anchors: List[torch.Tensor], pred_scores: List[torch.Tensor],
                              pred_deltas: List[torch.Tensor], image_sizes: List[Tuple[int, int]], score_thresh: float,
                              topk_candidates: int, nms_thresh: float, max_detections_per_image: int,
@@ -65,6 +131,24 @@ def dense_detector_inference(anchors: List[torch.Tensor], pred_scores: List[torc
     """anchors[l]: (R_l, 4) anchors of level l; pred_scores[l]: (N, R_l, K) class scores (already sigmoid-ed);
     pred_deltas[l]: (N, R_l, 4) box regression outputs.  Returns one `Detections` per image with the fields of the
     reference's `Instances` (pred_boxes, scores, pred_classes), in the reference's order (descending score)."""
+    if not pred_scores[0].is_cuda:
+        return _dense_detector_inference_host(anchors, pred_scores, pred_deltas, image_sizes, score_thresh, topk_candidates,
+                                              nms_thresh, max_detections_per_image, box2box_weights, scale_clamp)
+    ob, osc, ocl, counts = dense_detector_inference_fixed(anchors, pred_scores, pred_deltas, len(image_sizes), score_thresh,
+                                                          topk_candidates, nms_thresh, max_detections_per_image,
+                                                          box2box_weights, scale_clamp)
+    counts_host = counts.tolist()  # the one host sync: the reference contract returns exactly-sized results
+    return [Detections(sz, ob[i, :counts_host[i]], osc[i, :counts_host[i]], ocl[i, :counts_host[i]])
+            for i, sz in enumerate(image_sizes)]
+
+
+def _dense_detector_inference_host(anchors: List[torch.Tensor], pred_scores: List[torch.Tensor],
+                                   pred_deltas: List[torch.Tensor], image_sizes: List[Tuple[int, int]], score_thresh: float,
+                                   topk_candidates: int, nms_thresh: float, max_detections_per_image: int,
+                                   box2box_weights: Sequence[float] = (1.0, 1.0, 1.0, 1.0),
+                                   scale_clamp: float = _DEFAULT_SCALE_CLAMP) -> List[Detections]:
+    """The same selection written with torch ops (host-logic restatement pinned to the real reference functions by
+    tests/test_host_logic_cpu.py with the NMS replaced by the oracle; the CUDA path above is the product)."""
     num_images = len(image_sizes)
     device = pred_scores[0].device
     ncls = pred_scores[0].shape[2]

@@ -5,14 +5,16 @@ The reference processes one image at a time: boolean row filtering, `nonzero()` 
 sync), one `batched_nms`, slicing.  Here every image of the batch goes through ONE NMS pipeline and there is a single
 host synchronisation (the read of the per-image output lengths):
 
-  * candidates are the (row, class) pairs with score > score_thresh; instead of `nonzero()` the top `CAP` pairs per image
-    are taken with one `topk` (score -inf for non-candidates) and re-sorted by flat index, so the candidate order is
-    the reference's row-major order (it decides ties inside NMS).  Greedy NMS never lets a lower score influence a
-    higher one, so truncating the candidate list at CAP cannot change the first `topk_per_image` survivors as long as
-    the list was not actually truncated -- which is checked on the device and read with the output lengths; an image
-    that overflowed CAP is recomputed with the exact (synchronising) candidate list;
+  * candidates are the (row, class) pairs with score > score_thresh; instead of `nonzero()` one kernel
+    (`d2b_frcnn_prepare`, one CTA per image) drops the non-finite rows, compacts the pairs IN ROW-MAJOR ORDER (the
+    reference's order; it decides ties inside NMS) into `CAP` slots per image, clips the boxes and applies the NMS
+    coordinate offsets.  The candidate count is checked on the device and read with the output lengths; an image that
+    overflowed CAP is recomputed with the exact (synchronising) candidate list;
   * NMS category = image * (K + 1) + class with the per-image fp32 coordinate offsets of torchvision's
-    `batched_nms` reproduced exactly (`D2B_NMS_NO_OFFSET`), empty candidate slots parked in a dummy category.
+    `batched_nms` reproduced exactly (`D2B_NMS_NO_OFFSET`), empty candidate slots carry category -1 (ignored);
+  * `d2b_rpn_select` hands every image the first `topk_per_image` entries of the score-ordered keep list.
+Launch sequence for the whole batch: prepare, memset + 3 NMS kernels, select, two small gathers.  CPU tensors take the
+same selection written with torch ops (`_fast_rcnn_inference_host`, the host-logic restatement pinned by the CPU tests).
 """
 from typing import List, Tuple
 
@@ -68,10 +70,102 @@ def _single_image_exact(boxes, scores, image_shape, score_thresh, nms_thresh, to
     return Detections(image_shape, boxes[keep], scores[keep], filter_inds[keep, 1]), filter_inds[keep, 0]
 
 
+def fast_rcnn_inference_fixed(boxes: List[torch.Tensor], scores: List[torch.Tensor], image_shapes, score_thresh: float,
+                              nms_thresh: float, topk_per_image: int, cap: int = 0):
+    """Sync-free, fixed-capacity form (CUDA tensors only).  Returns a dict of device tensors: `boxes` [N, topk, 4],
+    `scores` / `classes` / `rows` [N, topk] (rows = index among the image's valid rows), `counts` [N] and `n_cand` [N]
+    (an image with n_cand > cap overflowed its candidate slots and must be redone exactly).  Static shapes: capturable."""
+    import ctypes as C
+
+    from . import _C
+    from ._C import check, ptr, stream_ptr
+
+    n = len(boxes)
+    device = boxes[0].device
+    _C.require_cuda(*boxes, *scores)
+    if n > _C.MAX_IMAGES:
+        raise RuntimeError("fast_rcnn_inference_fixed: at most %d images per call" % _C.MAX_IMAGES)
+    ncls = scores[0].shape[1] - 1
+    kreg = boxes[0].shape[1] // 4
+    rcounts = [int(b.shape[0]) for b in boxes]
+    starts = [0]
+    for r in rcounts:
+        starts.append(starts[-1] + r)
+    all_b = (boxes[0] if n == 1 else torch.cat(boxes, dim=0)).float().contiguous()
+    all_s = (scores[0] if n == 1 else torch.cat(scores, dim=0)).float().contiguous()
+    cap = int(cap) if cap else min(CANDIDATE_CAP, max(rcounts + [0]) * ncls)
+    topk = int(topk_per_image) if topk_per_image >= 0 else cap
+    if isinstance(image_shapes, torch.Tensor):
+        hw = image_shapes.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        hw = torch.tensor([[float(h), float(w)] for (h, w) in image_shapes], dtype=torch.float32).to(device)
+    m = n * cap
+    f32 = dict(dtype=torch.float32, device=device)
+    i64 = dict(dtype=torch.int64, device=device)
+    cand_boxes, nms_boxes = torch.empty((m, 4), **f32), torch.empty((m, 4), **f32)
+    nms_scores, raw_scores = torch.empty((m,), **f32), torch.empty((m,), **f32)
+    cand_flat, cat_ids = torch.empty((m,), **i64), torch.empty((m,), **i64)
+    n_cand = torch.zeros((n,), **i64)
+    row_map = torch.empty((starts[-1],), **i64)
+    out_boxes = torch.zeros((n, topk, 4), **f32)
+    out_scores = torch.zeros((n, topk), **f32)
+    out_index = torch.zeros((n, topk), **i64)
+    counts = torch.zeros((n,), **i64)
+    rs = (C.c_int * (n + 1))(*starts)
+    with torch.cuda.device(device):
+        check(_C.lib().d2b_frcnn_prepare(ptr(all_b), ptr(all_s), rs, n, ncls, kreg, ptr(hw), float(score_thresh), cap,
+                                         ptr(cand_boxes), ptr(nms_boxes), ptr(nms_scores), ptr(raw_scores), ptr(cand_flat),
+                                         ptr(cat_ids), ptr(n_cand), ptr(row_map), stream_ptr(device)), "frcnn_prepare")
+        if m and topk:
+            # a (image, class) category holds at most one candidate per proposal row
+            keep, num_keep = ops.nms_fixed(nms_boxes, nms_scores, cat_ids, float(nms_thresh), False, apply_offsets=False,
+                                           max_segment=max(min(cap, max(rcounts)), 1))
+            check(_C.lib().d2b_rpn_select(ptr(keep), ptr(num_keep), n, cap, topk, ptr(cand_boxes), ptr(raw_scores),
+                                          ptr(cat_ids), ptr(out_boxes), ptr(out_scores), ptr(out_index), ptr(counts),
+                                          stream_ptr(device)), "det_select")
+    flat = cand_flat[out_index.reshape(-1)].reshape(n, topk) if m else out_index
+    rows_local = torch.div(flat, ncls, rounding_mode="floor")
+    classes = flat - rows_local * ncls
+    # index of the kept rows among the image's valid rows (no host-built offsets: the sequence stays graph-capturable)
+    # (padded entries point at candidate 0, possibly another image's: clamp into the image's own rows)
+    rows = torch.stack([row_map[starts[j]:starts[j + 1]][rows_local[j].clamp(max=rcounts[j] - 1)] if rcounts[j] else rows_local[j]
+                        for j in range(n)]) if n else rows_local
+    return {"boxes": out_boxes, "scores": out_scores, "classes": classes, "rows": rows, "counts": counts, "n_cand": n_cand,
+            "cap": cap}
+
+
 def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], image_shapes: List[Tuple[int, int]],
                         score_thresh: float, nms_thresh: float, topk_per_image: int):
     """boxes[i]: R_i x (K*4) or R_i x 4 predicted boxes, scores[i]: R_i x (K+1) class scores (last = background).
     Returns (list[Detections], list[Tensor of kept row indices]) exactly like the reference."""
+    if not boxes[0].is_cuda:
+        return _fast_rcnn_inference_host(boxes, scores, image_shapes, score_thresh, nms_thresh, topk_per_image)
+    from . import _C
+
+    results, kept_rows = [], []
+    for i0 in range(0, len(boxes), _C.MAX_IMAGES):  # chunks of the ABI's image bound
+        sl = slice(i0, i0 + _C.MAX_IMAGES)
+        out = fast_rcnn_inference_fixed(boxes[sl], scores[sl], image_shapes[sl], score_thresh, nms_thresh, topk_per_image)
+        stats = torch.stack([out["counts"], out["n_cand"]], dim=1).tolist()  # the one host sync: exactly-sized results
+        dt = scores[i0].dtype
+        for j, (c, n_cand) in enumerate(stats):
+            i = i0 + j
+            if n_cand > out["cap"]:  # candidate list was truncated: redo this image exactly (rare)
+                det, rows_i = _single_image_exact(boxes[i], scores[i], image_shapes[i], score_thresh, nms_thresh,
+                                                  topk_per_image)
+            else:
+                det = Detections(image_shapes[i], out["boxes"][j, :c], out["scores"][j, :c].to(dt), out["classes"][j, :c])
+                rows_i = out["rows"][j, :c]
+            results.append(det)
+            kept_rows.append(rows_i)
+    return results, kept_rows
+
+
+def _fast_rcnn_inference_host(boxes: List[torch.Tensor], scores: List[torch.Tensor], image_shapes: List[Tuple[int, int]],
+                              score_thresh: float, nms_thresh: float, topk_per_image: int):
+    """The same selection written with torch ops: top-`CAP` pairs per image by one `topk` (score -inf for non-candidates)
+    re-sorted by flat index = the reference's row-major candidate order.  Host-logic restatement pinned to the real
+    reference function by tests/test_host_logic_cpu.py (NMS replaced by the oracle); the CUDA path above is the product."""
     num_images = len(boxes)
     device = boxes[0].device
     ncls = scores[0].shape[1] - 1

@@ -211,8 +211,12 @@ roi_align_op.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
 
 
 # ----------------------------------------------------------------------------------- fused multi-level pooler
-def _pyramid(feats, grads, scales, min_level, max_level, canonical_level, canonical_box_size):
+_HALF = (torch.float16, torch.bfloat16)
+
+
+def _pyramid(feats, grads, scales, min_level, max_level, canonical_level, canonical_box_size, level_rois=None):
     P = _C.Pyramid()
+    P.level_rois = level_rois.data_ptr() if level_rois is not None else None
     P.num_levels = len(feats)
     for l, t in enumerate(feats):
         P.feat[l] = t.data_ptr()
@@ -232,7 +236,11 @@ def roi_pooler_op(feats: List[Tensor], rois: Tensor, scales: List[float], pooled
     if len(feats) < 1 or len(feats) > _C.MAX_LEVELS or len(feats) != len(scales):
         raise RuntimeError("roi_pooler: need 1..%d feature levels with one scale each" % _C.MAX_LEVELS)
     fs = [t.to(dtype=torch.float32) for t in feats]
-    r = _f32c(rois)
+    r_lvl = _f32c(rois)
+    # half-precision feature maps: the reference samples with the rois cast to the feature dtype (layers/roi_align.py:60,
+    # then torchvision's autocast wrapper upcasts both) while the FPN level comes from the fp32 boxes (poolers.py:245)
+    half = feats[0].dtype in _HALF
+    r = r_lvl.to(feats[0].dtype).to(torch.float32) if half else r_lvl
     n, c = fs[0].shape[:2]
     k = r.shape[0]
     out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=r.device)
@@ -243,7 +251,7 @@ def roi_pooler_op(feats: List[Tensor], rois: Tensor, scales: List[float], pooled
             if layout != "cl":
                 fs = [t.contiguous() for t in fs]
             # channels_last tensors: same logical shape, NHWC storage -- _pyramid only takes pointers and H, W
-            P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size)
+            P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size, r_lvl if half else None)
             if layout == "nchw":
                 check(_C.lib().d2b_roi_pooler_forward(C.byref(P), *args), "roi_pooler_forward")
             else:
@@ -265,9 +273,12 @@ def _(feats, rois, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_leve
 def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales: List[float], pooled_h: int,
                            pooled_w: int, sampling_ratio: int, aligned: bool, min_level: int, max_level: int,
                            canonical_level: int, canonical_box_size: float,
-                           channels_last: bool = False) -> List[Tensor]:
-    _C.require_cuda(grad, rois)
+                           channels_last: bool = False, level_rois: Optional[Tensor] = None) -> List[Tensor]:
+    """`level_rois`: the fp32 boxes the FPN level was assigned from when `rois` are the feature-dtype-rounded ones the forward
+    sampled with (half-precision features, see roi_pooler_op)."""
+    _C.require_cuda(grad, rois, level_rois)
     g, r = _f32c(grad), _f32c(rois)
+    lr = _f32c(level_rois)
     nl = len(scales)
     n, c = shapes[0], shapes[1]
     hw = [(shapes[2 + 2 * l], shapes[3 + 2 * l]) for l in range(nl)]
@@ -276,12 +287,12 @@ def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales
     with torch.cuda.device(g.device):
         if layout == "nchw":
             grads = [torch.empty((n, c, h, w), dtype=torch.float32, device=g.device) for (h, w) in hw]
-            P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size)
+            P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size, lr)
             check(_C.lib().d2b_roi_pooler_backward(C.byref(P), *pargs), "roi_pooler_backward")
         else:
             bufs = [torch.empty((n, h, w, c), dtype=torch.float32, device=g.device) for (h, w) in hw]
             views = [b.permute(0, 3, 1, 2) for b in bufs]  # logical NCHW shape: _pyramid reads H, W from dims 2, 3
-            P = _pyramid(views, views, scales, min_level, max_level, canonical_level, canonical_box_size)
+            P = _pyramid(views, views, scales, min_level, max_level, canonical_level, canonical_box_size, lr)
             check(_C.lib().d2b_roi_pooler_backward_nhwc(C.byref(P), *pargs), "roi_pooler_backward_nhwc")
             grads = views if layout == "cl" else _from_nhwc(bufs, n, c, g.device)
     return grads
@@ -289,7 +300,7 @@ def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales
 
 @roi_pooler_backward_op.register_fake
 def _(grad, rois, shapes, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_level, max_level, canonical_level,
-      canonical_box_size, channels_last=False):
+      canonical_box_size, channels_last=False, level_rois=None):
     n, c = shapes[0], shapes[1]
     outs = [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
     return [o.contiguous(memory_format=torch.channels_last) for o in outs] if channels_last else outs
@@ -308,7 +319,9 @@ def _pooler_setup(ctx, inputs, output):
 def _pooler_bwd(ctx, grad):
     (rois,) = ctx.saved_tensors
     shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, dts, chl = ctx.args
-    grads = roi_pooler_backward_op(grad, rois, shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, chl)
+    half = dts[0] in _HALF  # same rois as the forward: rounded to the feature dtype for sampling, fp32 for the level
+    grads = roi_pooler_backward_op(grad, rois.to(dts[0]).to(torch.float32) if half else rois, shapes, scales, ph, pw, sr,
+                                   aligned, lo, hi, cl, cs, chl, rois if half else None)
     return [g.to(dt) for g, dt in zip(grads, dts)], None, None, None, None, None, None, None, None, None, None
 
 

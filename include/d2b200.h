@@ -31,7 +31,7 @@ extern "C" {
 #define D2B_EWORKSPACE (-2)  /* workspace too small */
 #define D2B_EUNSUPPORTED (-3)
 
-#define D2B_ABI_VERSION 3
+#define D2B_ABI_VERSION 4
 int d2b_abi_version(void);
 /* compile-time facts, replaces detectron2._C.get_cuda_version / has_cuda (csrc/vision.cpp:23-49,86-88) */
 int d2b_cuda_version(void);
@@ -67,6 +67,10 @@ typedef struct {
   float scale[D2B_MAX_LEVELS];
   int min_level, max_level, canonical_level;
   float canonical_box_size;
+  /* Optional [K,5] boxes the FPN level is assigned from (NULL: the sampling rois).  The reference assigns levels from the
+   * fp32 boxes (poolers.py:245) but samples half-precision feature maps with rois cast to the feature dtype
+   * (layers/roi_align.py:60): a host that reproduces that hands the rounded rois as `rois` and the fp32 ones here. */
+  const float* level_rois;
 } d2b_pyramid;
 int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
                            int pooled_w, int sampling_ratio, int aligned, float* out, void* stream);
@@ -170,6 +174,41 @@ int d2b_rpn_prepare(const d2b_rpn_levels* lv, int N, const float* image_hw, floa
 int d2b_rpn_select(const int64_t* keep, const int64_t* num_keep, int N, int T, int post_nms_topk,
                    const float* flat_boxes, const float* raw_scores, const int64_t* cat_ids, float* out_boxes,
                    float* out_scores, int64_t* out_index, int64_t* counts, void* stream);
+
+/* ---- Fast R-CNN and dense-head (RetinaNet) inference candidates around the NMS -----------------
+ * Replace the per-image Python loops of detectron2/modeling/roi_heads/fast_rcnn.py:46-173 (`fast_rcnn_inference`:
+ * boolean filtering, `nonzero()` sync, per-image batched_nms, slicing) and of meta_arch/dense_detector.py:186-258 +
+ * meta_arch/retinanet.py:256-308 (per-level filter / top-k / apply_deltas, per-image batched_nms) by
+ *   d2b_frcnn_prepare | (torch.topk per level ->) d2b_dense_prepare  ->  d2b_nms(category = image*(K+1) + class,
+ *   D2B_NMS_NO_OFFSET)  ->  d2b_rpn_select (the same per-image first-topk selection).
+ * d2b_frcnn_prepare: boxes [Rtot, kreg*4] predicted boxes (kreg = 1 class-agnostic or K), scores [Rtot, K+1] (last column =
+ *   background) of N <= D2B_MAX_IMAGES images concatenated; row_start [N+1] HOST array of the images' first rows;
+ *   image_hw [N,2] on the device.  Per image the (row, class) pairs with score > score_thresh of the rows whose box and
+ *   score entries are all finite are written in row-major order into `cap` slots: cand_boxes (clipped), nms_boxes
+ *   (+ torchvision's class * (max coordinate + 1) offsets), nms_scores (-inf in dead slots), raw_scores, cand_flat
+ *   (row_in_image * K + class), cat_ids (image*(K+1) + class, -1 = dead); n_cand [N] = the image's candidate count (larger
+ *   than cap: the list was truncated and the caller must redo that image); row_map [Rtot] = index of a row among its image's
+ *   valid rows (-1 for dropped rows) -- what the reference returns as kept row indices.
+ * d2b_dense_prepare: per level l anchors [R_l,4], deltas [N,R_l,4], and the batched top-k of the thresholded scores
+ *   (topk_idx [N,k_l] = anchor*K + class, topk_scores [N,k_l] with -inf in dead slots); weights[4] (HOST) and scale_clamp of
+ *   Box2BoxTransform.  Writes for all N*T candidates (T = sum k_l): flat_boxes (decoded), nms_boxes (+ offsets while the
+ *   image has <= 25 000 live candidates, as torchvision), nms_scores, raw_scores, classes, cat_ids. */
+#define D2B_MAX_IMAGES 64
+typedef struct {
+  int num_levels;
+  const float* anchors[D2B_MAX_LEVELS];
+  const float* deltas[D2B_MAX_LEVELS];
+  const int64_t* topk_idx[D2B_MAX_LEVELS];
+  const float* topk_scores[D2B_MAX_LEVELS];
+  int R[D2B_MAX_LEVELS], k[D2B_MAX_LEVELS];
+} d2b_dense_levels;
+int d2b_frcnn_prepare(const float* boxes, const float* scores, const int* row_start, int N, int num_classes, int kreg,
+                      const float* image_hw, float score_thresh, int cap, float* cand_boxes, float* nms_boxes,
+                      float* nms_scores, float* raw_scores, int64_t* cand_flat, int64_t* cat_ids, int64_t* n_cand,
+                      int64_t* row_map, void* stream);
+int d2b_dense_prepare(const d2b_dense_levels* lv, int N, int num_classes, const float* weights, float scale_clamp,
+                      float* flat_boxes, float* nms_boxes, float* nms_scores, float* raw_scores, int64_t* classes,
+                      int64_t* cat_ids, void* stream);
 
 /* ---- Mask-head training targets + loss ------------------------------------------------------
  * Replaces, for one image, BitMasks.crop_and_resize (detectron2/structures/masks.py:193-224) + the class gather and

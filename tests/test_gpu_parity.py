@@ -647,6 +647,66 @@ def test_roi_pooler_nhwc_paths_vs_reference_loop(mode, monkeypatch):
     assert ok, err
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_half_precision_inputs_through_the_public_api(L, dt):
+    """bf16 / fp16 activations (what autocast training hands the ops; the reference upcasts them, roi_align_rotated.py:81-83,
+    torchvision's autocast wrapper): fp32 arithmetic on the stored values, results and gradients returned in the input dtype.
+    Oracle = the fp32 op on the same (half-representable) values; tolerance = the rounding of the returned dtype."""
+    from detectron2_b200.poolers import ROIPooler
+
+    g = torch.Generator().manual_seed(3)
+    eps = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    feats = [torch.randn(2, 40, 200 // 2 ** i, 336 // 2 ** i, generator=g).to(dt) for i in range(4)]
+    per_img = []
+    for _ in range(2):
+        s = torch.exp(torch.rand(90, generator=g) * (math.log(600) - math.log(16)) + math.log(16))
+        ctr = torch.rand(90, 2, generator=g) * torch.tensor([1344.0, 800.0])
+        per_img.append(torch.cat([ctr - s[:, None] / 2, ctr + s[:, None] / 2], 1))
+    rois = torch.cat([torch.cat([torch.full((90, 1), float(i)), b], 1) for i, b in enumerate(per_img)])
+    # the reference's recipe for half features: level from the fp32 boxes (poolers.py:245), sampling with the rois cast to
+    # the feature dtype (layers/roi_align.py:60)
+    sizes = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(2, 5).long() - 2
+    rois_geo = rois.to(dt).float()
+    ref = torch.zeros(len(rois), 40, 7, 7)
+    for l, s_ in enumerate(scales):
+        idx = torch.nonzero(lv == l, as_tuple=True)[0]
+        ref[idx] = orc.roi_align_forward(feats[l].float(), rois_geo[idx], s_, 7, 7, 0, True)
+    fd = [f.to(DEV).requires_grad_(True) for f in feats]
+    y = ROIPooler(7, scales, 0, "ROIAlignV2")(fd, [b.to(DEV) for b in per_img])
+    assert y.dtype == dt
+    ok, err = rel_close(y, ref, rtol=2 * eps, atol=2 * eps)
+    assert ok, err
+    go = torch.randn(y.shape, generator=g).to(dt)
+    y.backward(go.to(DEV))
+    assert all(f.grad.dtype == dt for f in fd)
+    for l, s_ in enumerate(scales):
+        idx = torch.nonzero(lv == l, as_tuple=True)[0]
+        gref = orc.roi_align_backward(go.float()[idx], rois_geo[idx], s_, 7, 7, 2, 40, feats[l].shape[2], feats[l].shape[3], 0, True)
+        ok, err = rel_close(fd[l].grad, gref, rtol=2 * eps, atol=2 * eps * max(gref.abs().max().item(), 1.0))
+        assert ok, (l, err)
+    # deformable conv (tensor-core path): half activations / offsets / gradient, fp32 master weight
+    x = torch.randn(2, 64, 20, 28, generator=g).to(dt)
+    off = (torch.randn(2, 18, 20, 28, generator=g) * 2).to(dt)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    xd, od, wd = x.to(DEV).requires_grad_(True), off.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    yd = L.deform_conv(xd, od, wd, 1, 1, 1, 1, 1)
+    assert yd.dtype == dt
+    r = orc.deform_conv_forward(x.float(), off.float(), None, w, None, 1, 1, 1, 1, 1)
+    ok, err = rel_close(yd, r, rtol=2 * eps, atol=2 * eps * r.abs().max().item())
+    assert ok, err
+    gy = torch.randn(r.shape, generator=g).to(dt)
+    yd.backward(gy.to(DEV))
+    gx, goff, _, gw, _ = orc.deform_conv_backward(x.float(), off.float(), None, w, gy.float(), 1, 1, 1, 1, 1, False)
+    assert xd.grad.dtype == dt and od.grad.dtype == dt and wd.grad.dtype == torch.float32
+    for a, b in ((xd.grad, gx), (od.grad, goff)):
+        ok, err = rel_close(a, b, rtol=2 * eps, atol=2 * eps * b.abs().max().item())
+        assert ok, err
+    ok, err = rel_close(wd.grad, gw, rtol=1e-4, atol=1e-4 * gw.abs().max().item())
+    assert ok, err
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc", "cl"])
 def test_roi_pooler_backward_layouts_vs_oracle(layout, monkeypatch):
     # the three backward routes: NCHW kernel, channels-last kernel into scratch + layout change, channels-last in place
@@ -1007,6 +1067,60 @@ def test_fast_rcnn_inference_golden(golden):
     assert len(det) == 0 and r.numel() == 0
 
 
+def test_fast_rcnn_inference_kernels_vs_host_restatement_coco_size():
+    """The fused candidate / selection kernels against the torch-op restatement of the same selection (itself pinned to the
+    real reference function by the CPU tests), at Mask R-CNN test size: 3 images x 1000 proposals x 80 classes, tied scores,
+    non-finite rows, one image without proposals; and the fixed-capacity form replayed from a CUDA graph."""
+    from detectron2_b200 import fast_rcnn_inference as fri
+
+    g = torch.Generator().manual_seed(21)
+    k = 80
+    boxes, scores, shapes = [], [], [(800, 1333), (768, 1024), (600, 900), (480, 640)]
+    for r in (1000, 1000, 700, 0):
+        ctr = torch.rand(r, 1, 2, generator=g) * torch.tensor([1333.0, 800.0])
+        wh = 20 + 300 * torch.rand(r, 1, 2, generator=g)
+        jit = torch.randn(r, k, 4, generator=g) * 8
+        b = (torch.cat([ctr - wh / 2, ctr + wh / 2], 2) + jit).reshape(r, k * 4)
+        logits = torch.randn(r, k + 1, generator=g) * 2.0
+        logits[:, -1] += 2.0
+        sc = logits.softmax(1)
+        sc = (sc * 64).round() / 64  # many exact ties: the candidate order decides them
+        if r > 10:
+            b[3, 5] = float("nan")
+            sc[7, 2] = float("inf")
+        boxes.append(b.to(DEV))
+        scores.append(sc.to(DEV))
+    res, rows = fri.fast_rcnn_inference(boxes, scores, shapes, 0.05, 0.5, 100)
+    ref, ref_rows = fri._fast_rcnn_inference_host(boxes, scores, shapes, 0.05, 0.5, 100)
+    assert sum(len(r) for r in res) > 150
+    for a, b, ra, rb in zip(res, ref, rows, ref_rows):
+        assert torch.equal(a.pred_boxes, b.pred_boxes) and torch.equal(a.scores, b.scores)
+        assert torch.equal(a.pred_classes, b.pred_classes) and torch.equal(ra, rb)
+    # class-agnostic regression (R x 4 boxes)
+    res, rows = fri.fast_rcnn_inference([b[:, :4].contiguous() for b in boxes], scores, shapes, 0.05, 0.5, 100)
+    ref, ref_rows = fri._fast_rcnn_inference_host([b[:, :4].contiguous() for b in boxes], scores, shapes, 0.05, 0.5, 100)
+    for a, b, ra, rb in zip(res, ref, rows, ref_rows):
+        assert torch.equal(a.pred_boxes, b.pred_boxes) and torch.equal(a.scores, b.scores)
+        assert torch.equal(a.pred_classes, b.pred_classes) and torch.equal(ra, rb)
+    # CUDA graph of the fixed-capacity sequence
+    hw = torch.tensor([[float(h), float(w)] for (h, w) in shapes], device=DEV)
+    fri.fast_rcnn_inference_fixed(boxes[:3], scores[:3], hw[:3], 0.05, 0.5, 100)  # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st):
+            out = fri.fast_rcnn_inference_fixed(boxes[:3], scores[:3], hw[:3], 0.05, 0.5, 100)
+    graph.replay()
+    torch.cuda.synchronize()
+    res, rows = fri.fast_rcnn_inference(boxes[:3], scores[:3], shapes[:3], 0.05, 0.5, 100)
+    for i in range(3):
+        c = int(out["counts"][i])
+        assert c == len(res[i])
+        assert torch.equal(out["boxes"][i, :c], res[i].pred_boxes) and torch.equal(out["classes"][i, :c], res[i].pred_classes)
+        assert torch.equal(out["rows"][i, :c], rows[i])
+
+
 # ------------------------------------------------------------------------------- batched RetinaNet inference (8f-2)
 def _check_dense(res, ref_scores, ref_classes, ref_boxes, tag):
     # scores / classes are selected, never recomputed: exact.  Boxes go through exp() in the decode, which differs between
@@ -1080,6 +1194,33 @@ def test_retinanet_inference_coco_size_vs_oracle():
         missing = len(set(gs.tolist()) ^ set(s[kept].tolist()))  # a flipped decision shifts the list: compare as sets
         assert missing <= 4, (i, missing)
         assert (gs[:-1] >= gs[1:]).all()
+
+
+def test_retinanet_inference_kernels_vs_host_restatement():
+    """d2b_dense_prepare / d2b_rpn_select against the torch-op restatement of the same selection on the same device: identical
+    scores / classes, boxes identical up to the last bit of exp() (torch's CUDA exp and expf in our kernel)."""
+    from detectron2_b200 import dense_inference as di
+
+    g = torch.Generator().manual_seed(13)
+    n, k_cls = 3, 80
+    sizes = [(800, 1333), (768, 1024), (640, 640)]
+    anchors, scores, deltas = [], [], []
+    for stride in [8, 16, 32, 64, 128]:
+        h, w = math.ceil(800 / stride), math.ceil(1333 / stride)
+        r = h * w * 9
+        ctr = torch.rand(r, 2, generator=g) * torch.tensor([1333.0, 800.0])
+        wh = stride * (2 + 6 * torch.rand(r, 2, generator=g))
+        anchors.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1).to(DEV))
+        sc = (torch.randn(n, r, k_cls, generator=g) * 1.2 - 4.0).sigmoid()
+        sc[2] = 0.0  # an image without candidates
+        scores.append(sc.to(DEV))
+        deltas.append((torch.randn(n, r, 4, generator=g) * 0.2).to(DEV))
+    res = di.dense_detector_inference(anchors, scores, deltas, sizes, 0.05, 1000, 0.5, 100, (1.0, 1.0, 2.0, 2.0))
+    ref = di._dense_detector_inference_host(anchors, scores, deltas, sizes, 0.05, 1000, 0.5, 100, (1.0, 1.0, 2.0, 2.0))
+    assert len(res[0]) == 100 and len(res[2]) == 0
+    for a, b in zip(res, ref):
+        assert torch.equal(a.scores, b.scores) and torch.equal(a.pred_classes, b.pred_classes)
+        assert torch.allclose(a.pred_boxes, b.pred_boxes, rtol=1e-6, atol=1e-4)
 
 
 # ------------------------------------------------------------------------------- mask targets / detector post-processing (8f-4)
