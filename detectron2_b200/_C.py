@@ -26,6 +26,7 @@ MAX_LEVELS = 8
 MAX_IMAGES = 64  # D2B_MAX_IMAGES
 ABI_VERSION = 4  # include/d2b200.h D2B_ABI_VERSION
 DCN_X_NHWC = 1   # D2B_DCN_X_NHWC
+DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}  # D2B_F32 / D2B_F16 / D2B_BF16
 
 
 class Pyramid(C.Structure):
@@ -61,6 +62,10 @@ def _declare(lib):
         "d2b_roi_pooler_forward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, i, i, i, i, i, f32p, vp]),
         "d2b_pyramid_nchw_to_nhwc": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), vp]),
         "d2b_pyramid_nhwc_to_nchw": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), vp]),
+        "d2b_pyramid_nchw_to_nhwc_t": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), i, vp]),
+        "d2b_pyramid_nhwc_to_nchw_t": (i, [C.POINTER(Pyramid), i, i, C.POINTER(C.c_void_p), i, vp]),
+        "d2b_roi_pooler_forward_nhwc_t": (i, [C.POINTER(Pyramid), i, i, f32p, i, i, i, i, i, vp, i, vp]),
+        "d2b_roi_pooler_backward_nhwc_t": (i, [C.POINTER(Pyramid), i, i, vp, i, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_backward_nhwc": (i, [f32p, f32p, i, f, i, i, i, i, i, i, i, i, f32p, vp]),
         "d2b_roi_pooler_backward_nhwc": (i, [C.POINTER(Pyramid), i, i, f32p, f32p, i, i, i, i, i, vp]),
         "d2b_roi_align_rotated_forward": (i, [f32p, i, i, i, i, f32p, i, f, i, i, i, f32p, vp]),

@@ -14,6 +14,9 @@
 //   * rotated forward: one CTA per (RoI, channel slab) with a 2-D tap table in shared memory (the sample grid of a
 //     rotated RoI is not a product grid), threads mapped to (channel, bin);
 //   * rotated backward: thread per (channel, bin), red.global.add per tap.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -22,6 +25,44 @@
 namespace {
 
 constexpr int kThreads = 256;
+
+// Element types by the ABI's dtype code (D2B_F32 / D2B_F16 / D2B_BF16): half-precision activations and gradients are read and
+// written in place by the layout-change and pooling kernels (fp32 arithmetic), instead of a separate cast pass per tensor.
+// Compile-time: the fp32 instantiations are the kernels as they were.
+template <int DT>
+struct Elem;
+template <>
+struct Elem<D2B_F32> {
+  using T = float;
+  static __device__ __forceinline__ float ld(const T* __restrict__ p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(T* __restrict__ p, float v) { *p = v; }
+};
+template <>
+struct Elem<D2B_F16> {
+  using T = __half;
+  static __device__ __forceinline__ float ld(const T* __restrict__ p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ void st(T* __restrict__ p, float v) { *p = __float2half_rn(v); }
+};
+template <>
+struct Elem<D2B_BF16> {
+  using T = __nv_bfloat16;
+  static __device__ __forceinline__ float ld(const T* __restrict__ p) { return __bfloat162float(__ldg(p)); }
+  static __device__ __forceinline__ void st(T* __restrict__ p, float v) { *p = __float2bfloat16_rn(v); }
+};
+#define D2B_DISPATCH_DTYPE(dt, ...)                  \
+  do {                                               \
+    if ((dt) == D2B_F32) {                           \
+      constexpr int DT = D2B_F32;                    \
+      __VA_ARGS__;                                   \
+    } else if ((dt) == D2B_F16) {                    \
+      constexpr int DT = D2B_F16;                    \
+      __VA_ARGS__;                                   \
+    } else {                                         \
+      constexpr int DT = D2B_BF16;                   \
+      __VA_ARGS__;                                   \
+    }                                                \
+  } while (0)
+static inline bool dtype_ok(int dt) { return dt == D2B_F32 || dt == D2B_F16 || dt == D2B_BF16; }
 
 struct RoiGeom {
   int b;
@@ -862,10 +903,10 @@ __device__ __forceinline__ void nhwc_unit(const char* __restrict__ base, const C
 }
 
 // 4 CTAs x 7 warps per SM at 72 registers: measured faster than 3 CTAs at 80 (95 vs 97 us on the box-head call)
-template <bool WIDE>
+template <bool WIDE, int ODT>
 __global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
                                                              int PW, int sr, int aligned, int chunk, int chunk_pad,
-                                                             int allow_shared, float* __restrict__ out) {
+                                                             int allow_shared, void* __restrict__ out_v) {
   extern __shared__ __align__(16) float otile[];  // [4 (channel of the quad)][32 (lane)][chunk_pad]
   __shared__ CTap ytab[kMaxE * kMaxP];            // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];            // [tap][pw]
@@ -1062,17 +1103,17 @@ __global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_ker
     }
     __syncthreads();
     // channel-major write-out: channel c0+cl, bins [bin0, bin0+nb) -- one contiguous run of the output per channel
-    float* __restrict__ obase = out + ((size_t)k * C + c0) * bins + bin0;
+    typename Elem<ODT>::T* __restrict__ obase = reinterpret_cast<typename Elem<ODT>::T*>(out_v) + ((size_t)k * C + c0) * bins + bin0;
     const unsigned magic = 0xFFFFFFFFu / (unsigned)nb + 1u;  // i / nb == umulhi(i, magic) for i < 2^16 (i < 128 * 64 here)
     for (int i = tid; i < ncta * nb; i += blockDim.x) {
       const int cl = nb == 1 ? i : (int)__umulhi((unsigned)i, magic), bl = i - cl * nb;  // (magic wraps to 0 for nb == 1)
-      obase[(size_t)cl * bins + bl] = otile[((cl & 3) * 32 + (cl >> 2)) * chunk_pad + bl];
+      Elem<ODT>::st(obase + (size_t)cl * bins + bl, otile[((cl & 3) * 32 + (cl >> 2)) * chunk_pad + bl]);
     }
   }
 }
 
 static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C, int PH, int PW, int sr, int aligned,
-                           float* out, cudaStream_t stream) {
+                           void* out, cudaStream_t stream, int out_dt = D2B_F32) {
   if (C % 4 != 0) return D2B_EUNSUPPORTED;
   for (int l = 0; l < P.num_levels; ++l) {
     if ((long long)P.H[l] * P.W[l] * (C / 4) >= (1LL << 28)) return D2B_EUNSUPPORTED;  // 32-bit byte offsets inside an image
@@ -1096,10 +1137,10 @@ static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   // load batches; 2 = per-bin loop only
   static const int mode = [] { const char* e = getenv("D2B_NHWC_MODE"); return e ? atoi(e) : 0; }();
   if (mode == 1)
-    roi_align_nhwc_kernel<true><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, 1, out);
+    roi_align_nhwc_kernel<true, D2B_F32><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, 1, out);
   else
-    roi_align_nhwc_kernel<false><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad,
-                                                                        mode == 2 ? 0 : 1, out);
+    D2B_DISPATCH_DTYPE(out_dt, (roi_align_nhwc_kernel<false, DT><<<grid, kNhwcThreads, smem, stream>>>(
+                                   P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, mode == 2 ? 0 : 1, out)));
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
@@ -1121,16 +1162,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 }
 
 // Per-sample scatter (taps on the fly, one red.v4 per tap): pooled sizes > 16 and footprints wider than the column table.
-__device__ void bwd_nhwc_per_sample(const RoiGeom& g, const float* __restrict__ go, float* __restrict__ gimg, int H, int W,
-                                    int C, int PH, int PW, bool lane_live) {
+template <int GDT>
+__device__ void bwd_nhwc_per_sample(const RoiGeom& g, const typename Elem<GDT>::T* __restrict__ go, float* __restrict__ gimg,
+                                    int H, int W, int C, int PH, int PW, bool lane_live) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int bins = PH * PW;
   for (int bin = warp; bin < bins; bin += nwarps) {
     const int ph = bin / PW, pw = bin - ph * PW;
     float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane_live) {
-      const float* q = go + (size_t)(lane * 4) * bins + bin;
-      gv = make_float4(q[0] * g.inv_count, q[bins] * g.inv_count, q[2 * bins] * g.inv_count, q[3 * bins] * g.inv_count);
+      const typename Elem<GDT>::T* q = go + (size_t)(lane * 4) * bins + bin;
+      gv = make_float4(Elem<GDT>::ld(q) * g.inv_count, Elem<GDT>::ld(q + bins) * g.inv_count,
+                       Elem<GDT>::ld(q + 2 * bins) * g.inv_count, Elem<GDT>::ld(q + 3 * bins) * g.inv_count);
     }
     for (int iy = 0; iy < g.gh; ++iy) {
       const Tap1 ty = make_tap1(g.start_h + (float)ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
@@ -1147,9 +1190,10 @@ __device__ void bwd_nhwc_per_sample(const RoiGeom& g, const float* __restrict__ 
   }
 }
 
+template <int GDT>
 __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C,
                                                                        int PH, int PW, int sr, int aligned,
-                                                                       const float* __restrict__ gout) {
+                                                                       const void* __restrict__ gout) {
   extern __shared__ __align__(16) float gs[];  // [bin][128 ch], float4 slots XOR-swizzled with the bin index
   __shared__ float WyT[kBwdBand * kMaxP];      // [row of the band][ph]
   __shared__ float WxT[kBwdMaxFw * kMaxP];     // [column of the footprint][pw]
@@ -1177,10 +1221,10 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   __syncthreads();
   const RoiGeom g = sg;
   float* __restrict__ gimg = P.grad[lvl] + (size_t)g.b * H * W * C + c0 + lane * 4;
-  const float* __restrict__ go = gout + ((size_t)k * C + c0) * bins;
+  const typename Elem<GDT>::T* __restrict__ go = reinterpret_cast<const typename Elem<GDT>::T*>(gout) + ((size_t)k * C + c0) * bins;
 
   if (PH > kMaxP || PW > kMaxP) {  // pooled size beyond the tables: per-sample path
-    bwd_nhwc_per_sample(g, go, gimg, H, W, C, PH, PW, lane_live);
+    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live);
     return;
   }
   // ---- footprint bounds (rows / columns that receive a non-zero weight)
@@ -1212,7 +1256,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int xmin = s_xmin, fw = s_xmax - s_xmin + 1, ymin = s_ymin, ymax = s_ymax;
   if (s_xmax < 0 || ymax < 0) return;  // no sample inside the map: zero gradient
   if (fw > kBwdMaxFw) {  // very wide footprint (block-uniform)
-    bwd_nhwc_per_sample(g, go, gimg, H, W, C, PH, PW, lane_live);
+    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live);
     return;
   }
   // ---- column table + gradient tile
@@ -1228,7 +1272,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   }
   for (int e = tid; e < ncta * bins; e += kBwdThreads) {  // coalesced read of [ch][bin], transposed + swizzled store
     const int c = e / bins, bin = e - c * bins;
-    gs[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] = __ldg(go + e) * g.inv_count;
+    gs[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] = Elem<GDT>::ld(go + e) * g.inv_count;
   }
   __syncthreads();
   for (int x = tid; x < fw; x += kBwdThreads) {
@@ -1350,7 +1394,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
 }
 
 static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C, int PH, int PW, int sr, int aligned,
-                           const float* gout, cudaStream_t stream) {
+                           const void* gout, cudaStream_t stream, int g_dt = D2B_F32) {
   if (C % 4 != 0) return D2B_EUNSUPPORTED;
   for (int l = 0; l < P.num_levels; ++l)
     if ((reinterpret_cast<uintptr_t>(P.grad[l]) & 15) != 0) return D2B_EINVAL;
@@ -1358,9 +1402,11 @@ static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   // gradient tile [bins][128] + per-warp row-collapsed tile [8 warps][PW][128]
   const size_t smem = sizeof(float) * kNhwcCh * ((size_t)PH * PW + (size_t)(kBwdThreads / 32) * PW);
   if (smem > 180 * 1024) return D2B_EUNSUPPORTED;
-  D2B_ALLOW_BIG_SMEM(roi_align_bwd_nhwc_kernel);
   dim3 grid(K, d2b_cdiv(C, kNhwcCh));
-  roi_align_bwd_nhwc_kernel<<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, gout);
+  D2B_DISPATCH_DTYPE(g_dt, {
+    D2B_ALLOW_BIG_SMEM(roi_align_bwd_nhwc_kernel<DT>);
+    roi_align_bwd_nhwc_kernel<DT><<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, gout);
+  });
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
@@ -1479,12 +1525,13 @@ static int launch_rot_nhwc(const float* in, float* gin, const float* rois, int K
 // NCHW -> NHWC of every pyramid level in one launch: 32 channels x 64 pixels per CTA through a padded tile.
 struct XposeLevels {
   int num_levels;
-  const float* src[D2B_MAX_LEVELS];
-  float* dst[D2B_MAX_LEVELS];
+  const void* src[D2B_MAX_LEVELS];
+  void* dst[D2B_MAX_LEVELS];
   int HW[D2B_MAX_LEVELS];
   int tile_begin[D2B_MAX_LEVELS + 1];
 };
 
+template <int SDT>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const XposeLevels L, int C) {
   __shared__ float tile[32][65];
   int l = 0;
@@ -1493,15 +1540,17 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const XposeLevels L, 
   const int hw0 = ((int)blockIdx.x - L.tile_begin[l]) * 64;
   const int c0 = blockIdx.y * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* __restrict__ src = L.src[l] + (size_t)blockIdx.z * C * HW;
-  float* __restrict__ dst = L.dst[l] + (size_t)blockIdx.z * HW * C;
+  // source elements of type SDT: for half-precision inputs the layout change doubles as the up-cast
+  const typename Elem<SDT>::T* __restrict__ src =
+      reinterpret_cast<const typename Elem<SDT>::T*>(L.src[l]) + (size_t)blockIdx.z * C * HW;
+  float* __restrict__ dst = reinterpret_cast<float*>(L.dst[l]) + (size_t)blockIdx.z * HW * C;
 #pragma unroll
   for (int r = warp; r < 32; r += 8) {  // read: lanes along the pixels of one channel plane
     const int c = c0 + r;
     const int hwa = hw0 + lane, hwb = hw0 + 32 + lane;
-    const float* __restrict__ p = src + (size_t)min(c, C - 1) * HW;
-    tile[r][lane] = hwa < HW ? __ldg(p + hwa) : 0.f;
-    tile[r][lane + 32] = hwb < HW ? __ldg(p + hwb) : 0.f;
+    const typename Elem<SDT>::T* __restrict__ p = src + (size_t)min(c, C - 1) * HW;
+    tile[r][lane] = hwa < HW ? Elem<SDT>::ld(p + hwa) : 0.f;
+    tile[r][lane + 32] = hwb < HW ? Elem<SDT>::ld(p + hwb) : 0.f;
   }
   __syncthreads();
   // write: 8 lanes x float4 = the 32 channels of one pixel (128 B), 4 pixels per warp instruction; tile pitch 65 and
@@ -1520,6 +1569,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const XposeLevels L, 
 }
 
 // the inverse (gradients accumulated channels-last go back to the reference's NCHW): same tiling, roles swapped
+template <int DDT>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const XposeLevels L, int C) {
   __shared__ float tile[32][65];
   int l = 0;
@@ -1528,8 +1578,9 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const XposeLevels L, 
   const int hw0 = ((int)blockIdx.x - L.tile_begin[l]) * 64;
   const int c0 = blockIdx.y * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* __restrict__ src = L.src[l] + (size_t)blockIdx.z * HW * C;
-  float* __restrict__ dst = L.dst[l] + (size_t)blockIdx.z * C * HW;
+  const float* __restrict__ src = reinterpret_cast<const float*>(L.src[l]) + (size_t)blockIdx.z * HW * C;
+  // destination elements of type DDT: for half-precision gradients the layout change doubles as the down-cast
+  typename Elem<DDT>::T* __restrict__ dst = reinterpret_cast<typename Elem<DDT>::T*>(L.dst[l]) + (size_t)blockIdx.z * C * HW;
   const int cq = tid & 7;
   const int c = c0 + cq * 4;
 #pragma unroll
@@ -1548,10 +1599,10 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const XposeLevels L, 
   for (int r = warp; r < 32; r += 8) {  // write: lanes along the pixels of one channel plane
     const int cc = c0 + r;
     if (cc >= C) continue;
-    float* __restrict__ p = dst + (size_t)cc * HW;
+    typename Elem<DDT>::T* __restrict__ p = dst + (size_t)cc * HW;
     const int hwa = hw0 + lane, hwb = hw0 + 32 + lane;
-    if (hwa < HW) p[hwa] = tile[r][lane];
-    if (hwb < HW) p[hwb] = tile[r][lane + 32];
+    if (hwa < HW) Elem<DDT>::st(p + hwa, tile[r][lane]);
+    if (hwb < HW) Elem<DDT>::st(p + hwb, tile[r][lane + 32]);
   }
 }
 
@@ -1621,18 +1672,25 @@ D2B_API int d2b_roi_pooler_forward(const d2b_pyramid* pyr, int N, int C, const f
   return launch_fwd(P, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
 }
 
-D2B_API int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
-                                        int pooled_w, int sampling_ratio, int aligned, float* out, void* stream) {
+D2B_API int d2b_roi_pooler_forward_nhwc_t(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                          int pooled_w, int sampling_ratio, int aligned, void* out, int out_dtype, void* stream) {
   if (K == 0 || C == 0) return D2B_OK;
   Pyr P;
-  if (!make_pyr(pyr, P) || !rois || !out || N <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0) return D2B_EINVAL;
+  if (!make_pyr(pyr, P) || !rois || !out || N <= 0 || pooled_h <= 0 || pooled_w <= 0 || K < 0 || !dtype_ok(out_dtype))
+    return D2B_EINVAL;
   for (int l = 0; l < P.num_levels; ++l)
     if (!P.feat[l]) return D2B_EINVAL;
-  return launch_fwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream);
+  return launch_fwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, out, (cudaStream_t)stream, out_dtype);
 }
 
-D2B_API int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
-  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0) return D2B_EINVAL;
+D2B_API int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                        int pooled_w, int sampling_ratio, int aligned, float* out, void* stream) {
+  return d2b_roi_pooler_forward_nhwc_t(pyr, N, C, rois, K, pooled_h, pooled_w, sampling_ratio, aligned, out, D2B_F32, stream);
+}
+
+D2B_API int d2b_pyramid_nchw_to_nhwc_t(const d2b_pyramid* pyr, int N, int C, float* const* dst, int src_dtype, void* stream) {
+  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0 || !dtype_ok(src_dtype))
+    return D2B_EINVAL;
   if (N == 0 || C == 0) return D2B_OK;
   if (C % 4 != 0) return D2B_EUNSUPPORTED;
   XposeLevels L = {};
@@ -1650,13 +1708,18 @@ D2B_API int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float
   L.tile_begin[pyr->num_levels] = tiles;
   if (N > 65535 || d2b_cdiv(C, 32) > 65535) return D2B_EUNSUPPORTED;
   dim3 grid(tiles, d2b_cdiv(C, 32), N);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
+  D2B_DISPATCH_DTYPE(src_dtype, (nchw_to_nhwc_kernel<DT><<<grid, 256, 0, (cudaStream_t)stream>>>(L, C)));
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }
 
-D2B_API int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
-  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0) return D2B_EINVAL;
+D2B_API int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
+  return d2b_pyramid_nchw_to_nhwc_t(pyr, N, C, dst, D2B_F32, stream);
+}
+
+D2B_API int d2b_pyramid_nhwc_to_nchw_t(const d2b_pyramid* pyr, int N, int C, void* const* dst, int dst_dtype, void* stream) {
+  if (!pyr || !dst || pyr->num_levels < 1 || pyr->num_levels > D2B_MAX_LEVELS || N < 0 || C < 0 || !dtype_ok(dst_dtype))
+    return D2B_EINVAL;
   if (N == 0 || C == 0) return D2B_OK;
   if (C % 4 != 0) return D2B_EUNSUPPORTED;
   XposeLevels L = {};
@@ -1674,9 +1737,13 @@ D2B_API int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float
   L.tile_begin[pyr->num_levels] = tiles;
   if (N > 65535 || d2b_cdiv(C, 32) > 65535) return D2B_EUNSUPPORTED;
   dim3 grid(tiles, d2b_cdiv(C, 32), N);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, C);
+  D2B_DISPATCH_DTYPE(dst_dtype, (nhwc_to_nchw_kernel<DT><<<grid, 256, 0, (cudaStream_t)stream>>>(L, C)));
   D2B_CHECK_LAUNCH();
   return D2B_OK;
+}
+
+D2B_API int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream) {
+  return d2b_pyramid_nhwc_to_nchw_t(pyr, N, C, reinterpret_cast<void* const*>(dst), D2B_F32, stream);
 }
 
 D2B_API int d2b_roi_align_rotated_forward_nhwc(const float* input, int N, int C, int H, int W, const float* rois, int K,
@@ -1702,10 +1769,11 @@ D2B_API int d2b_roi_align_rotated_backward_nhwc(const float* grad_out, const flo
                                nullptr, (cudaStream_t)stream);
 }
 
-D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
-                                         int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
+D2B_API int d2b_roi_pooler_backward_nhwc_t(const d2b_pyramid* pyr, int N, int C, const void* grad_out, int grad_dtype,
+                                           const float* rois, int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
+                                           void* stream) {
   Pyr P;
-  if (!make_pyr(pyr, P) || N < 0 || C < 0) return D2B_EINVAL;
+  if (!make_pyr(pyr, P) || N < 0 || C < 0 || !dtype_ok(grad_dtype)) return D2B_EINVAL;
   {
     void* zp[D2B_MAX_LEVELS];
     size_t zb[D2B_MAX_LEVELS];
@@ -1719,7 +1787,12 @@ D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, c
   }
   if (K == 0 || C == 0 || N == 0) return D2B_OK;
   if (!grad_out || !rois || pooled_h <= 0 || pooled_w <= 0) return D2B_EINVAL;
-  return launch_bwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, grad_out, (cudaStream_t)stream);
+  return launch_bwd_nhwc(P, N, rois, K, C, pooled_h, pooled_w, sampling_ratio, aligned, grad_out, (cudaStream_t)stream, grad_dtype);
+}
+
+D2B_API int d2b_roi_pooler_backward_nhwc(const d2b_pyramid* pyr, int N, int C, const float* grad_out, const float* rois,
+                                         int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, void* stream) {
+  return d2b_roi_pooler_backward_nhwc_t(pyr, N, C, grad_out, D2B_F32, rois, K, pooled_h, pooled_w, sampling_ratio, aligned, stream);
 }
 
 D2B_API int d2b_roi_align_backward_nhwc(const float* grad_out, const float* rois, int K, float spatial_scale,

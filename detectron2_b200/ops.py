@@ -61,11 +61,17 @@ def _pick_layout(feats, n_out: int) -> str:
 
 
 def _to_nhwc(fs, P, n: int, c: int, device):
-    """One launch: every level of the NCHW pyramid `P` -> freshly allocated NHWC buffers; returns them."""
+    """One launch: every level of the NCHW pyramid `P` (fp32, fp16 or bf16 elements, all levels alike) -> freshly allocated
+    fp32 NHWC buffers; returns them.  For half-precision levels the layout change is also the up-cast."""
     bufs = [torch.empty((t.shape[0], t.shape[2], t.shape[3], t.shape[1]), dtype=torch.float32, device=device) for t in fs]
     dst = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
-    check(_C.lib().d2b_pyramid_nchw_to_nhwc(C.byref(P), n, c, dst, stream_ptr(device)), "pyramid_nchw_to_nhwc")
+    check(_C.lib().d2b_pyramid_nchw_to_nhwc_t(C.byref(P), n, c, dst, _C.DTYPE_CODE[fs[0].dtype], stream_ptr(device)),
+          "pyramid_nchw_to_nhwc")
     return bufs
+
+
+def _same_half_dtype(ts) -> bool:
+    return ts[0].dtype in _HALF and all(t.dtype == ts[0].dtype for t in ts)
 
 
 def pyramid_to_channels_last(feats: List[Tensor]) -> List[Tensor]:
@@ -153,16 +159,18 @@ def _bwd_layout(shapes_nchw, n_out: int, channels_last: bool) -> str:
     return "xpose" if n_out * _NHWC_BWD_PS_PER_OUT + feat_bytes * _XPOSE_PS_PER_BYTE < n_out * _NCHW_BWD_PS_PER_OUT else "nchw"
 
 
-def _from_nhwc(bufs, n: int, c: int, device):
-    """One launch: NHWC buffers -> freshly allocated NCHW tensors."""
-    outs = [torch.empty((b.shape[0], b.shape[3], b.shape[1], b.shape[2]), dtype=torch.float32, device=device) for b in bufs]
+def _from_nhwc(bufs, n: int, c: int, device, dtype=torch.float32):
+    """One launch: fp32 NHWC buffers -> freshly allocated NCHW tensors of `dtype` (fp32, or fp16 / bf16: the layout change
+    is also the down-cast of the gradients of half-precision features)."""
+    outs = [torch.empty((b.shape[0], b.shape[3], b.shape[1], b.shape[2]), dtype=dtype, device=device) for b in bufs]
     P = _C.Pyramid()
     P.num_levels = len(bufs)
     for l, b in enumerate(bufs):
         P.feat[l] = b.data_ptr()
         P.H[l], P.W[l] = b.shape[1], b.shape[2]
     dst = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-    check(_C.lib().d2b_pyramid_nhwc_to_nchw(C.byref(P), n, c, dst, stream_ptr(device)), "pyramid_nhwc_to_nchw")
+    check(_C.lib().d2b_pyramid_nhwc_to_nchw_t(C.byref(P), n, c, dst, _C.DTYPE_CODE[dtype], stream_ptr(device)),
+          "pyramid_nhwc_to_nchw")
     return outs
 
 
@@ -235,32 +243,39 @@ def roi_pooler_op(feats: List[Tensor], rois: Tensor, scales: List[float], pooled
     _C.require_cuda(rois, *feats)
     if len(feats) < 1 or len(feats) > _C.MAX_LEVELS or len(feats) != len(scales):
         raise RuntimeError("roi_pooler: need 1..%d feature levels with one scale each" % _C.MAX_LEVELS)
-    fs = [t.to(dtype=torch.float32) for t in feats]
     r_lvl = _f32c(rois)
     # half-precision feature maps: the reference samples with the rois cast to the feature dtype (layers/roi_align.py:60,
     # then torchvision's autocast wrapper upcasts both) while the FPN level comes from the fp32 boxes (poolers.py:245)
     half = feats[0].dtype in _HALF
     r = r_lvl.to(feats[0].dtype).to(torch.float32) if half else r_lvl
-    n, c = fs[0].shape[:2]
+    n, c = feats[0].shape[:2]
     k = r.shape[0]
-    out = torch.empty((k, c, pooled_h, pooled_w), dtype=torch.float32, device=r.device)
-    if out.numel():
-        layout = _pick_layout(fs, out.numel())
-        args = (n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio, int(aligned), ptr(out), stream_ptr(r.device))
+    numel = k * c * pooled_h * pooled_w
+    layout = _pick_layout(feats, numel) if numel else "nchw"
+    # half-precision NCHW levels: the layout-change launch reads them as they are (it is also the up-cast) and the pooling
+    # kernel writes the result in their dtype -- no cast passes; every other combination computes on fp32 copies
+    fused_half = layout == "xpose" and _same_half_dtype(feats)
+    fs = list(feats) if fused_half else [t.to(dtype=torch.float32) for t in feats]
+    out_dt = feats[0].dtype if (layout != "nchw" and feats[0].dtype in _C.DTYPE_CODE) else torch.float32
+    out = torch.empty((k, c, pooled_h, pooled_w), dtype=out_dt, device=r.device)
+    if numel:
         with torch.cuda.device(r.device):
             if layout != "cl":
                 fs = [t.contiguous() for t in fs]
             # channels_last tensors: same logical shape, NHWC storage -- _pyramid only takes pointers and H, W
             P = _pyramid(fs, None, scales, min_level, max_level, canonical_level, canonical_box_size, r_lvl if half else None)
             if layout == "nchw":
-                check(_C.lib().d2b_roi_pooler_forward(C.byref(P), *args), "roi_pooler_forward")
+                check(_C.lib().d2b_roi_pooler_forward(C.byref(P), n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio,
+                                                      int(aligned), ptr(out), stream_ptr(r.device)), "roi_pooler_forward")
             else:
                 if layout == "xpose":
                     bufs = _to_nhwc(fs, P, n, c, r.device)
                     for l, b in enumerate(bufs):
                         P.feat[l] = b.data_ptr()
-                check(_C.lib().d2b_roi_pooler_forward_nhwc(C.byref(P), *args), "roi_pooler_forward_nhwc")
-    return out.to(feats[0].dtype)
+                check(_C.lib().d2b_roi_pooler_forward_nhwc_t(C.byref(P), n, c, ptr(r), k, pooled_h, pooled_w, sampling_ratio,
+                                                             int(aligned), ptr(out), _C.DTYPE_CODE[out_dt],
+                                                             stream_ptr(r.device)), "roi_pooler_forward_nhwc")
+    return out if out.dtype == feats[0].dtype else out.to(feats[0].dtype)
 
 
 @roi_pooler_op.register_fake
@@ -273,36 +288,48 @@ def _(feats, rois, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_leve
 def roi_pooler_backward_op(grad: Tensor, rois: Tensor, shapes: List[int], scales: List[float], pooled_h: int,
                            pooled_w: int, sampling_ratio: int, aligned: bool, min_level: int, max_level: int,
                            canonical_level: int, canonical_box_size: float,
-                           channels_last: bool = False, level_rois: Optional[Tensor] = None) -> List[Tensor]:
+                           channels_last: bool = False, level_rois: Optional[Tensor] = None,
+                           half_grads: bool = False) -> List[Tensor]:
     """`level_rois`: the fp32 boxes the FPN level was assigned from when `rois` are the feature-dtype-rounded ones the forward
-    sampled with (half-precision features, see roi_pooler_op)."""
+    sampled with (half-precision features, see roi_pooler_op).  `half_grads`: return NCHW gradients in `grad`'s fp16 / bf16
+    dtype (written by the layout-change launch) instead of fp32."""
     _C.require_cuda(grad, rois, level_rois)
-    g, r = _f32c(grad), _f32c(rois)
+    r = _f32c(rois)
     lr = _f32c(level_rois)
     nl = len(scales)
     n, c = shapes[0], shapes[1]
     hw = [(shapes[2 + 2 * l], shapes[3 + 2 * l]) for l in range(nl)]
-    layout = _bwd_layout([(n, c, h, w) for (h, w) in hw], g.numel(), channels_last) if n * c else "nchw"
-    pargs = (n, c, ptr(g), ptr(r), r.shape[0], pooled_h, pooled_w, sampling_ratio, int(aligned), stream_ptr(g.device))
+    layout = _bwd_layout([(n, c, h, w) for (h, w) in hw], grad.numel(), channels_last) if n * c else "nchw"
+    # the channels-last kernel reads fp16 / bf16 gradients in place; the NCHW kernel takes fp32
+    g = grad.contiguous() if (layout != "nchw" and grad.dtype in _C.DTYPE_CODE) else _f32c(grad)
     with torch.cuda.device(g.device):
         if layout == "nchw":
             grads = [torch.empty((n, c, h, w), dtype=torch.float32, device=g.device) for (h, w) in hw]
             P = _pyramid(grads, grads, scales, min_level, max_level, canonical_level, canonical_box_size, lr)
-            check(_C.lib().d2b_roi_pooler_backward(C.byref(P), *pargs), "roi_pooler_backward")
+            check(_C.lib().d2b_roi_pooler_backward(C.byref(P), n, c, ptr(g), ptr(r), r.shape[0], pooled_h, pooled_w,
+                                                   sampling_ratio, int(aligned), stream_ptr(g.device)), "roi_pooler_backward")
         else:
             bufs = [torch.empty((n, h, w, c), dtype=torch.float32, device=g.device) for (h, w) in hw]
             views = [b.permute(0, 3, 1, 2) for b in bufs]  # logical NCHW shape: _pyramid reads H, W from dims 2, 3
             P = _pyramid(views, views, scales, min_level, max_level, canonical_level, canonical_box_size, lr)
-            check(_C.lib().d2b_roi_pooler_backward_nhwc(C.byref(P), *pargs), "roi_pooler_backward_nhwc")
-            grads = views if layout == "cl" else _from_nhwc(bufs, n, c, g.device)
+            check(_C.lib().d2b_roi_pooler_backward_nhwc_t(C.byref(P), n, c, ptr(g), _C.DTYPE_CODE[g.dtype], ptr(r), r.shape[0],
+                                                          pooled_h, pooled_w, sampling_ratio, int(aligned),
+                                                          stream_ptr(g.device)), "roi_pooler_backward_nhwc")
+            if layout == "cl":
+                grads = views
+            else:
+                grads = _from_nhwc(bufs, n, c, g.device, grad.dtype if (half_grads and grad.dtype in _HALF) else torch.float32)
+    if half_grads and grad.dtype in _HALF:
+        grads = [t if t.dtype == grad.dtype else t.to(grad.dtype) for t in grads]
     return grads
 
 
 @roi_pooler_backward_op.register_fake
 def _(grad, rois, shapes, scales, pooled_h, pooled_w, sampling_ratio, aligned, min_level, max_level, canonical_level,
-      canonical_box_size, channels_last=False, level_rois=None):
+      canonical_box_size, channels_last=False, level_rois=None, half_grads=False):
     n, c = shapes[0], shapes[1]
-    outs = [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l])) for l in range(len(scales))]
+    dt = grad.dtype if half_grads else torch.float32
+    outs = [grad.new_empty((n, c, shapes[2 + 2 * l], shapes[3 + 2 * l]), dtype=dt) for l in range(len(scales))]
     return [o.contiguous(memory_format=torch.channels_last) for o in outs] if channels_last else outs
 
 
@@ -321,7 +348,8 @@ def _pooler_bwd(ctx, grad):
     shapes, scales, ph, pw, sr, aligned, lo, hi, cl, cs, dts, chl = ctx.args
     half = dts[0] in _HALF  # same rois as the forward: rounded to the feature dtype for sampling, fp32 for the level
     grads = roi_pooler_backward_op(grad, rois.to(dts[0]).to(torch.float32) if half else rois, shapes, scales, ph, pw, sr,
-                                   aligned, lo, hi, cl, cs, chl, rois if half else None)
+                                   aligned, lo, hi, cl, cs, chl, rois if half else None,
+                                   half and grad.dtype == dts[0] and all(d == dts[0] for d in dts))
     return [g.to(dt) for g, dt in zip(grads, dts)], None, None, None, None, None, None, None, None, None, None
 
 
@@ -621,15 +649,19 @@ def _dcn_train_layout(x: Tensor, p, precision: int):
     """(x for the kernel, flags, saved channels-last copy or None, cols or None).  When the tensor-core kernels take the
     shape in both directions, x is laid out channels-last ONCE (our layout kernel) and that copy serves the forward and both
     gradient kernels; the forward also keeps its sampled columns for the weight gradient."""
-    xf = x.to(dtype=torch.float32)
     lib = _C.lib()
     if precision != 0 and lib.d2b_deform_conv_tc_shape_supported(C.byref(p), 0) and \
-            lib.d2b_deform_conv_tc_shape_supported(C.byref(p), 1) and xf.numel():
-        if _is_channels_last(xf) and xf.data_ptr() % 16 == 0:
+            lib.d2b_deform_conv_tc_shape_supported(C.byref(p), 1) and x.numel():
+        xf = x.to(dtype=torch.float32) if (_is_channels_last(x) or x.dtype not in _C.DTYPE_CODE) else None
+        if xf is not None and _is_channels_last(xf) and xf.data_ptr() % 16 == 0:
             xs = None
             xk = xf
         else:
-            xs = pyramid_to_channels_last([xf.detach().contiguous()])[0]
+            # NCHW fp32 / fp16 / bf16 -> fp32 channels-last in ONE launch (for half inputs it is also the up-cast)
+            src = (xf if xf is not None else x).detach().contiguous()
+            with torch.cuda.device(x.device):
+                buf = _to_nhwc([src], _pyramid([src], None, [1.0], 0, 0, 0, 1.0), src.shape[0], src.shape[1], x.device)[0]
+            xs = buf.permute(0, 3, 1, 2)
             xk = xs
         if _is_channels_last(xk) and xk.data_ptr() % 16 == 0:
             nb = lib.d2b_deform_conv_cols_bytes(C.byref(p), precision)
@@ -674,9 +706,14 @@ def _dcnt_setup(ctx, inputs, output):
     ctx.save_for_backward(x if xs.numel() == 0 else xs, offset, mask, weight, cols)
     ctx.args = (stride, padding, dilation, groups, dg, bias is not None, precision, x.dtype)
     ctx.has_mask = mask is not None
+    # the saved copy of x and the column tiles are outputs only so that autograd can keep them: nobody differentiates through
+    # them, and materialising their (zero) gradients would fill 155 MB per res3 layer in every backward
+    ctx.set_materialize_grads(False)
 
 
 def _dcnt_bwd(ctx, grad, _gxs, _gcols):
+    if grad is None:
+        return (None,) * 11
     x, offset, mask, weight, cols = ctx.saved_tensors
     stride, padding, dilation, groups, dg, with_bias, precision, xdtype = ctx.args
     need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ctx.has_mask and ctx.needs_input_grad[2])
@@ -833,9 +870,12 @@ def _dcnft_setup(ctx, inputs, output):
     y, xs, cols = output
     ctx.save_for_backward(x if xs.numel() == 0 else xs, offset_mask, weight, scale, y, cols)
     ctx.args = (relu, stride, padding, dilation, groups, dg, 1 if precision == -1 else precision, x.dtype)
+    ctx.set_materialize_grads(False)  # see _dcnt_setup
 
 
 def _dcnft_bwd(ctx, grad, _gxs, _gcols):
+    if grad is None:
+        return (None,) * 12
     x, offset_mask, weight, scale, y, cols = ctx.saved_tensors
     relu, stride, padding, dilation, groups, dg, precision, xdtype = ctx.args
     gx, gom, gw = deform_conv_fused_backward_op(x, offset_mask, weight, scale, relu, y, grad, stride, padding, dilation,

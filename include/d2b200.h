@@ -92,6 +92,23 @@ int d2b_roi_pooler_forward_nhwc(const d2b_pyramid* pyr, int N, int C, const floa
 int d2b_pyramid_nchw_to_nhwc(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream);
 /* The inverse: pyr->feat[l] [N,H,W,C] -> dst[l] [N,C,H,W], one launch. */
 int d2b_pyramid_nhwc_to_nchw(const d2b_pyramid* pyr, int N, int C, float* const* dst, void* stream);
+/* Half-precision activations / gradients (dtype codes below): the same kernels read or write fp16 / bf16 elements in place
+ * of fp32 ones -- fp32 arithmetic, no separate cast pass.  The reference up-casts such tensors before its fp32 kernels
+ * (torchvision's autocast wrapper of roi_align; layers/roi_align_rotated.py:81-83) and casts the result back.
+ *   d2b_pyramid_nchw_to_nhwc_t   pyr->feat[l] point to [N,C,H,W] elements of `src_dtype`; dst[l] are fp32 [N,H,W,C]
+ *   d2b_pyramid_nhwc_to_nchw_t   pyr->feat[l] fp32 [N,H,W,C]; dst[l] [N,C,H,W] elements of `dst_dtype`
+ *   d2b_roi_pooler_forward_nhwc_t    out [K,C,PH,PW] elements of `out_dtype`
+ *   d2b_roi_pooler_backward_nhwc_t   grad_out [K,C,PH,PW] elements of `grad_dtype`; pyr->grad[l] stay fp32 (accumulators) */
+#define D2B_F32 0
+#define D2B_F16 1
+#define D2B_BF16 2
+int d2b_pyramid_nchw_to_nhwc_t(const d2b_pyramid* pyr, int N, int C, float* const* dst, int src_dtype, void* stream);
+int d2b_pyramid_nhwc_to_nchw_t(const d2b_pyramid* pyr, int N, int C, void* const* dst, int dst_dtype, void* stream);
+int d2b_roi_pooler_forward_nhwc_t(const d2b_pyramid* pyr, int N, int C, const float* rois, int K, int pooled_h,
+                                  int pooled_w, int sampling_ratio, int aligned, void* out, int out_dtype, void* stream);
+int d2b_roi_pooler_backward_nhwc_t(const d2b_pyramid* pyr, int N, int C, const void* grad_out, int grad_dtype,
+                                   const float* rois, int K, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
+                                   void* stream);
 /* Channels-last backward (autograd of the two forwards above): grad_in / pyr->grad[l] are [N,H,W,C] fp32, 16-byte aligned,
  * fully written (zero-filled inside, then accumulated with one 128-bit vector reduction per footprint pixel and 4 channels).
  * grad_out stays [K,C,PH,PW].  Same results contract as d2b_roi_align_backward / d2b_roi_pooler_backward. */

@@ -647,13 +647,18 @@ def test_roi_pooler_nhwc_paths_vs_reference_loop(mode, monkeypatch):
     assert ok, err
 
 
+@pytest.mark.parametrize("layout", ["auto", "nhwc"])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_half_precision_inputs_through_the_public_api(L, dt):
+def test_half_precision_inputs_through_the_public_api(L, dt, layout, monkeypatch):
     """bf16 / fp16 activations (what autocast training hands the ops; the reference upcasts them, roi_align_rotated.py:81-83,
     torchvision's autocast wrapper): fp32 arithmetic on the stored values, results and gradients returned in the input dtype.
     Oracle = the fp32 op on the same (half-representable) values; tolerance = the rounding of the returned dtype."""
+    from detectron2_b200 import ops
     from detectron2_b200.poolers import ROIPooler
 
+    # "nhwc": the layout-change launches read / write the half tensors directly (fused casts) and the channels-last kernels take
+    # half gradients and write half outputs; "auto" picks the NCHW kernels for a call of this size (fp32 copies)
+    monkeypatch.setattr(ops, "POOLER_LAYOUT", layout)
     g = torch.Generator().manual_seed(3)
     eps = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
     scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]

@@ -19,16 +19,23 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--autograd", action="store_true", help="the public-API + torch.autograd step of the end-to-end measurement")
+    ap.add_argument("--bf16", action="store_true", help="activations / gradients in bf16 (the end-to-end transport)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     r = bench.TrainRunner(dev)
-    d = r.to_device(bench.make_train_inputs(0))
+    h = bench.make_train_inputs(0)
+    if a.bf16:
+        to_half = lambda t: t.to(torch.bfloat16) if t.is_floating_point() else t  # noqa: E731
+        h = {k: bench.map_tensors({k: v}, to_half if k in bench.E2E_HALF_KEYS else (lambda t: t))[k] for k, v in h.items()}
+    d = r.to_device(h)
+    step = (lambda d: r.step_autograd(d, True)) if a.autograd else r.step
     for _ in range(2):
-        r.step(d)
+        step(d)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(a.iters):
-            r.step(d)
+            step(d)
         torch.cuda.synchronize()
     tot = collections.OrderedDict()
     for e in prof.events():
