@@ -120,6 +120,12 @@ def tensors_of(d):
                     yield from t
 
 
+# constants read off the committed ncu --set full capture of this step (profiles/r2_ncu_full.txt); sm__pipe_tensor_cycles_active
+# per kernel, res3 (C=128) / res4 (C=256) / res5 (C=512) layers
+R2_NCU = {"bwd_pair_dram_bytes": 57178624 + 99328 + 172992256 + 4922624,
+          "tensor_pipe_active_pct": {"dcn_fwd_tc_kernel": [16.0, 32.4, 40.0], "dcn_bwd_data_tc_kernel": [8.8, 17.5, 31.8],
+                                     "dcn_bwd_weight_cols_kernel": [44.6, 47.8, 51.2]}}
+
 E2E_HALF_KEYS = ("feats", "go_box", "go_mask", "dc_x", "dc_off", "dc_go")  # activations / gradients: bf16 under autocast
 
 
@@ -806,7 +812,11 @@ def main():
                              % (IMGS_PER_GPU * h * w * 9 * c * 16 / 1e6),
                      "algorithmic_bytes": dconv_bwd_algorithmic_bytes(c, h, w, IMGS_PER_GPU),
                      "achieved_hbm_gbs": gbs(dconv_bwd_algorithmic_bytes(c, h, w, IMGS_PER_GPU), bwd_ms),
-                     "traffic": None},
+                     # DRAM bytes of the two kernels from the committed capture (profiles/r2_ncu_full.txt, launches 11 + 12:
+                     # dcn_bwd_data_tc_kernel 57.2 + 0.1 MB, dcn_bwd_weight_cols_kernel 173.0 + 4.9 MB -- the latter streams the
+                     # forward's saved columns back, 155 MB by design, instead of sampling x a second time)
+                     "traffic": R2_NCU["bwd_pair_dram_bytes"],
+                     "tensor_pipe_active_pct_ncu": R2_NCU["tensor_pipe_active_pct"]},
         "roofline_other": {
             "roi_align_fwd_box_pooler": {"bound": "hbm", "algorithmic_bytes": box_alg_f, "avg_launch_ms": stage_ms["box_pool_fwd"],
                                          "achieved": gbs(box_alg_f, stage_ms["box_pool_fwd"]), "peak": hbm, "unit": "GB/s",

@@ -1164,11 +1164,11 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 // Per-sample scatter (taps on the fly, one red.v4 per tap): pooled sizes > 16 and footprints wider than the column table.
 template <int GDT>
 __device__ void bwd_nhwc_per_sample(const RoiGeom& g, const typename Elem<GDT>::T* __restrict__ go, float* __restrict__ gimg,
-                                    int H, int W, int C, int PH, int PW, bool lane_live) {
+                                    int H, int W, int C, int PH, int PW, bool lane_live, int ph0, int PHl) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int bins = PH * PW;
-  for (int bin = warp; bin < bins; bin += nwarps) {
-    const int ph = bin / PW, pw = bin - ph * PW;
+  for (int bl = warp; bl < PHl * PW; bl += nwarps) {  // the CTA's bin rows [ph0, ph0 + PHl)
+    const int ph = ph0 + bl / PW, pw = bl - (ph - ph0) * PW, bin = ph * PW + pw;
     float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane_live) {
       const typename Elem<GDT>::T* q = go + (size_t)(lane * 4) * bins + bin;
@@ -1192,7 +1192,7 @@ __device__ void bwd_nhwc_per_sample(const RoiGeom& g, const typename Elem<GDT>::
 
 template <int GDT>
 __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C,
-                                                                       int PH, int PW, int sr, int aligned,
+                                                                       int PH, int PW, int sr, int aligned, int rows_per_cta,
                                                                        const void* __restrict__ gout) {
   extern __shared__ __align__(16) float gs[];  // [bin][128 ch], float4 slots XOR-swizzled with the bin index
   __shared__ float WyT[kBwdBand * kMaxP];      // [row of the band][ph]
@@ -1210,6 +1210,9 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
   const int H = P.H[lvl], W = P.W[lvl];
   const int bins = PH * PW;
+  // bin rows [ph0, ph0 + PHl) of the RoI: a 14x14 mask-head tile (157 KB of shared memory, one CTA per SM) is split over
+  // grid.z so that several CTAs share an SM; rows shared by two CTAs' footprints simply receive both contributions
+  const int ph0 = blockIdx.z * rows_per_cta, PHl = min(rows_per_cta, PH - ph0), bins_l = PHl * PW;
   const int ncta = min(kNhwcCh, C - c0);
   const bool lane_live = lane * 4 < ncta;
   if (tid == 0) {
@@ -1224,14 +1227,14 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const typename Elem<GDT>::T* __restrict__ go = reinterpret_cast<const typename Elem<GDT>::T*>(gout) + ((size_t)k * C + c0) * bins;
 
   if (PH > kMaxP || PW > kMaxP) {  // pooled size beyond the tables: per-sample path
-    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live);
+    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live, ph0, PHl);
     return;
   }
   // ---- footprint bounds (rows / columns that receive a non-zero weight)
-  if (tid < PH) {
+  if (tid < PHl) {
     int lo = 1 << 30, hi = -1;
     for (int iy = 0; iy < g.gh; ++iy) {
-      const Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+      const Tap1 t = make_tap1(g.start_h + (float)(ph0 + tid) * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
       if (t.wl != 0.f) { lo = min(lo, t.lo); hi = max(hi, t.lo); }
       if (t.wh != 0.f) { lo = min(lo, t.hi); hi = max(hi, t.hi); }
     }
@@ -1256,7 +1259,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int xmin = s_xmin, fw = s_xmax - s_xmin + 1, ymin = s_ymin, ymax = s_ymax;
   if (s_xmax < 0 || ymax < 0) return;  // no sample inside the map: zero gradient
   if (fw > kBwdMaxFw) {  // very wide footprint (block-uniform)
-    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live);
+    bwd_nhwc_per_sample<GDT>(g, go, gimg, H, W, C, PH, PW, lane_live, ph0, PHl);
     return;
   }
   // ---- column table + gradient tile
@@ -1270,9 +1273,10 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
       if (t.wh != 0.f) WxT[(t.hi - xmin) * kMaxP + pw] += t.wh;
     }
   }
-  for (int e = tid; e < ncta * bins; e += kBwdThreads) {  // coalesced read of [ch][bin], transposed + swizzled store
-    const int c = e / bins, bin = e - c * bins;
-    gs[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] = Elem<GDT>::ld(go + e) * g.inv_count;
+  for (int e = tid; e < ncta * bins_l; e += kBwdThreads) {  // coalesced read of [ch][bin], transposed + swizzled store
+    const int c = e / bins_l, bin = e - c * bins_l;             // bin: index inside the CTA's rows
+    gs[bin * kNhwcCh + ((((c >> 2) ^ bin) & 31) << 2) + (c & 3)] =
+        Elem<GDT>::ld(go + (size_t)c * bins + ph0 * PW + bin) * g.inv_count;
   }
   __syncthreads();
   for (int x = tid; x < fw; x += kBwdThreads) {
@@ -1293,16 +1297,16 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
     colE[x] = make_float4(__int_as_float(ia), __int_as_float(ib), wa, wb);
     if (cnt > 2) atomicOr(&s_wide, 1);
   }
-  float* __restrict__ Ts = gs + (size_t)bins * kNhwcCh + (size_t)warp * PW * kNhwcCh;  // this warp's row-collapsed gradients
+  float* __restrict__ Ts = gs + (size_t)bins_l * kNhwcCh + (size_t)warp * PW * kNhwcCh;  // this warp's row-collapsed gradients
   // ---- bands of footprint rows
   for (int yb = ymin; yb <= ymax; yb += kBwdBand) {
     const int nrow = min(kBwdBand, ymax - yb + 1);
     __syncthreads();  // previous band consumed
     for (int i = tid; i < nrow * kMaxP; i += kBwdThreads) WyT[i] = 0.f;
     __syncthreads();
-    if (tid < PH) {
+    if (tid < PHl) {
       for (int iy = 0; iy < g.gh; ++iy) {
-        const Tap1 t = make_tap1(g.start_h + (float)tid * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
+        const Tap1 t = make_tap1(g.start_h + (float)(ph0 + tid) * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.gh, H);
         if (t.wl != 0.f && t.lo >= yb && t.lo < yb + nrow) WyT[(t.lo - yb) * kMaxP + tid] += t.wl;
         if (t.wh != 0.f && t.hi >= yb && t.hi < yb + nrow) WyT[(t.hi - yb) * kMaxP + tid] += t.wh;
       }
@@ -1311,7 +1315,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
     for (int y = tid; y < nrow; y += kBwdThreads) {
       int lo = 255, hi = 0, cnt = 0, ia = 0, ib = 0;
       float wa = 0.f, wb = 0.f;
-      for (int ph = 0; ph < PH; ++ph) {
+      for (int ph = 0; ph < PHl; ++ph) {
         const float w = WyT[y * kMaxP + ph];
         if (w != 0.f) {
           lo = min(lo, ph);
@@ -1399,13 +1403,20 @@ static int launch_bwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   for (int l = 0; l < P.num_levels; ++l)
     if ((reinterpret_cast<uintptr_t>(P.grad[l]) & 15) != 0) return D2B_EINVAL;
   (void)N;
-  // gradient tile [bins][128] + per-warp row-collapsed tile [8 warps][PW][128]
-  const size_t smem = sizeof(float) * kNhwcCh * ((size_t)PH * PW + (size_t)(kBwdThreads / 32) * PW);
+  // bin rows per CTA: all of them, unless that leaves fewer than ~2 CTAs per SM resident (shared memory) AND in the grid
+  const int slabs = d2b_cdiv(C, kNhwcCh);
+  int rows = PH;
+  auto smem_of = [&](int r) { return sizeof(float) * kNhwcCh * ((size_t)r * PW + (size_t)(kBwdThreads / 32) * PW); };
+  while (rows > 4 && (smem_of(rows) > 100 * 1024 || (long long)K * slabs * d2b_cdiv(PH, rows) < 4LL * kNumSMs) &&
+         smem_of(rows) > 56 * 1024)
+    rows = (rows + 1) / 2;
+  // gradient tile [rows * PW][128] + per-warp row-collapsed tile [8 warps][PW][128]
+  const size_t smem = smem_of(rows);
   if (smem > 180 * 1024) return D2B_EUNSUPPORTED;
-  dim3 grid(K, d2b_cdiv(C, kNhwcCh));
+  dim3 grid(K, slabs, d2b_cdiv(PH, rows));
   D2B_DISPATCH_DTYPE(g_dt, {
     D2B_ALLOW_BIG_SMEM(roi_align_bwd_nhwc_kernel<DT>);
-    roi_align_bwd_nhwc_kernel<DT><<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, gout);
+    roi_align_bwd_nhwc_kernel<DT><<<grid, kBwdThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, rows, gout);
   });
   D2B_CHECK_LAUNCH();
   return D2B_OK;
