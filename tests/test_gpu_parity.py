@@ -251,6 +251,29 @@ def test_batched_nms_100k_stress_one_call(L):
     assert torch.equal(got, ki[scores[ki].sort(descending=True, stable=True)[1]])
 
 
+def test_batched_nms_of_several_images_in_one_call(L):
+    """`batched_nms_images_fixed`: the per-image batched_nms of N images as ONE NMS call -- same kept indices per image, in
+    the same order, as N separate calls (and as the oracle), torchvision's per-image coordinate offsets included."""
+    g = torch.Generator().manual_seed(5)
+    n, m = 3, 3000
+    boxes, scores = [], []
+    for i in range(n):
+        ctr = torch.rand(m, 2, generator=g) * torch.tensor([1333.0 * (1 + i), 800.0])  # different max coordinate per image
+        wh = 8 + torch.rand(m, 2, generator=g) * 200
+        boxes.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+        scores.append((torch.rand(m, generator=g) * 256).round() / 256)  # ties
+    idxs = torch.randint(0, 5, (m,), generator=g)
+    keep, num = L.batched_nms_images_fixed([b.to(DEV) for b in boxes], [s.to(DEV) for s in scores], idxs.to(DEV), 0.7, 5,
+                                           max_segment=m)
+    kept = keep[: int(num.item())].cpu()
+    assert (keep[int(num.item()):] == 0).all()
+    for i in range(n):
+        mine = kept[(kept >= i * m) & (kept < (i + 1) * m)] - i * m
+        ref = orc.batched_nms(boxes[i], scores[i], idxs, 0.7)
+        assert torch.equal(mine, ref), i
+        assert torch.equal(mine, L.batched_nms(boxes[i].to(DEV), scores[i].to(DEV), idxs.to(DEV), 0.7).cpu()), i
+
+
 def test_nms_ignored_slots_padding_and_category_bound():
     from detectron2_b200 import ops
 
