@@ -18,7 +18,6 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -903,10 +902,10 @@ __device__ __forceinline__ void nhwc_unit(const char* __restrict__ base, const C
 }
 
 // 4 CTAs x 7 warps per SM at 72 registers: measured faster than 3 CTAs at 80 (95 vs 97 us on the box-head call)
-template <bool WIDE, int ODT>
-__global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
+template <int ODT>
+__global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const Pyr P, const float* __restrict__ rois, int C, int PH,
                                                              int PW, int sr, int aligned, int chunk, int chunk_pad,
-                                                             int allow_shared, void* __restrict__ out_v) {
+                                                             void* __restrict__ out_v) {
   extern __shared__ __align__(16) float otile[];  // [4 (channel of the quad)][32 (lane)][chunk_pad]
   __shared__ CTap ytab[kMaxE * kMaxP];            // [tap][ph]
   __shared__ CTap xtab[kMaxE * kMaxP];            // [tap][pw]
@@ -1041,7 +1040,7 @@ __global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_ker
     const int bin0 = blockIdx.z * chunk;  // one output chunk per CTA
     const int nb = min(chunk, bins - bin0);
     // column-shared path: pooled widths that split into units of 7 bins (7x7 box head, 14x14 mask head), chunks of whole units
-    const bool shared_cols = allow_shared && !onfly && s_colok && s_nymax <= 6 && PW % 7 == 0 && chunk % 7 == 0;
+    const bool shared_cols = !onfly && s_colok && s_nymax <= 6 && PW % 7 == 0 && chunk % 7 == 0;
     if (shared_cols) {
       const float inv_count = sg.inv_count;
       for (int u = warp; u * 7 < nb; u += nwarps) {
@@ -1060,9 +1059,9 @@ __global__ void __launch_bounds__(kNhwcThreads, WIDE ? 3 : 4) roi_align_nhwc_ker
         const CTap* __restrict__ yt0 = ytab + ph;
         switch (ry) {
           case 1: nhwc_unit<1, 4>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
-          case 2: nhwc_unit<2, WIDE ? 4 : 3>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 2: nhwc_unit<2, 3>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
           case 3: nhwc_unit<3, 2>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
-          case 4: nhwc_unit<4, WIDE ? 2 : 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
+          case 4: nhwc_unit<4, 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
           case 5: nhwc_unit<5, 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
           default: nhwc_unit<6, 1>(base_b, yt0, ny, nch, colE, cb, ce, skip, o, chunk_pad, inv_count); break;
         }
@@ -1133,14 +1132,9 @@ static int launch_fwd_nhwc(const Pyr& P, int N, const float* rois, int K, int C,
   const size_t smem = sizeof(float) * 128 * (size_t)chunk_pad;
   if (nchunks > 65535) return D2B_EUNSUPPORTED;
   dim3 grid(K, slabs, nchunks);
-  // tuning knob (measurement only): 0 = column-shared path, 4 CTAs / SM (default); 1 = column-shared, 3 CTAs / SM with wider
-  // load batches; 2 = per-bin loop only
-  static const int mode = [] { const char* e = getenv("D2B_NHWC_MODE"); return e ? atoi(e) : 0; }();
-  if (mode == 1)
-    roi_align_nhwc_kernel<true, D2B_F32><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, 1, out);
-  else
-    D2B_DISPATCH_DTYPE(out_dt, (roi_align_nhwc_kernel<false, DT><<<grid, kNhwcThreads, smem, stream>>>(
-                                   P, rois, C, PH, PW, sr, aligned, chunk, chunk_pad, mode == 2 ? 0 : 1, out)));
+  // (the per-bin loop alone and a 3-CTA / wider-batch variant were measured against this: profiles/r2_pooler_fwd_ab.md)
+  D2B_DISPATCH_DTYPE(out_dt, (roi_align_nhwc_kernel<DT><<<grid, kNhwcThreads, smem, stream>>>(P, rois, C, PH, PW, sr, aligned, chunk,
+                                                                                            chunk_pad, out)));
   D2B_CHECK_LAUNCH();
   return D2B_OK;
 }

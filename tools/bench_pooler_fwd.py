@@ -1,6 +1,7 @@
 """A/B timing of the channels-last ROIPooler forward (box head 1024 RoIs 7x7, mask head 256 RoIs 14x14, cfg1 single level) in
-CUDA graphs with rotating inputs.  The kernel variant comes from D2B_NHWC_MODE (read once per process): run once per mode.
-    D2B_NHWC_MODE=0|1|2 python tools/bench_pooler_fwd.py
+CUDA graphs with rotating inputs.  (profiles/r2_pooler_fwd_ab.md was taken with a build that selected the kernel variant
+through an environment knob; the shipped kernel chooses per RoI.)
+    python tools/bench_pooler_fwd.py
 """
 import json
 import os
@@ -21,7 +22,7 @@ def main():
     devin = [runner.to_device(h) for h in host]
     cls = [ops.pyramid_to_channels_last(d["feats"]) for d in devin]
     side = torch.cuda.Stream()
-    res = {"mode": os.environ.get("D2B_NHWC_MODE", "0")}
+    res = {}
     # cfg1: 512 boxes over one 1x256x200x304 map (channels_last), sr = 0 and 2
     g = torch.Generator().manual_seed(0)
     x = [torch.rand(1, 256, 200, 304, generator=g).to(dev).contiguous(memory_format=torch.channels_last) for _ in range(2)]
