@@ -9,6 +9,8 @@ timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 400 python bench.py 2> gpurun_out/bench.err | tail -1 > gpurun_out/bench_n1.json; echo "bench rc=$?"
 timeout 400 python bench.py --impl reference 2> gpurun_out/bench_ref.err | tail -1 > gpurun_out/bench_ref_n1.json; echo "bench ref rc=$?"
 timeout 120 python tools/kernel_times.py > gpurun_out/kernel_times.txt 2>/dev/null; echo "kernel_times rc=$?"
+timeout 120 python tools/kernel_times.py --autograd --bf16 > gpurun_out/kernel_times_autograd_bf16.txt 2>/dev/null; echo "kernel_times autograd rc=$?"
+timeout 120 python tools/bench_pooler_fwd.py > gpurun_out/pooler_fwd.json 2>/dev/null; echo "pooler fwd rc=$?"
 timeout 500 python tools/bench_ops.py --out gpurun_out/ops.md > gpurun_out/ops.log 2> gpurun_out/ops.err; echo "ops rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 450 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_launch.log 2>&1; echo "launches rc=$?"

@@ -13,12 +13,23 @@ def launches(path, out):
         u = row["Metric Unit"]
         v = v / 1000 if u in ("ns", "nsecond") else (v * 1000 if u in ("ms", "msecond") else v)
         agg.setdefault(row["Kernel Name"][:90], []).append(v)
-    tot = sum(sum(v) for v in agg.values())
-    with open(out, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write("%-92s %5s %10s %7s\n" % ("kernel", "n", "avg_us", "share"))
-        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    # kernels that only the one-off validation of the step launches (bench.validate_step: the fp32 FFMA deform-conv path the
+    # tensor-core results are compared with, torch reductions of the comparisons) and the eager end-to-end arm's torch casts
+    val_only = ("dcn_fwd_kernel(", "dcn_bwd_data_kernel(", "dcn_bwd_weight_kernel(", "reduce_kernel", "AbsFunctor", "direct_copy_kernel",
+                "bfloat16_copy_kernel", "CUDAFunctor_add<c10::BFloat16>", "MaxNanFunctor", "index_elementwise", "CompareFunctor")
+    step = collections.OrderedDict((k, v) for k, v in agg.items() if not any(t in k for t in val_only))
+
+    def table(f, rows, title):
+        tot = sum(sum(v) for v in rows.values())
+        f.write("\n## %s\n%-92s %5s %10s %7s\n" % (title, "kernel", "n", "avg_us", "share"))
+        for k, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
             f.write("%-92s %5d %10.1f %6.1f%%\n" % (k, len(v), sum(v) / len(v), 100 * sum(v) / tot))
+
+    with open(out, "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none of `python bench.py --steps 2 --warmup 1`\n"
+                "# (cold-cache, serialised launches: compare SHARES, not absolute times)\n")
+        table(f, step, "kernels of the step (device-resident graphs, per-stage graphs, end-to-end arms), validation-only kernels excluded")
+        table(f, agg, "every launch of the command, incl. the one-off validation against the fp32 FFMA path / the oracle")
     print(open(out).read())
 
 
