@@ -175,3 +175,52 @@ def test_wrappers_are_scriptable():
 
 def _nms_rotated_fn(boxes: torch.Tensor, scores: torch.Tensor, threshold: float) -> torch.Tensor:
     return torch.ops.detectron2.nms_rotated(boxes, scores, threshold)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Status codes of the round-2 entry points on invalid arguments (checked before anything is launched): negative =
+    d2b error (include/d2b200.h), what the Python host turns into RuntimeError."""
+    import ctypes as C
+
+    from detectron2_b200 import _C
+
+    lib = _C.lib()
+    EINVAL = -1
+    # Fast R-CNN candidates: too many images for one call, class-specific boxes that do not match the class count, no row table
+    rs = (C.c_int * 3)(0, 4, 8)
+    assert lib.d2b_frcnn_prepare(None, None, rs, _C.MAX_IMAGES + 1, 80, 80, None, 0.05, 16, *([None] * 8), None) == EINVAL
+    assert lib.d2b_frcnn_prepare(None, None, rs, 2, 80, 3, None, 0.05, 16, *([None] * 8), None) == EINVAL
+    assert lib.d2b_frcnn_prepare(None, None, None, 2, 80, 80, None, 0.05, 16, *([None] * 8), None) == EINVAL
+    assert lib.d2b_frcnn_prepare(None, None, rs, 0, 80, 80, None, 0.05, 16, *([None] * 8), None) == 0  # no images: nothing to do
+    # dense head: level count out of range, missing weights
+    lv = _C.DenseLevels()
+    lv.num_levels = 0
+    w = (C.c_float * 4)(1, 1, 1, 1)
+    assert lib.d2b_dense_prepare(C.byref(lv), 2, 80, w, 4.135, *([None] * 6), None) == EINVAL
+    lv.num_levels = 1
+    assert lib.d2b_dense_prepare(C.byref(lv), 2, 80, None, 4.135, *([None] * 6), None) == EINVAL
+    assert lib.d2b_dense_prepare(C.byref(lv), 0, 80, w, 4.135, *([None] * 6), None) == 0
+    # dtype codes of the half-precision variants
+    P = _C.Pyramid()
+    P.num_levels = 1
+    P.H[0], P.W[0] = 8, 8
+    dst = (C.c_void_p * 1)(None)
+    assert lib.d2b_pyramid_nchw_to_nhwc_t(C.byref(P), 1, 4, dst, 7, None) == EINVAL
+    assert lib.d2b_pyramid_nhwc_to_nchw_t(C.byref(P), 1, 4, dst, -1, None) == EINVAL
+    assert lib.d2b_roi_pooler_forward_nhwc_t(C.byref(P), 1, 4, None, 3, 7, 7, 0, 1, None, 5, None) == EINVAL
+    assert lib.d2b_roi_pooler_backward_nhwc_t(C.byref(P), 1, 4, None, 9, None, 3, 7, 7, 0, 1, None) == EINVAL
+    assert _C.DTYPE_CODE == {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def test_post_processing_dispatch_and_pyramid_struct():
+    """CPU tensors take the torch-op restatements (pinned to the real reference functions in test_host_logic_cpu.py); the ABI
+    struct carries the level_rois field of ABI v4."""
+    from detectron2_b200 import _C, dense_inference, fast_rcnn_inference
+
+    assert [n for n, _ in _C.Pyramid._fields_][-1] == "level_rois"
+    assert callable(fast_rcnn_inference.fast_rcnn_inference_fixed) and callable(dense_inference.dense_detector_inference_fixed)
+    with pytest.raises(NotImplementedError):  # the fixed-capacity forms are CUDA only
+        fast_rcnn_inference.fast_rcnn_inference_fixed([torch.zeros(2, 4)], [torch.zeros(2, 3)], [(10, 10)], 0.05, 0.5, 10)
+    with pytest.raises(NotImplementedError):
+        dense_inference.dense_detector_inference_fixed([torch.zeros(4, 4)], [torch.zeros(1, 4, 2)], [torch.zeros(1, 4, 4)], 1,
+                                                       0.05, 10, 0.5, 10)
