@@ -91,14 +91,16 @@ __device__ __forceinline__ int pick_level(const Pyr& P, const float* __restrict_
   const float area = (roi[3] - roi[1]) * (roi[4] - roi[2]);
   const float size = sqrtf(area);
   float lvl = floorf((float)P.canonical_level + log2f(size / P.canonical_box_size + 1e-8f));
-  lvl = fminf(fmaxf(lvl, (float)P.min_level), (float)P.max_level);  // NaN (negative area) -> min_level like torch.clamp? see below
-  if (!(lvl == lvl)) lvl = (float)P.min_level;
+  // A NaN level (negative or NaN area: malformed box) survives torch.clamp as NaN and matches no level in the reference's loop
+  // (poolers.py:245-263): the RoI's output stays zero and it receives no gradient.  -1 tells the kernels exactly that.
+  if (!(lvl == lvl)) return -1;
+  lvl = fminf(fmaxf(lvl, (float)P.min_level), (float)P.max_level);
   return (int)lvl - P.min_level;
 }
 
 template <bool ROT>
 __device__ __forceinline__ RoiGeom load_geom(const float* __restrict__ roi, float scale, int PH, int PW, int sr,
-                                             int aligned) {
+                                             int aligned, bool dead = false) {
   RoiGeom g;
   g.b = (int)roi[0];
   float rw, rh;
@@ -133,6 +135,7 @@ __device__ __forceinline__ RoiGeom load_geom(const float* __restrict__ roi, floa
   g.gw = sr > 0 ? sr : (int)ceilf(rw / (float)PW);
   if (g.gh < 0) g.gh = 0;
   if (g.gw < 0) g.gw = 0;
+  if (dead) g.gh = g.gw = 0;  // RoI without a level: an empty sampling grid gives zero output and no gradient
   int c = g.gh * g.gw;
   g.count_raw = (float)c;
   g.inv_count = 1.0f / (float)(c < 1 ? 1 : c);
@@ -262,10 +265,11 @@ __global__ void __launch_bounds__(kThreads) roi_align_bwd_kernel(const Pyr P, co
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * c_per_cta;
   const int cn = min(c_per_cta, C - c0);
-  const int lvl = ROT ? 0 : pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl_raw = ROT ? 0 : pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl = max(lvl_raw, 0);
   float* __restrict__ gin = P.grad[lvl];
   const int H = P.H[lvl], W = P.W[lvl];
-  const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), P.scale[lvl], PH, PW, sr, aligned);
+  const RoiGeom g = load_geom<ROT>(rois + (size_t)k * (ROT ? 6 : 5), P.scale[lvl], PH, PW, sr, aligned, lvl_raw < 0);
   if (g.gh <= 0 || g.gw <= 0) return;
   const int bins = PH * PW;
   const int total = cn * bins;
@@ -357,11 +361,12 @@ __global__ void __launch_bounds__(kV3Threads, 3) roi_align_v3_kernel(const Pyr P
 
   const int k = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl_raw = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl = max(lvl_raw, 0);
   const float* __restrict__ in = BWD ? nullptr : P.feat[lvl];
   float* __restrict__ gin = BWD ? P.grad[lvl] : nullptr;
   const int H = P.H[lvl], W = P.W[lvl];
-  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+  const RoiGeom g = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned, lvl_raw < 0);
   const int bins = PH * PW;
   const int ngroup = d2b_cdiv(C, kChW);
   const int g_begin = blockIdx.y * groups_per_cta, g_end = min(ngroup, g_begin + groups_per_cta);
@@ -919,7 +924,8 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
   const int k = blockIdx.x;
   const int c0 = blockIdx.y * kNhwcCh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl_raw = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl = max(lvl_raw, 0);
   const int H = P.H[lvl], W = P.W[lvl];
   const int bins = PH * PW;
   const int C4 = C >> 2;
@@ -931,7 +937,7 @@ __global__ void __launch_bounds__(kNhwcThreads, 4) roi_align_nhwc_kernel(const P
     s_tapov = 0;
     s_colok = 0;
     s_nymax = 0;
-    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned, lvl_raw < 0);
   }
   __syncthreads();
   const float4* __restrict__ base =
@@ -1201,7 +1207,8 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int c0 = blockIdx.y * kNhwcCh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kBwdThreads / 32;
-  const int lvl = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl_raw = pick_level(P, (P.level_rois ? P.level_rois : rois) + (size_t)k * 5);
+  const int lvl = max(lvl_raw, 0);
   const int H = P.H[lvl], W = P.W[lvl];
   const int bins = PH * PW;
   // bin rows [ph0, ph0 + PHl) of the RoI: a 14x14 mask-head tile (157 KB of shared memory, one CTA per SM) is split over
@@ -1210,7 +1217,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_align_bwd_nhwc_kernel(const P
   const int ncta = min(kNhwcCh, C - c0);
   const bool lane_live = lane * 4 < ncta;
   if (tid == 0) {
-    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned);
+    sg = load_geom<false>(rois + (size_t)k * 5, P.scale[lvl], PH, PW, sr, aligned, lvl_raw < 0);
     s_xmin = s_ymin = 1 << 30;
     s_xmax = s_ymax = -1;
     s_wide = 0;

@@ -755,15 +755,20 @@ def test_roi_pooler_backward_layouts_vs_oracle(layout, monkeypatch):
     per_img[0][0] = torch.tensor([50.0, 60.0, 50.0, 60.0])        # empty box: no samples
     per_img[1][0] = torch.tensor([-300.0, -200.0, 1700.0, 1000.0])  # larger than the image
     per_img[1][1] = torch.tensor([200.0, 300.0, 203.0, 302.0])      # bins much smaller than a pixel
+    # negative area: the level is NaN, no level matches in the reference's loop (poolers.py:245-263) -> zero output, no gradient
+    per_img[0][1] = torch.tensor([300.0, 100.0, 120.0, 260.0])
     rois = torch.cat([torch.cat([torch.full((90, 1), float(i)), b], 1) for i, b in enumerate(per_img)])
     for out in (7, 14):
-        _, lv = _oracle_pooler([f[:, :1] for f in feats], rois, scales, out, 0, True)
+        yref, lv = _oracle_pooler([f[:, :8] for f in feats], rois, scales, out, 0, True)
+        assert not (lv[1] >= 0 and lv[1] < 4) and (yref[1] == 0).all()
         if layout == "cl":
             fg = [f.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
         else:
             monkeypatch.setattr(ops, "POOLER_LAYOUT", layout)
             fg = [f.to(DEV).requires_grad_(True) for f in feats]
         y = ROIPooler(out, scales, 0, "ROIAlignV2")(fg, [b.to(DEV) for b in per_img])
+        ok, err = rel_close(y[:, :8], yref, rtol=1e-4, atol=5e-5)
+        assert ok and (y[1] == 0).all(), (layout, out, err)
         go = torch.randn(y.shape, generator=g)
         y.backward(go.to(DEV))
         for l, sc in enumerate(scales):
