@@ -95,6 +95,7 @@ def _declare(lib):
         "d2b_deform_conv_fused_backward": (i, [f32p, f32p, f32p, f32p, i, f32p, f32p, C.POINTER(DcnParams), i, i, vp, f32p,
                                                f32p, f32p, vp, sz, vp]),
         "d2b_paste_masks": (i, [f32p, f32p, i, i, i, i, f, u8p, vp]),
+        "d2b_paste_masks_packed": (i, [f32p, f32p, i, i, i, i, f, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == symbol missing from the .so

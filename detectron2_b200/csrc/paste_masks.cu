@@ -10,6 +10,8 @@
 //   g  = ((p + 0.5 - b0) / (b1 - b0)) * 2 - 1          (mask_ops.py:53-54)
 //   i  = ((g + 1) * M - 1) / 2                           (grid_sample, align_corners=False)
 //   v  = nw*w_nw + ne*w_ne + sw*w_sw + se*w_se           (zeros padding)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -274,7 +276,58 @@ __global__ void __launch_bounds__(kThreads) paste_masks_kernel(const float* __re
   }
 }
 
+// Bit-packed boolean output: one thread per 32-bit word = 32 pixels of a row (bit b of word w of row y = pixel (y, 32 w + b)),
+// rows padded to whole words.  Same rectangle shortcut, same sample_coord / paste_value expressions as the byte kernel, so the
+// unpacked result is identical; 13 MB instead of 107 MB for 100 masks on an 800 x 1333 image -- what matters when the masks
+// leave the device (the inference post-processing's D2H copy, mask_ops.py:144-147 / postprocessing.py:61-66).
+__global__ void __launch_bounds__(kThreads) paste_masks_packed_kernel(const float* __restrict__ masks,
+                                                                      const float* __restrict__ boxes, int M, int H, int W,
+                                                                      int Ww, float threshold, uint32_t* __restrict__ out) {
+  __shared__ float smask[kMaxM * kMaxM];
+  const int n = blockIdx.y;
+  const float* __restrict__ mk = masks + (size_t)n * M * M;
+  for (int i = threadIdx.x; i < M * M; i += kThreads) smask[i] = mk[i];
+  const float x0 = boxes[4 * n], y0 = boxes[4 * n + 1], x1 = boxes[4 * n + 2], y1 = boxes[4 * n + 3];
+  __syncthreads();
+  const float fM = (float)M;
+  const PasteRect rect = paste_rect(x0, y0, x1, y1, fM, H, W);
+  const bool empty = rect.cx1 < rect.cx0 || rect.ry1 < rect.ry0;
+  const uint32_t zbit = (0.f >= threshold) ? 1u : 0u;  // value of a pixel that cannot see the mask
+  const long long words = (long long)H * Ww;
+  uint32_t* __restrict__ obase = out + (size_t)n * words;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < words; idx += (long long)gridDim.x * kThreads) {
+    const int y = (int)(idx / Ww), w = (int)(idx - (long long)y * Ww);
+    const int px0 = 32 * w;
+    const int nvalid = min(32, W - px0);
+    const uint32_t valid = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    uint32_t word;
+    if (empty || y < rect.ry0 || y > rect.ry1 || px0 + 31 < rect.cx0 || px0 > rect.cx1) {
+      word = zbit ? valid : 0u;
+    } else {
+      const float iy = sample_coord((float)y, y0, y1, fM);
+      word = 0u;
+      for (int b = 0; b < nvalid; ++b)
+        word |= paste_value(smask, M, fM, sample_coord((float)(px0 + b), x0, x1, fM), iy, threshold) << b;
+    }
+    obase[idx] = word;
+  }
+}
+
 }  // namespace
+
+D2B_API int d2b_paste_masks_packed(const float* masks, const float* boxes, int N, int M, int H, int W, float threshold,
+                                   uint32_t* out, void* stream) {
+  if (N == 0 || H == 0 || W == 0) return D2B_OK;
+  if (!masks || !boxes || !out || N < 0 || M <= 0 || H < 0 || W < 0 || !(threshold >= 0.f)) return D2B_EINVAL;
+  if (M > kMaxM || N > 65535) return D2B_EUNSUPPORTED;
+  const int Ww = d2b_cdiv(W, 32);
+  const long long words = (long long)H * Ww;
+  if ((long long)H * W >= (1LL << 30)) return D2B_EUNSUPPORTED;
+  int gx = (int)std::min<long long>(d2b_cdiv(words, kThreads), std::max<long long>(1, d2b_cdiv(16LL * kNumSMs, N)));
+  paste_masks_packed_kernel<<<dim3(gx, N), kThreads, 0, (cudaStream_t)stream>>>(masks, boxes, M, H, W, Ww, threshold, out);
+  D2B_CHECK_LAUNCH();
+  return D2B_OK;
+}
 
 D2B_API int d2b_paste_masks(const float* masks, const float* boxes, int N, int M, int H, int W, float threshold,
                             uint8_t* out, void* stream) {

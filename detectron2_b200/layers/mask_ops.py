@@ -5,7 +5,7 @@ import torch
 
 from .. import ops  # noqa: F401  (registers torch.ops.d2b200.*)
 
-__all__ = ["paste_masks_in_image"]
+__all__ = ["paste_masks_in_image", "paste_masks_in_image_packed", "unpack_mask_bits"]
 
 
 @torch.jit.script_if_tracing
@@ -24,3 +24,28 @@ def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape: 
     if masks.dim() == 4:  # (N, 1, M, M) as produced upstream
         masks = masks[:, 0]
     return torch.ops.d2b200.paste_masks(masks, boxes, img_h, img_w, float(threshold))
+
+
+def paste_masks_in_image_packed(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5):
+    """`paste_masks_in_image` with the boolean result bit-packed on the device: int32 (N, H, ceil(W / 32)), bit b of word w of
+    row y = pixel (y, 32 w + b).  Same decisions as the byte form, 1 / 8 of the bytes to copy to the host (the consumer of the
+    pasted masks -- RLE encoding for COCO evaluation, postprocessing.py:61-66 -- runs there); `unpack_mask_bits` restores the
+    (N, H, W) bool tensor on either side."""
+    assert masks.shape[-1] == masks.shape[-2], "Only square mask predictions are supported"
+    n = len(masks)
+    img_h, img_w = int(image_shape[0]), int(image_shape[1])
+    if n == 0:
+        return masks.new_empty((0, img_h, (img_w + 31) // 32), dtype=torch.int32)
+    if not isinstance(boxes, torch.Tensor):
+        boxes = boxes.tensor
+    assert len(boxes) == n, boxes.shape
+    if masks.dim() == 4:
+        masks = masks[:, 0]
+    return torch.ops.d2b200.paste_masks_packed(masks, boxes, img_h, img_w, float(threshold))
+
+
+def unpack_mask_bits(packed: torch.Tensor, width: int) -> torch.Tensor:
+    """(N, H, ceil(W / 32)) int32 words -> (N, H, W) bool (plain torch ops: works on CPU tensors after the copy)."""
+    shifts = torch.arange(32, device=packed.device, dtype=torch.int32)
+    bits = (packed.unsqueeze(-1) >> shifts) & 1
+    return bits.reshape(packed.shape[0], packed.shape[1], -1)[..., :width].to(torch.bool)

@@ -918,6 +918,27 @@ def _(masks, boxes, img_h, img_w, threshold):
     return masks.new_empty((masks.shape[0], img_h, img_w), dtype=torch.bool if threshold >= 0 else torch.uint8)
 
 
+@torch.library.custom_op("d2b200::paste_masks_packed", mutates_args=(), device_types="cuda")
+def paste_masks_packed_op(masks: Tensor, boxes: Tensor, img_h: int, img_w: int, threshold: float) -> Tensor:
+    """Bit-packed boolean paste: int32 [N, H, ceil(W / 32)], bit b of word w of row y = pixel (y, 32 w + b)."""
+    _C.require_cuda(masks, boxes)
+    if not threshold >= 0:
+        raise RuntimeError("paste_masks_packed: boolean output only (threshold >= 0)")
+    mk, bx = _f32c(masks), _f32c(boxes)
+    n, m = mk.shape[0], mk.shape[-1]
+    out = torch.empty((n, img_h, (img_w + 31) // 32), dtype=torch.int32, device=mk.device)
+    if out.numel():
+        with torch.cuda.device(mk.device):
+            check(_C.lib().d2b_paste_masks_packed(ptr(mk), ptr(bx), n, m, img_h, img_w, threshold, ptr(out),
+                                                  stream_ptr(mk.device)), "paste_masks_packed")
+    return out
+
+
+@paste_masks_packed_op.register_fake
+def _(masks, boxes, img_h, img_w, threshold):
+    return masks.new_empty((masks.shape[0], img_h, (img_w + 31) // 32), dtype=torch.int32)
+
+
 # =================================================================================== detectron2::* dispatcher ops
 def _d2_nms_rotated(dets: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
     return nms_op(dets, scores, None, iou_threshold, True)

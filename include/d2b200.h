@@ -311,6 +311,11 @@ int d2b_deform_conv_fused_backward(const float* x, const float* offset_mask, con
  * threshold >= 0, else (uint8)(v*255). */
 int d2b_paste_masks(const float* masks, const float* boxes, int N, int M, int H, int W,
                     float threshold, uint8_t* out, void* stream);
+/* The boolean result (threshold >= 0 only) bit-packed: out [N,H,ceil(W/32)] uint32, bit b of word w of row y = pixel
+ * (y, 32 w + b), unused bits of a row's last word zero.  Identical decisions to d2b_paste_masks; 1/8 of the bytes for the
+ * device -> host copy that follows the paste in inference post-processing. */
+int d2b_paste_masks_packed(const float* masks, const float* boxes, int N, int M, int H, int W,
+                           float threshold, uint32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -210,6 +210,9 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.d2b_roi_pooler_forward_nhwc_t(C.byref(P), 1, 4, None, 3, 7, 7, 0, 1, None, 5, None) == EINVAL
     assert lib.d2b_roi_pooler_backward_nhwc_t(C.byref(P), 1, 4, None, 9, None, 3, 7, 7, 0, 1, None) == EINVAL
     assert _C.DTYPE_CODE == {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+    # bit-packed paste: boolean output only
+    assert lib.d2b_paste_masks_packed(None, None, 3, 28, 10, 10, -1.0, None, None) == EINVAL
+    assert lib.d2b_paste_masks_packed(None, None, 0, 28, 10, 10, 0.5, None, None) == 0
 
 
 def test_post_processing_dispatch_and_pyramid_struct():

@@ -510,6 +510,29 @@ def test_paste_masks_many_masks_uniform_grid_vs_oracle(L):
     assert torch.equal(out.cpu(), orc.paste_masks(masks, boxes, (h, w), 0.5))
 
 
+@pytest.mark.parametrize("h,w,thr", [(800, 1333, 0.5), (37, 129, 0.5), (5, 7, 0.3), (64, 64, 0.0), (3, 33, 0.5)])
+def test_paste_masks_bit_packed_equals_byte_form(L, h, w, thr):
+    """d2b_paste_masks_packed: same decisions as the byte kernel (itself byte-exact vs the oracle), 32 pixels per word."""
+    g = torch.Generator().manual_seed(h + w)
+    n = 100 if h == 800 else 9
+    masks = torch.rand(n, 28, 28, generator=g)
+    ctr = torch.rand(n, 2, generator=g) * torch.tensor([float(w), float(h)])
+    wh = 2 + torch.rand(n, 2, generator=g) * torch.tensor([w * 0.6, h * 0.6])
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    boxes[0] = torch.tensor([-10.0, -10.0, w + 10.0, h + 10.0])   # larger than the image
+    boxes[1] = torch.tensor([3.0, 2.0, 3.0, 2.0])                 # degenerate
+    ref = L.paste_masks_in_image(masks.to(DEV), boxes.to(DEV), (h, w), thr)
+    packed = L.paste_masks_in_image_packed(masks.to(DEV), boxes.to(DEV), (h, w), thr)
+    assert packed.shape == (n, h, (w + 31) // 32) and packed.dtype == torch.int32
+    assert torch.equal(L.unpack_mask_bits(packed, w), ref)
+    assert torch.equal(L.unpack_mask_bits(packed.cpu(), w), ref.cpu())       # unpacking after the (8x smaller) copy
+    if w % 32:
+        tail = L.unpack_mask_bits(packed, ((w + 31) // 32) * 32)[..., w:]
+        assert not tail.any()                                                 # unused bits of a row's last word are zero
+    with pytest.raises(RuntimeError):
+        L.paste_masks_in_image_packed(masks.to(DEV), boxes.to(DEV), (h, w), -1.0)
+
+
 def test_paste_masks_full_size_vs_oracle(L):
     # config 2: 100 masks, 800x1333 image; oracle on a 12-mask subset (seconds), all 100 via a checksum property
     g = torch.Generator().manual_seed(42)
