@@ -227,3 +227,17 @@ def test_post_processing_dispatch_and_pyramid_struct():
     with pytest.raises(NotImplementedError):
         dense_inference.dense_detector_inference_fixed([torch.zeros(4, 4)], [torch.zeros(1, 4, 2)], [torch.zeros(1, 4, 4)], 1,
                                                        0.05, 10, 0.5, 10)
+
+
+def test_unpack_mask_bits_host_side():
+    """The receiving side of the bit-packed paste: plain torch ops, CPU tensors (bit b of word w = pixel 32 w + b)."""
+    import detectron2_b200.layers as L
+
+    g = torch.Generator().manual_seed(0)
+    ref = torch.rand(3, 5, 70, generator=g) > 0.5
+    words = torch.zeros(3, 5, 3, dtype=torch.int64)
+    for x in range(70):
+        words[..., x // 32] |= ref[..., x].to(torch.int64) << (x % 32)
+    packed = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)  # two's-complement int32 words
+    assert torch.equal(L.unpack_mask_bits(packed, 70), ref)
+    assert L.paste_masks_in_image_packed(torch.zeros(0, 28, 28), torch.zeros(0, 4), (10, 40)).shape == (0, 10, 2)
