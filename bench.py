@@ -726,16 +726,19 @@ def main():
         # device-event time; the host clock guards against stream-order artefacts
         return max(e0.elapsed_time(e1), ms_host), steps, nbytes_of(hosts[0]), check
 
-    e2e_graphed = True
-    try:
-        e2e_ms, e2e_steps, e2e_bytes, chk_half = e2e_measure("bf16", True)
-        e2e32_ms, e2e32_steps, e2e32_bytes, chk_full = e2e_measure("fp32", True)
-    except Exception as exc:  # never lose the bench line to a capture problem: fall back to eager launches and say so
-        sys.stderr.write("graphed end-to-end step failed (%s: %s); measuring eagerly\n" % (type(exc).__name__, exc))
-        torch.cuda.synchronize()
-        e2e_graphed = False
-        e2e_ms, e2e_steps, e2e_bytes, chk_half = e2e_measure("bf16", False)
-        e2e32_ms, e2e32_steps, e2e32_bytes, chk_full = e2e_measure("fp32", False)
+    def e2e_measure_graphed(transport):
+        """Graph replay of the public-API step; if the capture fails, the same measurement with eager launches (never lose the
+        bench line to a capture problem).  A failed capture raises before the measurement's first barrier, so every rank runs
+        the same number of barriers whichever way it goes."""
+        try:
+            return e2e_measure(transport, True) + (True,)
+        except Exception as exc:
+            sys.stderr.write("graphed end-to-end step (%s) failed (%s: %s); measuring eagerly\n" % (transport, type(exc).__name__, exc))
+            torch.cuda.synchronize()
+            return e2e_measure(transport, False) + (False,)
+
+    e2e_ms, e2e_steps, e2e_bytes, chk_half, e2e_graphed = e2e_measure_graphed("bf16")
+    e2e32_ms, e2e32_steps, e2e32_bytes, chk_full, _ = e2e_measure_graphed("fp32")
     e2e_eager_ms, e2e_eager_steps, _, chk_eager = e2e_measure("fp32", False)
     assert torch.allclose(chk_eager, chk_full, rtol=1e-3, atol=1e-3 * chk_full.abs().max().item()), "graphed step differs from eager"
     # the two transports run the same step: their result vectors (gradient checksums of slot 1) agree to bf16 rounding
