@@ -241,3 +241,19 @@ def test_unpack_mask_bits_host_side():
     packed = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)  # two's-complement int32 words
     assert torch.equal(L.unpack_mask_bits(packed, 70), ref)
     assert L.paste_masks_in_image_packed(torch.zeros(0, 28, 28), torch.zeros(0, 4), (10, 40)).shape == (0, 10, 2)
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every prototype of include/d2b200.h against the ctypes binding: same number of parameters (a missing / extra argument in
+    the binding would shift every following pointer)."""
+    from detectron2_b200 import _C
+
+    _C.lib()
+    header = open(os.path.join(ROOT, "include", "d2b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(d2b_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_C.EXPORTED[name][1]) == n, (name, n, len(_C.EXPORTED[name][1]))
