@@ -175,3 +175,28 @@ def test_detector_postprocess_and_crop_host_logic(golden, monkeypatch):
     nomask = pp.detector_postprocess(det, oh, ow)
     assert nomask.pred_masks is None and torch.equal(nomask.pred_boxes, T(d["out_boxes"]))
     check_crops(d, pp.crop_and_resize(T(d["bit_masks"]), T(d["crop_boxes"]), int(d["mask_size"])))
+
+
+def test_batched_nms_of_several_images_host_logic(cpu_nms):
+    """`layers.batched_nms_images_fixed`: the category / per-image-offset construction around the one NMS call, against
+    torchvision's own batched_nms run per image (the reference's loop, proposal_utils.py:96-133) on CPU."""
+    import torchvision
+
+    import detectron2_b200.layers as L
+
+    g = torch.Generator().manual_seed(2)
+    n, m = 3, 700
+    boxes, scores = [], []
+    for i in range(n):
+        ctr = torch.rand(m, 2, generator=g) * torch.tensor([900.0 * (1 + i), 600.0])  # a different max coordinate per image
+        wh = 8 + torch.rand(m, 2, generator=g) * 150
+        boxes.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+        scores.append((torch.rand(m, generator=g) * 128).round() / 128)
+    idxs = torch.randint(0, 5, (m,), generator=g)
+    keep, num = L.batched_nms_images_fixed(boxes, scores, idxs, 0.7, 5, max_segment=m)
+    kept = keep[: int(num)]
+    for i in range(n):
+        mine = kept[(kept >= i * m) & (kept < (i + 1) * m)] - i * m
+        ref = torchvision.ops.boxes.batched_nms(boxes[i], scores[i], idxs, 0.7)  # CPU: coordinate trick below 4 000 elements
+        assert sorted(mine.tolist()) == sorted(ref.tolist()), i
+        assert torch.equal(mine, orc.batched_nms(boxes[i], scores[i], idxs, 0.7)), i  # order: score desc, lower index first on ties
